@@ -1,0 +1,82 @@
+"""Import the *real* reference modules from /root/reference (only possible in the build
+container; the GPU box has no /root/reference).  TEST INFRASTRUCTURE ONLY.
+
+The reference imports ``nimblephysics`` (C++/pybind, ~=0.10.20, not installed, not vendored)
+at ``src/data/AddBiomechanicsDataset.py:1`` and ``matplotlib`` at
+``src/loss/RegressionLossEvaluator.py:6``.  Neither is needed by the hot path, so both are
+replaced by empty stub modules before import (SURVEY §8c recipe).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("IBM_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "models"))
+
+
+def _install_stubs() -> None:
+    if "nimblephysics" not in sys.modules:
+        nimble = types.ModuleType("nimblephysics")
+        for sub, attrs in {
+            "biomechanics": ["SubjectOnDisk", "FrameList", "FramePass", "Frame", "MissingGRFReason"],
+            "dynamics": ["Skeleton", "BodyNode"],
+            "math": [],
+        }.items():
+            m = types.ModuleType(f"nimblephysics.{sub}")
+            for a in attrs:
+                setattr(m, a, type(a, (), {}))
+            setattr(nimble, sub, m)
+            sys.modules[f"nimblephysics.{sub}"] = m
+        sys.modules["nimblephysics"] = nimble
+    try:
+        import matplotlib.pyplot  # noqa: F401
+    except Exception:
+        mpl = types.ModuleType("matplotlib")
+        plt = types.ModuleType("matplotlib.pyplot")
+        mpl.pyplot = plt
+        sys.modules["matplotlib"] = mpl
+        sys.modules["matplotlib.pyplot"] = plt
+    try:
+        import wandb  # noqa: F401
+    except Exception:
+        w = types.ModuleType("wandb")
+        w.log = lambda *a, **k: None
+        sys.modules["wandb"] = w
+
+
+_cache = {}
+
+
+def load_reference():
+    """Returns a namespace with the reference classes.  Raises RuntimeError if absent."""
+    if "ns" in _cache:
+        return _cache["ns"]
+    if not reference_available():
+        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    _install_stubs()
+    src = os.path.join(REFERENCE_ROOT, "src")
+    for p in (src, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import io
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        from data.AddBiomechanicsDataset import InputDataKeys, OutputDataKeys
+        from models.FeedForwardRegressionBaseline import FeedForwardBaseline
+        from models.Groundlink import Groundlink
+        from models.TransformerBaseline import (TransformerLayer, TemporalEmbedding,
+                                                SimpleAttention, TransformerBaseline)
+        from loss.RegressionLossEvaluator import RegressionLossEvaluator
+    ns = types.SimpleNamespace(
+        InputDataKeys=InputDataKeys, OutputDataKeys=OutputDataKeys,
+        FeedForwardBaseline=FeedForwardBaseline, Groundlink=Groundlink,
+        TransformerLayer=TransformerLayer, TemporalEmbedding=TemporalEmbedding,
+        SimpleAttention=SimpleAttention, TransformerBaseline=TransformerBaseline,
+        RegressionLossEvaluator=RegressionLossEvaluator)
+    _cache["ns"] = ns
+    return ns
