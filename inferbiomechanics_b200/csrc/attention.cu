@@ -1,0 +1,387 @@
+// Whole-sequence softmax attention per (window, head), forward and backward.
+//
+// Replaces nn.MultiheadAttention's scaled-dot-product core at
+//   /root/reference/src/models/TransformerBaseline.py:12-13,29 (3 heads x 36 at d=108, fp64 in the
+//   reference) and SimpleAttention (…:51-70, unscaled, value dim 3), and serves the builder-owned
+//   denoiser (8 heads x 64).  Sequences are short (T = 50 … 200 frames) so K and V of one
+//   (window, head) live entirely in shared memory and the T x T score matrix never leaves
+//   registers; long streams scale by sharding windows, not the sequence.
+//
+// The projections around it are tcgen05 GEMMs (gemm_sm100.cu).  The score/PV products here are
+// <2 % of the layer FLOPs at these sizes and use warp-level mma.sync.m16n8k16 (bf16 in, fp32
+// accumulate) with an online softmax; one CTA = 4 warps = 64 query rows.
+#include "common.cuh"
+
+namespace ibm {
+namespace attn {
+
+constexpr int kThreads = 128;
+constexpr int kPad = 8;             // bf16 elements of row padding → conflict-free fragment loads
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// B fragment (16 k x 8 n) from a row-major [k][n] tile: lanes 0-15 pass &X[k0 + lane][n0]
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+// A fragment (16 m x 16 k) of Y^T from a row-major Y[k][m] tile
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+// cooperative tile load: rows [r0, r0+nrows) x W columns (W % 8 == 0) into smem with row stride LDS;
+// rows >= r_valid are zero-filled.
+template <int W, int LDS>
+__device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t ld, int nrows, int r_valid) {
+  constexpr int CPR = W / 8;
+  for (int i = threadIdx.x; i < nrows * CPR; i += kThreads) {
+    const int r = i / CPR, c = (i - r * CPR) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < r_valid) v = *reinterpret_cast<const uint4*>(src + (int64_t)r * ld + c);
+    *reinterpret_cast<uint4*>(dst + r * LDS + c) = v;
+  }
+}
+
+// ---------------------------------------- forward ----------------------------------------------
+template <int HQ, int HV>
+__global__ void __launch_bounds__(kThreads)
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
+                const __nv_bfloat16* __restrict__ v, int64_t ldv, __nv_bfloat16* __restrict__ o, int64_t ldo, int T,
+                int H, int q_tiles, float scale_log2) {
+  constexpr int LK = HQ + kPad, LV = HV + kPad;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int Tpad = (T + 63) & ~63;
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* Vs = Ks + Tpad * LK;
+
+  const int qt = blockIdx.x % q_tiles;
+  const int wh = blockIdx.x / q_tiles;
+  const int h = wh % H;
+  const int64_t win = wh / H;
+  const int64_t row0 = win * T;
+  load_tile<HQ, LK>(Ks, k + row0 * ldk + h * HQ, ldk, Tpad, T);
+  load_tile<HV, LV>(Vs, v + row0 * ldv + h * HV, ldv, Tpad, T);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int qr = qt * 64 + warp * 16 + g;            // this thread's rows: qr and qr + 8
+  // Q fragments straight from global (each element read exactly once per CTA)
+  uint32_t qa[HQ / 16][4];
+  {
+    const __nv_bfloat16* q0 = q + (row0 + qr) * ldq + h * HQ;
+    const __nv_bfloat16* q1 = q0 + 8 * ldq;
+#pragma unroll
+    for (int kk = 0; kk < HQ / 16; ++kk) {
+      qa[kk][0] = qr < T ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 2 * t) : 0u;
+      qa[kk][1] = qr + 8 < T ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 2 * t) : 0u;
+      qa[kk][2] = qr < T ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 8 + 2 * t) : 0u;
+      qa[kk][3] = qr + 8 < T ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 8 + 2 * t) : 0u;
+    }
+  }
+  __syncthreads();
+
+  float oacc[HV / 8][4];
+#pragma unroll
+  for (int j = 0; j < HV / 8; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int kb = 0; kb < Tpad; kb += 64) {
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < HQ / 16; ++kk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat16* kp = Ks + (kb + j * 8 + g) * LK + kk * 16 + 2 * t;
+        mma16816(s[j], qa[kk], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+      }
+    }
+    // scale into log2 domain, mask keys >= T, running max
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = kb + j * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = key + (e & 1) < T;
+        s[j][e] = ok ? s[j][e] * scale_log2 : -INFINITY;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float corr0 = exp2f(m0 - mx0), corr1 = exp2f(m1 - mx1);     // m = -inf on first block → 0
+    m0 = mx0; m1 = mx1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f(s[j][0] - m0); s[j][1] = exp2f(s[j][1] - m0);
+      s[j][2] = exp2f(s[j][2] - m1); s[j][3] = exp2f(s[j][3] - m1);
+      rs0 += s[j][0] + s[j][1];
+      rs1 += s[j][2] + s[j][3];
+    }
+    l0 = l0 * corr0 + rs0;
+    l1 = l1 * corr1 + rs1;
+#pragma unroll
+    for (int j = 0; j < HV / 8; ++j) { oacc[j][0] *= corr0; oacc[j][1] *= corr0; oacc[j][2] *= corr1; oacc[j][3] *= corr1; }
+    // O += P V   (P from the score accumulators: C-fragment layout == A-fragment layout)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int j = 0; j < HV / 8; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, Vs + (kb + kk * 16 + (lane & 15)) * LV + j * 8);
+        mma16816(oacc[j], pa, b0, b1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  __nv_bfloat16* o0 = o + (row0 + qr) * ldo + h * HV + 2 * t;
+  __nv_bfloat16* o1 = o0 + 8 * ldo;
+#pragma unroll
+  for (int j = 0; j < HV / 8; ++j) {
+    if (qr < T) *reinterpret_cast<uint32_t*>(o0 + j * 8) = pack_bf16x2(oacc[j][0] * inv0, oacc[j][1] * inv0);
+    if (qr + 8 < T) *reinterpret_cast<uint32_t*>(o1 + j * 8) = pack_bf16x2(oacc[j][2] * inv1, oacc[j][3] * inv1);
+  }
+}
+
+// ---------------------------------------- backward (T <= 64) -----------------------------------
+// dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(P o dP)), dQ = scale dS K, dK = scale dS^T Q.
+template <int HD>
+__global__ void __launch_bounds__(kThreads)
+attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_off, const __nv_bfloat16* __restrict__ dout,
+                int64_t ldo, __nv_bfloat16* __restrict__ dqkv, int T, int H, float scale) {
+  constexpr int LD = HD + kPad;       // operand tiles [64][LD]
+  constexpr int LP = 64 + kPad;       // P / dS tiles  [64][LP]
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* Ks = Qs + 64 * LD;
+  __nv_bfloat16* Vs = Ks + 64 * LD;
+  __nv_bfloat16* dOs = Vs + 64 * LD;
+  __nv_bfloat16* Ps = dOs + 64 * LD;
+  __nv_bfloat16* dSs = Ps + 64 * LP;
+
+  const int h = blockIdx.x % H;
+  const int64_t win = blockIdx.x / H;
+  const int64_t row0 = win * T;
+  const __nv_bfloat16* base = qkv + row0 * ld + h * HD;
+  load_tile<HD, LD>(Qs, base, ld, 64, T);
+  load_tile<HD, LD>(Ks, base + kv_off, ld, 64, T);
+  load_tile<HD, LD>(Vs, base + 2 * kv_off, ld, 64, T);
+  load_tile<HD, LD>(dOs, dout + row0 * ldo + h * HD, ldo, 64, T);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = warp * 16 + g;                      // rows r0, r0+8 (queries in phase 1, keys in phase 2)
+  const float scale_log2 = scale * 1.4426950408889634f;
+
+  // ---- phase 1: this warp owns 16 query rows ----
+  float s[8][4], dp[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < HD / 16; ++kk) {
+    uint32_t qa[4], da[4];
+    const __nv_bfloat16* qp = Qs + r0 * LD + kk * 16 + 2 * t;
+    const __nv_bfloat16* dpp = dOs + r0 * LD + kk * 16 + 2 * t;
+    qa[0] = *reinterpret_cast<const uint32_t*>(qp);          qa[1] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD);
+    qa[2] = *reinterpret_cast<const uint32_t*>(qp + 8);      qa[3] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD + 8);
+    da[0] = *reinterpret_cast<const uint32_t*>(dpp);         da[1] = *reinterpret_cast<const uint32_t*>(dpp + 8 * LD);
+    da[2] = *reinterpret_cast<const uint32_t*>(dpp + 8);     da[3] = *reinterpret_cast<const uint32_t*>(dpp + 8 * LD + 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat16* kp = Ks + (j * 8 + g) * LD + kk * 16 + 2 * t;
+      const __nv_bfloat16* vp = Vs + (j * 8 + g) * LD + kk * 16 + 2 * t;
+      mma16816(s[j], qa, *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+      mma16816(dp[j], da, *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
+    }
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int key = j * 8 + 2 * t;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[j][e] = (key + (e & 1) < T) ? s[j][e] * scale_log2 : -INFINITY;
+    mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j][0] = exp2f(s[j][0] - mx0); s[j][1] = exp2f(s[j][1] - mx0);
+    s[j][2] = exp2f(s[j][2] - mx1); s[j][3] = exp2f(s[j][3] - mx1);
+    l0 += s[j][0] + s[j][1];
+    l1 += s[j][2] + s[j][3];
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j][0] *= inv0; s[j][1] *= inv0; s[j][2] *= inv1; s[j][3] *= inv1;      // P
+    d0 += s[j][0] * dp[j][0] + s[j][1] * dp[j][1];
+    d1 += s[j][2] * dp[j][2] + s[j][3] * dp[j][3];
+  }
+  d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+  d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+  uint32_t dsa[4][4];                                  // scale*dS as A fragments for dQ = dS K
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float e0 = scale * s[j][0] * (dp[j][0] - d0), e1 = scale * s[j][1] * (dp[j][1] - d0);
+    const float e2 = scale * s[j][2] * (dp[j][2] - d1), e3 = scale * s[j][3] * (dp[j][3] - d1);
+    const uint32_t p01 = pack_bf16x2(s[j][0], s[j][1]), p23 = pack_bf16x2(s[j][2], s[j][3]);
+    const uint32_t s01 = pack_bf16x2(e0, e1), s23 = pack_bf16x2(e2, e3);
+    *reinterpret_cast<uint32_t*>(Ps + r0 * LP + j * 8 + 2 * t) = p01;
+    *reinterpret_cast<uint32_t*>(Ps + (r0 + 8) * LP + j * 8 + 2 * t) = p23;
+    *reinterpret_cast<uint32_t*>(dSs + r0 * LP + j * 8 + 2 * t) = s01;
+    *reinterpret_cast<uint32_t*>(dSs + (r0 + 8) * LP + j * 8 + 2 * t) = s23;
+    dsa[j >> 1][(j & 1) * 2] = s01;
+    dsa[j >> 1][(j & 1) * 2 + 1] = s23;
+  }
+  {
+    float dq[HD / 8][4];
+#pragma unroll
+    for (int j = 0; j < HD / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int j = 0; j < HD / 8; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, Ks + (kk * 16 + (lane & 15)) * LD + j * 8);
+        mma16816(dq[j], dsa[kk], b0, b1);
+      }
+    }
+    __nv_bfloat16* g0 = dqkv + (row0 + r0) * ld + h * HD + 2 * t;
+    __nv_bfloat16* g1 = g0 + 8 * ld;
+#pragma unroll
+    for (int j = 0; j < HD / 8; ++j) {
+      if (r0 < T) *reinterpret_cast<uint32_t*>(g0 + j * 8) = pack_bf16x2(dq[j][0], dq[j][1]);
+      if (r0 + 8 < T) *reinterpret_cast<uint32_t*>(g1 + j * 8) = pack_bf16x2(dq[j][2], dq[j][3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: this warp owns 16 key rows: dV = P^T dO, dK = (scale dS)^T Q ----
+  {
+    float dv[HD / 8][4], dk[HD / 8][4];
+#pragma unroll
+    for (int j = 0; j < HD / 8; ++j) { dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f; dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f; }
+    const int kr = warp * 16;
+    // x4.trans address pattern: matrices (q-rows 0-7 | keys 0-7), (q 0-7 | keys 8-15), (q 8-15 | keys 0-7), (q 8-15 | keys 8-15)
+    const int qoff = (lane & 7) + ((lane >> 4) << 3);
+    const int koff = ((lane >> 3) & 1) << 3;
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {
+      uint32_t pa[4], sa[4];
+      ldsm_x4_trans(pa, Ps + (kq * 16 + qoff) * LP + kr + koff);
+      ldsm_x4_trans(sa, dSs + (kq * 16 + qoff) * LP + kr + koff);
+#pragma unroll
+      for (int j = 0; j < HD / 8; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, dOs + (kq * 16 + (lane & 15)) * LD + j * 8);
+        mma16816(dv[j], pa, b0, b1);
+        ldsm_x2_trans(b0, b1, Qs + (kq * 16 + (lane & 15)) * LD + j * 8);
+        mma16816(dk[j], sa, b0, b1);
+      }
+    }
+    __nv_bfloat16* gk0 = dqkv + (row0 + r0) * ld + kv_off + h * HD + 2 * t;
+    __nv_bfloat16* gv0 = gk0 + kv_off;
+#pragma unroll
+    for (int j = 0; j < HD / 8; ++j) {
+      if (r0 < T) {
+        *reinterpret_cast<uint32_t*>(gk0 + j * 8) = pack_bf16x2(dk[j][0], dk[j][1]);
+        *reinterpret_cast<uint32_t*>(gv0 + j * 8) = pack_bf16x2(dv[j][0], dv[j][1]);
+      }
+      if (r0 + 8 < T) {
+        *reinterpret_cast<uint32_t*>(gk0 + 8 * ld + j * 8) = pack_bf16x2(dk[j][2], dk[j][3]);
+        *reinterpret_cast<uint32_t*>(gv0 + 8 * ld + j * 8) = pack_bf16x2(dv[j][2], dv[j][3]);
+      }
+    }
+  }
+}
+
+template <int HQ, int HV>
+static int launch_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                      int64_t n_win, int T, int H, float scale, cudaStream_t s) {
+  const int Tpad = (T + 63) & ~63;
+  const size_t smem = (size_t)Tpad * ((HQ + kPad) + (HV + kPad)) * 2;
+  auto kern = attn_fwd_kernel<HQ, HV>;
+  IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int q_tiles = Tpad / 64;
+  const int64_t grid = n_win * H * q_tiles;
+  IBM_CHECK_ARG(grid < (1ll << 31), "attention_fwd: grid too large");
+  kern<<<(unsigned)grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
+                                              static_cast<const __nv_bfloat16*>(v), ldv, static_cast<__nv_bfloat16*>(o), ldo, T, H,
+                                              q_tiles, scale * 1.4426950408889634f);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+template <int HD>
+static int launch_bwd(const void* qkv, int64_t ld, int64_t kv_off, const void* d_o, int64_t ldo, void* dqkv, int64_t n_win, int T,
+                      int H, float scale, cudaStream_t s) {
+  const size_t smem = (size_t)(4 * 64 * (HD + kPad) + 2 * 64 * (64 + kPad)) * 2;
+  auto kern = attn_bwd_kernel<HD>;
+  IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = n_win * H;
+  IBM_CHECK_ARG(grid < (1ll << 31), "attention_bwd: grid too large");
+  kern<<<(unsigned)grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv), ld, kv_off,
+                                              static_cast<const __nv_bfloat16*>(d_o), ldo, static_cast<__nv_bfloat16*>(dqkv), T, H, scale);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+}  // namespace attn
+}  // namespace ibm
+
+extern "C" int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                                 int64_t ldo, int64_t n_win, int32_t T, int32_t H, int32_t hd_qk, int32_t hd_v, float scale,
+                                 void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(q && k && v && o && n_win > 0 && T > 0 && H > 0, "attention_fwd: bad argument");
+  IBM_CHECK_ARG(T <= 256, "attention_fwd: T=%d > 256 unsupported (whole sequence must fit in shared memory)", T);
+  IBM_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0 && aligned16(q) && aligned16(k) && aligned16(v),
+                "attention_fwd: leading dimensions must be multiples of 8 and pointers 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (hd_qk == 64 && hd_v == 64) return attn::launch_fwd<64, 64>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+  if (hd_qk == 48 && hd_v == 48) return attn::launch_fwd<48, 48>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+  if (hd_qk == 32 && hd_v == 32) return attn::launch_fwd<32, 32>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+  if (hd_qk == 112 && hd_v == 8) return attn::launch_fwd<112, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+  set_error("attention_fwd: unsupported head dims (%d, %d); supported (64,64) (48,48) (32,32) (112,8)", hd_qk, hd_v);
+  return IBM_E_UNSUPPORTED;
+}
+
+extern "C" int ibm_attention_bwd(const void* qkv, int64_t ld_qkv, int64_t kv_off, const void* d_o, int64_t ld_o, void* dqkv,
+                                 int64_t n_win, int32_t T, int32_t H, int32_t head_dim, float scale, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(qkv && d_o && dqkv && n_win > 0 && T > 0 && H > 0, "attention_bwd: bad argument");
+  IBM_CHECK_ARG(T <= 64, "attention_bwd: T=%d > 64 unsupported", T);
+  IBM_CHECK_ARG(ld_qkv % 8 == 0 && ld_o % 8 == 0 && kv_off % 8 == 0 && aligned16(qkv) && aligned16(d_o) && aligned16(dqkv),
+                "attention_bwd: leading dimensions must be multiples of 8 and pointers 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (head_dim == 64) return attn::launch_bwd<64>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, s);
+  if (head_dim == 48) return attn::launch_bwd<48>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, s);
+  if (head_dim == 32) return attn::launch_bwd<32>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, s);
+  set_error("attention_bwd: unsupported head dim %d; supported 32, 48, 64", head_dim);
+  return IBM_E_UNSUPPORTED;
+}

@@ -1,0 +1,460 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA-fed tcgen05.mma with fp32 accumulators
+// in TMEM (double-buffered so the epilogue of tile i overlaps the main loop of tile i+1), fused
+// bias / activation / residual / activation-gradient epilogue, TMA store (or TMA reduce-add for
+// split-K weight gradients).
+//
+// Replaces the cuBLAS sgemm + separate bias/activation kernels behind
+//   nn.Linear  — /root/reference/src/models/FeedForwardRegressionBaseline.py:73,113,
+//                /root/reference/src/models/Groundlink.py:51-62,
+//                /root/reference/src/models/TransformerBaseline.py:12-18,91 (and their autograd
+//                backward: dgrad = dY·W, wgrad = dYᵀ·X)
+//   nn.Conv1d  — /root/reference/src/models/Groundlink.py:41 (taps > 1: implicit GEMM over row-shifted A)
+//
+// Roles (256 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM → registers → swizzled smem → TMA store).
+// Tile 128 x BN x 64, UMMA 128 x BN x 16, cta_group::1; operand tiles in SWIZZLE_128B layout.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace ibm {
+namespace gemm {
+
+using namespace ptx;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;      // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int kEpiWarp0 = 4;
+constexpr uint32_t kEpiBarrier = 1;
+constexpr int kStageA = BLOCK_M * BLOCK_K * 2;          // 16 KB
+constexpr int kOutStage = BLOCK_M * 128;                // 128 rows x 128 B = 16 KB
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStageB = BN * BLOCK_K * 2;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kSmem = 1024 /*align slack*/ + kStages * (kStageA + kStageB) + 2 * kOutStage + BN * 4 + 256;
+};
+
+struct Args {
+  int64_t M, N;
+  int32_t kb_total;        // number of 64-wide k blocks (all taps)
+  int32_t kb_per_tap;      // k blocks per tap (== kb_total when taps == 1)
+  int32_t kb_per_split;
+  int32_t splits;
+  int32_t tiles_m, tiles_n;
+  int32_t a_mn, b_mn;
+  int32_t act, aux_mode;
+  const float* bias;
+  const __nv_bfloat16* aux;
+  int64_t ldaux;
+};
+
+__device__ __forceinline__ void advance(int& stage, uint32_t& phase, int nstages) {
+  if (++stage == nstages) { stage = 0; phase ^= 1u; }
+}
+
+template <int BN, bool kOutF32, bool kAccum>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD, const Args args) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + C::kStages * kStageA;
+  uint8_t* smem_out = smem_b + C::kStages * C::kStageB;              // 2 x 16 KB, 1024-aligned
+  float* smem_bias = reinterpret_cast<float*>(smem_out + 2 * kOutStage);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_bias + BN);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads / 32); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_work = args.tiles_m * args.tiles_n * args.splits;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ======================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = kStageA + C::kStageB;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % args.splits;
+        const int tile = w / args.splits;
+        const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
+        const int m0 = tm * BLOCK_M, n0 = tn * BN;
+        const int kb0 = split * args.kb_per_split;
+        const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          uint8_t* sa = smem_a + stage * kStageA;
+          uint8_t* sb = smem_b + stage * C::kStageB;
+          const int tap = kb / args.kb_per_tap;
+          const int k0a = (kb - tap * args.kb_per_tap) * BLOCK_K;      // k coordinate inside A
+          const int k0b = kb * BLOCK_K;                                 // k coordinate inside B
+          if (!args.a_mn) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0a, m0 + tap);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_2d(sa + i * (BLOCK_K * 128), &tmA, &full_bar[stage], m0 + 64 * i, k0a);
+          }
+          if (!args.b_mn) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0b, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sb + i * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + 64 * i, k0b);
+          }
+          advance(stage, phase, C::kStages);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, args.a_mn, args.b_mn);
+      // K-major: 8-row groups are 1024 B apart (SBO); LBO unused.  MN-major: 64-wide MN atoms are
+      // BLOCK_K*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
+      const uint32_t a_lbo = args.a_mn ? BLOCK_K * 128 : 0, b_lbo = args.b_mn ? BLOCK_K * 128 : 0;
+      const uint32_t a_kstep = args.a_mn ? UMMA_K * 128 : UMMA_K * 2;
+      const uint32_t b_kstep = args.b_mn ? UMMA_K * 128 : UMMA_K * 2;
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % args.splits;
+        const int kb0 = split * args.kb_per_split;
+        const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * kStageA);
+          const uint32_t sb = smem_u32(smem_b + stage * C::kStageB);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          advance(stage, phase, C::kStages);
+        }
+        umma_commit(&tfull_bar[as]);               // accumulator complete → epilogue
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ======================================= epilogue ========================================
+    constexpr int CW = kOutF32 ? 32 : 64;           // columns per 128-byte staging row
+    const int q = warp & 3;                         // TMEM lane quadrant this warp may access
+    const int et = threadIdx.x - kEpiWarp0 * 32;    // 0..127
+    const int r_local = q * 32 + lane;              // tile row == TMEM lane
+    const bool leader = (et == 0);
+    int as = 0, ob = 0;
+    uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int tile = w / args.splits;
+      const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
+      const int m0 = tm * BLOCK_M, n0 = tn * BN;
+      const int64_t row = (int64_t)m0 + r_local;
+      const int n_valid = (int)min((int64_t)BN, args.N - n0);
+      const int n_chunks = (n_valid + CW - 1) / CW;
+
+      // stage this tile's bias slice (previous tile's readers are past their last named barrier)
+      if (!kAccum) {
+        for (int i = et; i < BN; i += kEpiThreads)
+          smem_bias[i] = (args.bias != nullptr && n0 + i < args.N) ? __ldg(args.bias + n0 + i) : 0.f;
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
+
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        float v[CW];
+        tmem_ld_32x32(tmem_acc + ch * CW, reinterpret_cast<uint32_t*>(v));
+        if (CW == 64) tmem_ld_32x32(tmem_acc + ch * CW + 32, reinterpret_cast<uint32_t*>(v) + 32);
+        tmem_ld_wait();
+        if (ch == n_chunks - 1) {
+          // all TMEM reads of this accumulator are done → hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        // make sure the staging buffer `ob` is no longer being read by the store issued 2 chunks ago,
+        // and (first chunk) that the bias slice is visible
+        if (leader) tma_wait_group_read<1>();
+        named_bar_sync(kEpiBarrier, kEpiThreads);
+
+        const int c0 = n0 + ch * CW;               // global column of v[0]
+        if (!kAccum) {
+          const float* bs = smem_bias + ch * CW;
+          const int act = args.act;
+          if (args.aux_mode == 2) {
+            // dgrad through an activation: out = (acc + bias) * act'(aux), aux = saved activation output
+            const __nv_bfloat16* ap = args.aux + row * args.ldaux + c0;
+#pragma unroll
+            for (int j = 0; j < CW; j += 8) {
+              float y[8];
+              if (row < args.M && c0 + j + 8 <= args.N) {
+                uint4 u = *reinterpret_cast<const uint4*>(ap + j);
+                float2 t;
+                t = unpack_bf16x2(u.x); y[0] = t.x; y[1] = t.y;
+                t = unpack_bf16x2(u.y); y[2] = t.x; y[3] = t.y;
+                t = unpack_bf16x2(u.z); y[4] = t.x; y[5] = t.y;
+                t = unpack_bf16x2(u.w); y[6] = t.x; y[7] = t.y;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = (row < args.M && c0 + j + e < args.N) ? __bfloat162float(ap[j + e]) : 0.f;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[j + e] = (v[j + e] + bs[j + e]) * act_grad_from_output(y[e], act);
+            }
+          } else {
+            switch (act) {
+              case IBM_ACT_RELU:
+#pragma unroll
+                for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j] + bs[j], 0.f);
+                break;
+              case IBM_ACT_NONE:
+#pragma unroll
+                for (int j = 0; j < CW; ++j) v[j] = v[j] + bs[j];
+                break;
+              default:
+#pragma unroll
+                for (int j = 0; j < CW; ++j) v[j] = act_apply(v[j] + bs[j], act);
+                break;
+            }
+            if (args.aux_mode == 1) {
+              // residual: out = act(acc + bias) + aux
+              const __nv_bfloat16* ap = args.aux + row * args.ldaux + c0;
+#pragma unroll
+              for (int j = 0; j < CW; j += 8) {
+                if (row < args.M && c0 + j + 8 <= args.N) {
+                  uint4 u = *reinterpret_cast<const uint4*>(ap + j);
+                  float2 t;
+                  t = unpack_bf16x2(u.x); v[j + 0] += t.x; v[j + 1] += t.y;
+                  t = unpack_bf16x2(u.y); v[j + 2] += t.x; v[j + 3] += t.y;
+                  t = unpack_bf16x2(u.z); v[j + 4] += t.x; v[j + 5] += t.y;
+                  t = unpack_bf16x2(u.w); v[j + 6] += t.x; v[j + 7] += t.y;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (row < args.M && c0 + j + e < args.N) v[j + e] += __bfloat162float(ap[j + e]);
+                }
+              }
+            }
+          }
+        }
+        // registers → swizzled staging rows (16-byte chunk index XOR (row & 7): conflict-free, and
+        // exactly the SWIZZLE_128B pattern the store tensor map expects)
+        uint8_t* srow = smem_out + ob * kOutStage + r_local * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 pk;
+          if (kOutF32) {
+            pk = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                            __float_as_uint(v[4 * j + 3]));
+          } else {
+            pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
+          *reinterpret_cast<uint4*>(srow + ((j ^ (r_local & 7)) << 4)) = pk;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(kEpiBarrier, kEpiThreads);
+        if (leader) {
+          if (kAccum) tma_reduce_add_2d(&tmD, smem_out + ob * kOutStage, c0, m0);
+          else tma_store_2d(&tmD, smem_out + ob * kOutStage, c0, m0);
+          tma_commit_group();
+        }
+        ob ^= 1;
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (leader) tma_wait_group<0>();      // all global writes issued by this CTA are complete
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------- host side -------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D row-major tensor [outer, inner] with row pitch ld (elements); box = [box_outer, box_inner]
+static int make_map(CUtensorMap* map, const void* base, bool f32, int64_t inner, int64_t outer, int64_t ld,
+                    uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return IBM_E_CUDA; }
+  const size_t es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld ld=%lld box=%ux%u", (int)r, (long long)inner,
+              (long long)outer, (long long)ld, box_inner, box_outer);
+    return IBM_E_CUDA;
+  }
+  return IBM_OK;
+}
+
+template <int BN, bool F32, bool ACC>
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const Args& args, int grid, cudaStream_t s) {
+  static bool attr_set = false;     // per instantiation
+  auto kern = gemm_kernel<BN, F32, ACC>;
+  if (!attr_set) {
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, Cfg<BN>::kSmem, s>>>(a, b, d, args);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+static int pick_bn(int64_t N) {
+  const int cands[4] = {256, 128, 64, 32};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const double eff = (double)N / (double)(ceil_div(N, bn) * bn);
+    if (eff >= 0.75) return bn;
+  }
+  return 32;
+}
+
+}  // namespace gemm
+}  // namespace ibm
+
+extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
+                             int64_t M, int64_t N, int64_t K, const float* bias, int32_t act, const void* aux, int64_t ldaux,
+                             int32_t aux_mode, void* D, int64_t ldd, int32_t out_dtype, int32_t accumulate, int32_t split_k,
+                             int32_t taps, void* stream) {
+  using namespace ibm;
+  using namespace ibm::gemm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(A && B && D, "gemm: null operand");
+  IBM_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
+  IBM_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
+  IBM_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && aligned16(A) && aligned16(B) && aligned16(D),
+                "gemm: lda/ldb must be multiples of 8 elements and pointers 16-byte aligned");
+  IBM_CHECK_ARG(out_dtype == IBM_BF16 || out_dtype == IBM_F32, "gemm: bad out dtype");
+  IBM_CHECK_ARG((out_dtype == IBM_BF16 && ldd % 8 == 0) || (out_dtype == IBM_F32 && ldd % 4 == 0), "gemm: ldd not 16-byte aligned");
+  IBM_CHECK_ARG(act >= 0 && act <= IBM_ACT_SILU, "gemm: bad activation %d", act);
+  IBM_CHECK_ARG(aux_mode >= 0 && aux_mode <= 2 && (aux_mode == 0 || aux != nullptr), "gemm: bad aux mode");
+  IBM_CHECK_ARG(aux_mode == 0 || (ldaux % 8 == 0 && aligned16(aux)), "gemm: aux must be 16-byte aligned with ld %% 8 == 0");
+  IBM_CHECK_ARG(!accumulate || (out_dtype == IBM_F32 && act == IBM_ACT_NONE && aux_mode == 0 && bias == nullptr),
+                "gemm: accumulate mode needs fp32 output and a plain epilogue");
+  if (taps < 1) taps = 1;
+  IBM_CHECK_ARG(taps == 1 || (!a_mn_major && K % taps == 0 && (K / taps) % 8 == 0), "gemm: taps needs K-major A and K/taps %% 8 == 0");
+
+  const int bn = pick_bn(N);
+  const int64_t k_tap = K / taps;
+  Args args;
+  args.M = M; args.N = N;
+  args.kb_per_tap = (int32_t)ceil_div(k_tap, BLOCK_K);
+  args.kb_total = args.kb_per_tap * taps;
+  args.tiles_m = (int32_t)ceil_div(M, BLOCK_M);
+  args.tiles_n = (int32_t)ceil_div(N, bn);
+  const int sms = sm_count();
+  int splits = 1;
+  if (accumulate) {
+    const int64_t tiles = (int64_t)args.tiles_m * args.tiles_n;
+    splits = split_k > 0 ? split_k : (int)ceil_div(2 * sms, tiles);
+    int max_splits = args.kb_total / 8 > 0 ? args.kb_total / 8 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  args.kb_per_split = (int32_t)ceil_div(args.kb_total, splits);
+  args.splits = (int32_t)ceil_div(args.kb_total, args.kb_per_split);
+  args.a_mn = a_mn_major ? 1 : 0;
+  args.b_mn = b_mn_major ? 1 : 0;
+  args.act = act; args.aux_mode = aux_mode;
+  args.bias = bias;
+  args.aux = static_cast<const __nv_bfloat16*>(aux);
+  args.ldaux = ldaux;
+  // With taps the B operand is [N, taps * kb_per_tap * 64] (each tap's K padded to whole k blocks).
+  const int64_t Kb = taps == 1 ? K : (int64_t)args.kb_total * BLOCK_K;
+
+  CUtensorMap ta, tb, td;
+  int rc;
+  if (!args.a_mn) rc = make_map(&ta, A, false, k_tap, M + (taps - 1), lda, BLOCK_K, BLOCK_M);
+  else rc = make_map(&ta, A, false, M, K, lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!args.b_mn) rc = make_map(&tb, B, false, Kb, N, ldb, BLOCK_K, (uint32_t)bn);
+  else rc = make_map(&tb, B, false, N, K, ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  const bool f32 = out_dtype == IBM_F32;
+  rc = make_map(&td, D, f32, N, M, ldd, f32 ? 32 : 64, BLOCK_M);
+  if (rc) return rc;
+
+  const int64_t work = (int64_t)args.tiles_m * args.tiles_n * args.splits;
+  const int grid = (int)(work < sms ? work : sms);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define IBM_GEMM_DISPATCH(BNV)                                                   \
+  do {                                                                           \
+    if (accumulate) return launch<BNV, true, true>(ta, tb, td, args, grid, s);   \
+    if (f32) return launch<BNV, true, false>(ta, tb, td, args, grid, s);         \
+    return launch<BNV, false, false>(ta, tb, td, args, grid, s);                 \
+  } while (0)
+  switch (bn) {
+    case 256: IBM_GEMM_DISPATCH(256);
+    case 128: IBM_GEMM_DISPATCH(128);
+    case 64: IBM_GEMM_DISPATCH(64);
+    default: IBM_GEMM_DISPATCH(32);
+  }
+#undef IBM_GEMM_DISPATCH
+}

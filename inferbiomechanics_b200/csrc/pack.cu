@@ -1,0 +1,163 @@
+// Window batcher kernels: candidate-window validity, frame gather into packed model inputs, and
+// label rows.  Bit-exact integer/byte/copy work, HBM-bound.
+//
+// Replaces, for data already resident in an HBM frame store:
+//   /root/reference/src/data/AddBiomechanicsDataset.py:131-139  (window enumeration predicate)
+//   /root/reference/src/data/AddBiomechanicsDataset.py:161-285  (__getitem__: ~18 row_stacks/window)
+//   /root/reference/src/models/FeedForwardRegressionBaseline.py:97-108 (concat + reshape + H2D)
+#include "common.cuh"
+
+namespace ibm {
+
+constexpr int kThreads = 256;
+
+// valid[c] = !any(missing[ws : ws+T : s])  — python slice semantics: indices ws, ws+s, … < ws+T.
+// The caller only enumerates candidates with ws + T < L (Dataset.py:135), so no bound check on L.
+__global__ void __launch_bounds__(kThreads)
+window_valid_kernel(const uint8_t* __restrict__ missing, const long long* __restrict__ trial_base,
+                    const int32_t* __restrict__ cand_trial, const int32_t* __restrict__ cand_start, long long n,
+                    int T, int s, uint8_t* __restrict__ valid) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint8_t* m = missing + __ldg(trial_base + __ldg(cand_trial + i)) + __ldg(cand_start + i);
+    uint8_t any = 0;
+    for (int k = 0; k < T; k += s) any |= __ldg(m + k);
+    valid[i] = any ? 0 : 1;
+  }
+}
+
+// One warp per (window, frame) source row.  Source rows are `stride` frames apart; each row is
+// read as float4 (16-byte vectorised; frame_ld % 4 == 0) and written once as fp32 and/or bf16.
+template <bool kVec4>
+__global__ void __launch_bounds__(kThreads)
+pack_windows_kernel(const float* __restrict__ frames, long long frame_ld, int C, const long long* __restrict__ row0,
+                    long long n_rows, int F, int stride, float* __restrict__ out_f32,
+                    __nv_bfloat16* __restrict__ out_bf16, long long fs, long long we, long long col0) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n_rows; r += warps) {
+    const long long i = r / F;
+    const int f = (int)(r - i * F);
+    const float* src = frames + (__ldg(row0 + i) + (long long)f * stride) * frame_ld;
+    float* d32 = out_f32 ? out_f32 + r * C : nullptr;
+    __nv_bfloat16* d16 = out_bf16 ? out_bf16 + r * fs + i * we + col0 : nullptr;
+    if (kVec4) {
+      // source rows 16-byte aligned; fp32 dst (if any) 16-byte aligned per row; bf16 dst 4-byte aligned
+      for (int c = lane * 4; c < C; c += 128) {
+        if (c + 4 <= C) {
+          float4 v = ld_stream_f4(src + c);
+          if (d32) st_stream_f4(d32 + c, v);
+          if (d16) {
+            *reinterpret_cast<uint32_t*>(d16 + c) = pack_bf16x2(v.x, v.y);
+            *reinterpret_cast<uint32_t*>(d16 + c + 2) = pack_bf16x2(v.z, v.w);
+          }
+        } else {                                   // ragged row tail (C % 4 != 0)
+          for (int k = c; k < C; ++k) {
+            float v = __ldg(src + k);
+            if (d32) d32[k] = v;
+            if (d16) d16[k] = __float2bfloat16_rn(v);
+          }
+        }
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        float v = __ldg(src + c);
+        if (d32) d32[c] = v;
+        if (d16) d16[c] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+// Label rows30: thread per (row, channel).  Raw per-frame layout: [cop 3nb | force 3nb | torque 3nb | wrench 6nb].
+__global__ void __launch_bounds__(kThreads)
+pack_labels_kernel(const float* __restrict__ raw, long long raw_ld, int nb, const long long* __restrict__ row0,
+                   const int32_t* __restrict__ contact_idx, const float* __restrict__ mass, long long n_win, int F,
+                   int stride, int last_only, float* __restrict__ out, long long out_ld) {
+  const int Fo = last_only ? 1 : F;
+  const int CH = 15 * nb;
+  const long long n = n_win * Fo * CH;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / CH;
+    const int ch = (int)(e - r * CH);
+    const long long i = r / Fo;
+    const int f = last_only ? F - 1 : (int)(r - i * Fo);
+    // channel → (quantity, body, component)
+    int q, w, rem;
+    if (ch < 3 * nb) { q = 0; w = 3; rem = ch; }
+    else if (ch < 6 * nb) { q = 1; w = 3; rem = ch - 3 * nb; }
+    else if (ch < 9 * nb) { q = 2; w = 3; rem = ch - 6 * nb; }
+    else { q = 3; w = 6; rem = ch - 9 * nb; }
+    const int body = rem / w, comp = rem - body * w;
+    const int ci = __ldg(contact_idx + i * nb + body);
+    float v = 0.f;
+    if (ci >= 0) {
+      const int qoff = q == 0 ? 0 : q == 1 ? 3 * nb : q == 2 ? 6 * nb : 9 * nb;
+      v = __ldg(raw + (__ldg(row0 + i) + (long long)f * stride) * raw_ld + qoff + ci * w + comp);
+      if (q != 0) v = __fdiv_rn(v, __ldg(mass + i));        // CoP is not mass-normalised (Dataset.py:251-253)
+    }
+    out[r * out_ld + ch] = v;
+  }
+}
+
+static int grid_for(long long items, int per_block) {
+  long long need = ceil_div(items, per_block);
+  long long cap = (long long)sm_count() * 16;
+  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+}  // namespace ibm
+
+extern "C" int ibm_window_valid_mask(const uint8_t* missing, const int64_t* trial_frame_base, const int32_t* cand_trial,
+                                     const int32_t* cand_start, int64_t n_cand, int32_t window_size, int32_t stride,
+                                     uint8_t* valid, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(window_size > 0 && stride > 0, "window_valid_mask: window_size and stride must be positive");
+  if (n_cand == 0) return IBM_OK;                       // empty dataset → empty index (Dataset.py:134 range(0))
+  IBM_CHECK_ARG(missing && trial_frame_base && cand_trial && cand_start && valid && n_cand > 0, "window_valid_mask: null argument");
+  window_valid_kernel<<<grid_for(n_cand, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      missing, reinterpret_cast<const long long*>(trial_frame_base), cand_trial, cand_start, n_cand, window_size, stride, valid);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+extern "C" int ibm_pack_windows(const float* frames, int64_t frame_ld, int32_t C, const int64_t* win_row0, int64_t n_win,
+                                int32_t F, int32_t stride, float* out_f32, void* out_bf16, int64_t bf16_frame_stride,
+                                int64_t bf16_win_extra, int64_t bf16_col0, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  if (n_win == 0) return IBM_OK;                        // ragged tail / empty batch
+  IBM_CHECK_ARG(frames && win_row0 && n_win > 0 && F > 0 && C > 0 && stride > 0 && frame_ld >= C, "pack_windows: bad argument");
+  IBM_CHECK_ARG(out_f32 || out_bf16, "pack_windows: no output requested");
+  const bool vec = (frame_ld % 4 == 0) && aligned16(frames) && (!out_f32 || (C % 4 == 0 && aligned16(out_f32))) &&
+                   (!out_bf16 || ((bf16_frame_stride % 2 == 0) && (bf16_win_extra % 2 == 0) && (bf16_col0 % 2 == 0) &&
+                                  (reinterpret_cast<uintptr_t>(out_bf16) % 4 == 0)));
+  const long long n_rows = (long long)n_win * F;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n_rows, kThreads / 32);
+  auto* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  auto* r0 = reinterpret_cast<const long long*>(win_row0);
+  if (vec) pack_windows_kernel<true><<<grid, kThreads, 0, s>>>(frames, frame_ld, C, r0, n_rows, F, stride, out_f32, ob,
+                                                              bf16_frame_stride, bf16_win_extra, bf16_col0);
+  else pack_windows_kernel<false><<<grid, kThreads, 0, s>>>(frames, frame_ld, C, r0, n_rows, F, stride, out_f32, ob,
+                                                            bf16_frame_stride, bf16_win_extra, bf16_col0);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+extern "C" int ibm_pack_labels(const float* raw, int64_t raw_ld, int32_t nb, const int64_t* win_row0,
+                               const int32_t* contact_idx, const float* mass, int64_t n_win, int32_t F, int32_t stride,
+                               int32_t last_frame_only, float* out_rows, int64_t out_ld, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  if (n_win == 0) return IBM_OK;
+  IBM_CHECK_ARG(raw && win_row0 && contact_idx && mass && out_rows && n_win > 0 && F > 0 && nb > 0 && stride > 0,
+                "pack_labels: bad argument");
+  IBM_CHECK_ARG(raw_ld >= 15 * nb && out_ld >= 15 * nb, "pack_labels: leading dimensions too small");
+  const long long n = (long long)n_win * (last_frame_only ? 1 : F) * 15 * nb;
+  pack_labels_kernel<<<grid_for(n, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      raw, raw_ld, nb, reinterpret_cast<const long long*>(win_row0), contact_idx, mass, n_win, F, stride, last_frame_only,
+      out_rows, out_ld);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}

@@ -1,0 +1,129 @@
+"""GPU parity: tcgen05 GEMM (through the C ABI) vs fp64 matmul of the same bf16-rounded operands.
+
+Tolerance: operands are exact bf16 on both sides and accumulation is fp32 in TMEM, so the only
+differences are fp32 summation order and the final output rounding: rtol 2e-2*|bf16 ulp| for bf16
+outputs (one bf16 rounding = 2^-8 relative) and 1e-4 relative-to-scale for fp32 outputs.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rows, cols, ld, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    buf = torch.zeros(rows, ld, dtype=torch.bfloat16)
+    buf[:, :cols] = (torch.randn(rows, cols, generator=g) * scale).to(torch.bfloat16)
+    return buf
+
+
+ACTS = {
+    "none": lambda x: x, "relu": lambda x: x.clamp_min(0), "sigmoid": torch.sigmoid, "tanh": torch.tanh,
+    "elu": torch.nn.functional.elu, "silu": torch.nn.functional.silu,
+}
+
+
+def _check(out, ref, bf16_out, what):
+    out = out.double().cpu()
+    scale = ref.abs().max().item() + 1e-30
+    err = (out - ref).abs().max().item()
+    tol = (1.0 / 128 if bf16_out else 2e-4) * scale
+    assert err <= tol, f"{what}: max abs err {err:.4g} > {tol:.4g} (scale {scale:.4g})"
+
+
+@pytest.mark.parametrize("M,N,K,act,out_f32", [
+    (128, 256, 64, "none", False),
+    (256, 256, 128, "relu", False),
+    (300, 300, 1470, "sigmoid", False),      # FeedForward layer shapes, ragged everything
+    (32, 512, 1470, "sigmoid", False),       # BASELINE config 1 batch
+    (1000, 512, 512, "tanh", True),
+    (520, 30, 512, "none", True),            # 30-channel head, fp32 out
+    (777, 1536, 512, "none", False),         # fused QKV
+    (640, 2048, 512, "relu", False),
+    (640, 512, 2048, "none", False),
+    (130, 128, 208, "elu", False),
+    (4096, 64, 72, "silu", False),
+])
+def test_gemm_forward(M, N, K, act, out_f32):
+    from inferbiomechanics_b200 import ops
+    lda, ldb = ops.round_up(K, 8), ops.round_up(K, 8)
+    A, B = _mk(M, K, lda, 1), _mk(N, K, ldb, 2, 1.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3))
+    ldd = ops.round_up(N, 4 if out_f32 else 8)
+    out = torch.full((M, ldd), 7.0, dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")
+    ops.gemm(A.cuda(), B.cuda(), out, M, N, K, bias=bias.cuda(), act=act)
+    torch.cuda.synchronize()
+    ref = ACTS[act](A[:, :K].double() @ B[:, :K].double().t() + bias.double())
+    _check(out[:, :N], ref, not out_f32, f"fwd {M}x{N}x{K} {act}")
+    if ldd > N:   # pad columns must be untouched (TMA store clips at N)
+        assert torch.all(out[:, N:].float() == 7.0)
+
+
+def test_gemm_residual_and_dact():
+    from inferbiomechanics_b200 import ops
+    M, N, K = 515, 512, 256
+    A, B = _mk(M, K, K, 4), _mk(N, K, K, 5, 1.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(6))
+    aux = _mk(M, N, N, 7)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A.cuda(), B.cuda(), out, M, N, K, bias=bias.cuda(), aux=aux.cuda(), aux_mode=1)
+    ref = A.double() @ B.double().t() + bias.double() + aux.double()
+    _check(out, ref, True, "residual")
+    for act, dfn in (("relu", lambda y: (y > 0).double()), ("sigmoid", lambda y: y * (1 - y)),
+                     ("tanh", lambda y: 1 - y * y), ("elu", lambda y: torch.where(y > 0, torch.ones_like(y), y + 1))):
+        y = ACTS[act](_mk(M, N, N, 8).float()).to(torch.bfloat16)
+        ops.gemm(A.cuda(), B.cuda(), out, M, N, K, act=act, aux=y.cuda(), aux_mode=2)
+        ref = (A.double() @ B.double().t()) * dfn(y.double())
+        _check(out, ref, True, f"dact {act}")
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 192), (1000, 1470, 512), (333, 512, 300), (640, 208, 512)])
+def test_gemm_dgrad_b_mn_major(M, N, K):
+    """dX[M,N] = dY[M,K] · W[K,N]  with W stored row-major [K, N] (MN-major B operand)."""
+    from inferbiomechanics_b200 import ops
+    dY = _mk(M, K, ops.round_up(K, 8), 11)
+    W = _mk(K, N, ops.round_up(N, 8), 12, 1.0 / math.sqrt(K))
+    out = torch.empty(M, ops.round_up(N, 8), dtype=torch.bfloat16, device="cuda")
+    ops.gemm(dY.cuda(), W.cuda(), out, M, N, K, b_mn=True)
+    ref = dY[:, :K].double() @ W[:, :N].double()
+    _check(out[:, :N], ref, True, f"dgrad {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("Mtok,Nout,Kin,split", [(512, 128, 256, 1), (4000, 512, 512, 0), (1111, 300, 512, 3),
+                                                 (2048, 512, 1472, 0), (6400, 30, 512, 0)])
+def test_gemm_wgrad_mn_mn_accumulate(Mtok, Nout, Kin, split):
+    """dW[Nout,Kin] += dY[Mtok,Nout]^T · X[Mtok,Kin]: both operands MN-major, split-K TMA reduce-add."""
+    from inferbiomechanics_b200 import ops
+    dY = _mk(Mtok, Nout, ops.round_up(Nout, 8), 21)
+    X = _mk(Mtok, Kin, ops.round_up(Kin, 8), 22)
+    init = torch.randn(Nout, Kin, generator=torch.Generator().manual_seed(23))
+    dW = init.clone().cuda()
+    ops.gemm(dY.cuda(), X.cuda(), dW, Nout, Kin, Mtok, a_mn=True, b_mn=True, accumulate=True, split_k=split)
+    ref = init.double() + dY[:, :Nout].double().t() @ X[:, :Kin].double()
+    _check(dW, ref, False, f"wgrad {Mtok} {Nout}x{Kin}")
+
+
+def test_gemm_taps_implicit_conv():
+    """K = taps*C: k-block kb reads A rows m + kb // kb_per_tap (temporal convolution as a GEMM)."""
+    from inferbiomechanics_b200 import ops
+    rows, C, N, taps = 400, 128, 256, 7
+    Xp = _mk(rows + taps - 1, C, C, 31)
+    W = _mk(N, taps * C, taps * C, 32, 1.0 / math.sqrt(taps * C))
+    out = torch.empty(rows, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(Xp.cuda(), W.cuda(), out, rows, N, taps * C, taps=taps)
+    ref = torch.zeros(rows, N, dtype=torch.float64)
+    for j in range(taps):
+        ref += Xp[j:j + rows].double() @ W[:, j * C:(j + 1) * C].double().t()
+    _check(out, ref, True, "taps")
+
+
+def test_gemm_argument_errors():
+    from inferbiomechanics_b200 import ops
+    A = torch.zeros(8, 12, dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros(8, 8, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(ValueError):
+        ops.gemm(A, A, out, 8, 8, 12)                   # lda=12 is not a multiple of 8
+    with pytest.raises(ValueError):
+        ops.gemm(out, out, out, 0, 8, 8)                # empty problem
