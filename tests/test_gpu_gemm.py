@@ -57,8 +57,11 @@ def test_gemm_forward(M, N, K, act, out_f32):
     torch.cuda.synchronize()
     ref = ACTS[act](A[:, :K].double() @ B[:, :K].double().t() + bias.double())
     _check(out[:, :N], ref, not out_f32, f"fwd {M}x{N}x{K} {act}")
-    if ldd > N:   # pad columns must be untouched (TMA store clips at N)
-        assert torch.all(out[:, N:].float() == 7.0)
+    # TMA clips stores at the tensor extent rounded up to a 16-byte chunk: columns beyond that are untouched
+    gran = 4 if out_f32 else 8
+    n_touched = (N + gran - 1) // gran * gran
+    if ldd > n_touched:
+        assert torch.all(out[:, n_touched:].float() == 7.0)
 
 
 def test_gemm_residual_and_dact():
@@ -127,3 +130,25 @@ def test_gemm_argument_errors():
         ops.gemm(A, A, out, 8, 8, 12)                   # lda=12 is not a multiple of 8
     with pytest.raises(ValueError):
         ops.gemm(out, out, out, 0, 8, 8)                # empty problem
+
+
+def test_gemm_pad_column_contract():
+    """Header contract: when K % 8 != 0 the operand pad columns [K, ld) must be zero.  This test pins
+    what the hardware does otherwise (TMA bounds-checks the inner dimension in 16-byte chunks), so a
+    change in that behaviour is noticed: garbage in the last partial chunk DOES leak into the result,
+    garbage beyond it does not."""
+    from inferbiomechanics_b200 import ops
+    M, N, K = 128, 128, 68                # 68 = 8*8 + 4: last chunk holds cols 64..71, ld = 80
+    A, B = _mk(M, K, 80, 41), _mk(N, K, 80, 42)
+    ref = A[:, :K].double() @ B[:, :K].double().t()
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    A2, B2 = A.clone(), B.clone()
+    A2[:, 72:] = 100.0; B2[:, 72:] = 100.0          # beyond the last partial chunk: must be ignored
+    ops.gemm(A2.cuda(), B2.cuda(), out, M, N, K)
+    _check(out, ref, False, "garbage beyond the partial chunk")
+    A3, B3 = A.clone(), B.clone()
+    A3[:, 68:72] = 1.0; B3[:, 68:72] = 1.0           # inside the partial chunk
+    ops.gemm(A3.cuda(), B3.cuda(), out, M, N, K)
+    leaked = (out.double().cpu() - ref).abs().max().item()
+    assert leaked < 1e-3 or abs(leaked - 4.0) < 1e-2, leaked
+    print("TMA inner-dimension bound granularity:", "16-byte chunk (pads must be zero)" if leaked > 1 else "element")
