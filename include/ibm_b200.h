@@ -79,6 +79,14 @@ int ibm_pack_windows(const float* frames, int64_t frame_ld, int32_t C, const int
                      int64_t n_win, int32_t F, int32_t stride, float* out_f32, void* out_bf16,
                      int64_t bf16_frame_stride, int64_t bf16_win_extra, int64_t bf16_col0, void* stream);
 
+/* Concatenate n_src (<= 10) fp32 tensors [n_rows, width_k] (contiguous) along the channel axis in
+ * the given order (the reference's torch.concat at FeedForward…py:97-108 / Groundlink.py:122-133)
+ * into packed rows; outputs addressed exactly as in ibm_pack_windows (row r = window*F + frame).
+ * h_src: host array of device pointers; h_widths: host int32[n_src]. */
+int ibm_pack_inputs(const void* const* h_src, const int32_t* h_widths, int32_t n_src, int64_t n_rows,
+                    int32_t F, float* out_f32, void* out_bf16, int64_t bf16_frame_stride,
+                    int64_t bf16_win_extra, int64_t bf16_col0, void* stream);
+
 /* Label rows (Dataset.py:216-261): raw first-pass per-frame [cop 3nb | force 3nb | torque 3nb |
  * wrench 6nb] in the SUBJECT's body order → rows30 in the DATASET's body order, force/torque/
  * wrench divided by the subject mass (IEEE fp32 division), absent bodies → 0.

@@ -324,7 +324,11 @@ static int launch_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, co
   const int Tpad = (T + 63) & ~63;
   const size_t smem = (size_t)Tpad * ((HQ + kPad) + (HV + kPad)) * 2;
   auto kern = attn_fwd_kernel<HQ, HV>;
-  IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set = 0;                    // per instantiation; raise the opt-in limit only when it grows
+  if (smem > smem_set) {
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   const int q_tiles = Tpad / 64;
   const int64_t grid = n_win * H * q_tiles;
   IBM_CHECK_ARG(grid < (1ll << 31), "attention_fwd: grid too large");
@@ -340,7 +344,11 @@ static int launch_bwd(const void* qkv, int64_t ld, int64_t kv_off, const void* d
                       int H, float scale, cudaStream_t s) {
   const size_t smem = (size_t)(4 * 64 * (HD + kPad) + 2 * 64 * (64 + kPad)) * 2;
   auto kern = attn_bwd_kernel<HD>;
-  IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;
+  if (!attr_set) {
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   const int64_t grid = n_win * H;
   IBM_CHECK_ARG(grid < (1ll << 31), "attention_bwd: grid too large");
   kern<<<(unsigned)grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv), ld, kv_off,

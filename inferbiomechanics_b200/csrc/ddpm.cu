@@ -83,7 +83,8 @@ posterior_kernel(const float* __restrict__ x0h, long long x0_ld, const float* __
     float2 n;
     if (z) n = *reinterpret_cast<const float2*>(z + 2 * p);
     else {
-      float4 z4 = philox_normal4(seed, offset, (uint64_t)(p >> 1));
+      // counter offset includes the step so a CUDA-graph replay (frozen arguments) still draws fresh noise
+      float4 z4 = philox_normal4(seed, offset + (uint64_t)tt, (uint64_t)(p >> 1));
       n = (p & 1) ? make_float2(z4.z, z4.w) : make_float2(z4.x, z4.y);
     }
     float2 r;

@@ -204,7 +204,11 @@ extern "C" int ibm_layernorm_bwd(const void* dy, const void* s, int64_t ld, cons
   const size_t smem = (size_t)3 * 8 * ch * 256 * sizeof(float);
 #define IBM_LN_BWD(CHV)                                                                                          \
   do {                                                                                                           \
-    IBM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    static bool attr_set_##CHV = false;                                                                          \
+    if (!attr_set_##CHV) {                                                                                       \
+      IBM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_set_##CHV = true;                                                                                     \
+    }                                                                                                            \
     layernorm_bwd_kernel<CHV><<<grid, kThreads, smem, st>>>(dyp, sp, ld, gamma, mean, rstd, M, d, dsp, dgamma, dbeta, dcolsum); \
   } while (0)
   switch (ch) {

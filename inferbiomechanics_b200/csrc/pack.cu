@@ -99,6 +99,32 @@ pack_labels_kernel(const float* __restrict__ raw, long long raw_ld, int nb, cons
   }
 }
 
+
+// Dict-of-tensors packer (A-4): up to 10 fp32 sources, each [rows, width_k] contiguous, concatenated
+// along the channel axis in the given order into one bf16 (and/or fp32) row per (window, frame).
+struct PackSrc {
+  const float* ptr[10];
+  int width[10];
+  int offset[11];
+  int n;
+};
+__global__ void __launch_bounds__(kThreads)
+pack_inputs_kernel(const PackSrc src, long long n_rows, int F, float* __restrict__ out_f32,
+                   __nv_bfloat16* __restrict__ out_bf16, long long fs, long long we, long long col0) {
+  const int C = src.offset[src.n];
+  const long long n = n_rows * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / C;
+    const int c = (int)(e - r * C);
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < 10; ++i) k += (i < src.n && c >= src.offset[i]) ? 1 : 0;
+    const float v = __ldg(src.ptr[k] + r * src.width[k] + (c - src.offset[k]));
+    if (out_f32) out_f32[e] = v;
+    if (out_bf16) out_bf16[r * fs + (r / F) * we + col0 + c] = __float2bfloat16_rn(v);
+  }
+}
+
 static int grid_for(long long items, int per_block) {
   long long need = ceil_div(items, per_block);
   long long cap = (long long)sm_count() * 16;
@@ -158,6 +184,29 @@ extern "C" int ibm_pack_labels(const float* raw, int64_t raw_ld, int32_t nb, con
   pack_labels_kernel<<<grid_for(n, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       raw, raw_ld, nb, reinterpret_cast<const long long*>(win_row0), contact_idx, mass, n_win, F, stride, last_frame_only,
       out_rows, out_ld);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+extern "C" int ibm_pack_inputs(const void* const* h_src, const int32_t* h_widths, int32_t n_src, int64_t n_rows, int32_t F,
+                               float* out_f32, void* out_bf16, int64_t bf16_frame_stride, int64_t bf16_win_extra,
+                               int64_t bf16_col0, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  if (n_rows == 0) return IBM_OK;
+  IBM_CHECK_ARG(h_src && h_widths && n_src > 0 && n_src <= 10 && n_rows > 0 && F > 0, "pack_inputs: bad argument");
+  IBM_CHECK_ARG(out_f32 || out_bf16, "pack_inputs: no output requested");
+  PackSrc src;
+  src.n = n_src;
+  src.offset[0] = 0;
+  for (int i = 0; i < 10; ++i) {
+    src.ptr[i] = i < n_src ? static_cast<const float*>(h_src[i]) : nullptr;
+    src.width[i] = i < n_src ? h_widths[i] : 0;
+    IBM_CHECK_ARG(i >= n_src || (src.ptr[i] && src.width[i] > 0), "pack_inputs: null source %d", i);
+    src.offset[i + 1] = src.offset[i] + src.width[i];
+  }
+  pack_inputs_kernel<<<grid_for(n_rows * src.offset[n_src], kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, n_rows, F, out_f32, static_cast<__nv_bfloat16*>(out_bf16), bf16_frame_stride, bf16_win_extra, bf16_col0);
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }

@@ -200,6 +200,14 @@ def pack_windows(frames, C, win_row0, F, stride, out_f32=None, out_bf16=None, fr
          _p(out_bf16), frame_stride, win_extra, col0, stream_ptr())
 
 
+def pack_inputs(srcs, n_rows, F, out_f32=None, out_bf16=None, frame_stride=0, win_extra=0, col0=0):
+    """srcs: list of contiguous fp32 CUDA tensors [n_rows, w_k] (any leading shape that flattens to n_rows)."""
+    n = len(srcs)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    widths = (ctypes.c_int32 * n)(*[t.shape[-1] for t in srcs])
+    call("ibm_pack_inputs", ptrs, widths, n, n_rows, F, _p(out_f32), _p(out_bf16), frame_stride, win_extra, col0, stream_ptr())
+
+
 def pack_labels(raw, nb, win_row0, contact_idx, mass, F, stride, last_only, out_rows):
     call("ibm_pack_labels", _p(raw), raw.stride(0), nb, _p(win_row0), _p(contact_idx), _p(mass), win_row0.numel(), F, stride,
          int(last_only), _p(out_rows), out_rows.stride(0), stream_ptr())
