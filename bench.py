@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""Benchmark of the InferBiomechanics hot path on B200 (contract: see task description / DESIGN.md §4).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the reference path on host cores
+
+Workload at every N: BASELINE.json configs[1]/[2] — motion-diffusion denoiser TRAINING on synthetic
+AddBiomechanics-shaped windows (F=50 frames, 177 kinematic channels, 30 target channels), bf16 GEMMs,
+per-GPU batch 4096 windows (weak scaling), d=512 / 8 heads / FFN 2048 / 8 layers, RMSprop 1e-4.
+One step = window packer → q_sample → forward → fused regression loss → backward → (bucketed NCCL
+allreduce) → fused optimizer.  `value` = windows/s with the frame store resident in HBM; `e2e` = the
+same step fed from pinned HOST tensors through Trainer.train_step_host (H2D of the step's inputs and a
+D2H read of the loss inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoiser_train_windows_per_sec"
+UNIT = "windows/s"
+F, C_IN, D_MODEL, HEADS, FF, LAYERS = 50, 177, 512, 8, 2048, 8
+PER_GPU_BATCH = 4096
+
+
+def config(n_gpus: int, batch: int) -> dict:
+    return {
+        "workload": "BASELINE configs[1] (N=1) / configs[2] (N>1): diffusion denoiser training, synthetic kinematic windows",
+        "frames": F, "cond_channels": C_IN, "target_channels": 30, "d_model": D_MODEL, "heads": HEADS, "ffn": FF,
+        "layers": LAYERS, "per_gpu_batch_windows": batch, "global_batch_windows": batch * n_gpus,
+        "optimizer": "rmsprop lr=1e-4", "parallelism": f"dp{n_gpus}",
+        "l2": "per-step working set (~25 GB of activations) >> 126 MB L2; no explicit flush needed",
+    }
+
+
+def peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [c for c in sm if c > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference_arm(args) -> None:
+    """The reference path on the box's host cores.  The reference is pure Python and lives only in the build
+    container (/root/reference does not exist here), so this times the CPU port of its training loop
+    (oracle/train.py; torch CPU ops + torch.optim.RMSprop, all host threads) on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import ddpm as oddpm
+    from oracle import train as otrain
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_b = 8
+    sd = otrain.init_denoiser(C_IN, F, D_MODEL, FF, LAYERS, seed=0)
+    tr = otrain.PortTrainer(sd, lr=1e-4, opt="rmsprop")
+    sched = oddpm.make_schedule()
+    g = torch.Generator().manual_seed(1234)
+    cond = torch.randn(sample_b, F, C_IN, generator=g)
+    _, labels = otrain.synthetic_batch(sample_b, F, 23, 30, 1235)
+    x0 = torch.cat([labels[k] for k in (otrain._loss.COP, otrain._loss.FORCE, otrain._loss.TORQUE, otrain._loss.WRENCH)], dim=-1)
+
+    def step():
+        t = torch.randint(0, 1000, (sample_b,), generator=g)
+        eps = torch.randn(sample_b, F, 30, generator=g)
+        tr.step_denoiser(sched, cond, x0, t, eps, labels, LAYERS, HEADS)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    v = sample_b / dt
+    sample = f"{sample_b} windows per step (of the {PER_GPU_BATCH}-window GPU batch), {steps} timed steps, torch CPU fp32, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config(args.gpus, sample_b),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU port of the reference training-loop shape (train.py:240-284) on the builder-owned denoiser; the "
+                "reference has no diffusion model, so no stock reference code exists for this workload",
+    }))
+
+
+def cpu_baseline_leg() -> dict:
+    """Bounded CPU sample of the same workload (oracle port), ~10-30 s."""
+    import torch
+    from oracle import ddpm as oddpm
+    from oracle import train as otrain
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_b = 8
+    tr = otrain.PortTrainer(otrain.init_denoiser(C_IN, F, D_MODEL, FF, LAYERS, seed=0), lr=1e-4)
+    sched = oddpm.make_schedule()
+    g = torch.Generator().manual_seed(1234)
+    cond = torch.randn(sample_b, F, C_IN, generator=g)
+    _, labels = otrain.synthetic_batch(sample_b, F, 23, 30, 1235)
+    x0 = torch.cat([labels[k] for k in (otrain._loss.COP, otrain._loss.FORCE, otrain._loss.TORQUE, otrain._loss.WRENCH)], dim=-1)
+    times = []
+    for i in range(4):
+        t = torch.randint(0, 1000, (sample_b,), generator=g)
+        eps = torch.randn(sample_b, F, 30, generator=g)
+        t0 = time.perf_counter()
+        tr.step_denoiser(sched, cond, x0, t, eps, labels, LAYERS, HEADS)
+        times.append(time.perf_counter() - t0)
+    dt = statistics.mean(times[1:])
+    return {"value": sample_b / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_b} windows/step x 3 timed steps (1 warm-up) of the same denoiser training step, torch CPU fp32"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="windows per GPU per step")
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary sampling / elementwise roofline measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from inferbiomechanics_b200 import _lib, ops, parallel
+    from inferbiomechanics_b200.data.window_store import WindowStore
+    from inferbiomechanics_b200.diffusion import GaussianDiffusion
+    from inferbiomechanics_b200.models.DiffusionDenoiser import DiffusionDenoiser
+    from inferbiomechanics_b200.trainer import Trainer
+
+    rank, world, local = parallel.init_from_env("nccl")
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch
+    torch.manual_seed(0)
+    model = DiffusionDenoiser(frames=F, d_model=D_MODEL, num_heads=HEADS, dim_feedforward=FF, num_layers=LAYERS).to(dev)
+    diffusion = GaussianDiffusion(device=dev)
+    trainer = Trainer(model, opt_type="rmsprop", lr=1e-4, diffusion=diffusion, seed=1234)
+    n_batches = 4
+    store = WindowStore.synthetic(B * n_batches, F, 1, C_IN, "all_frames", seed=1234 + rank, device=dev)
+    idx_all = store.shard(0, 1)
+    batches = [idx_all[i * B:(i + 1) * B] for i in range(n_batches)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------ value: HBM-resident inputs ---------------------------------
+    for i in range(args.warmup):
+        trainer.train_step(store, batches[i % n_batches])
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        res = trainer.train_step(store, batches[i % n_batches])
+    e1.record()
+    barrier()
+    launches = _lib.launch_count - launches0
+    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = elapsed_ms.item() / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    clock_info = clocks.stop() if rank == 0 else None
+    final_loss = res[0].item()
+
+    # ------------------------------------------------ e2e: host buffers through the public call ---------------------
+    host = trainer.make_host_batch(B, seed=99 + rank)               # pinned CPU tensors (dict of 10 inputs + 4 labels)
+    for _ in range(2):
+        trainer.train_step_host(host["inputs"], host["labels"])
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss_host = trainer.train_step_host(host["inputs"], host["labels"])       # returns a python float (D2H read)
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (e2e_ms.item() / args.steps * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host["inputs"].values()) + sum(t.numel() * t.element_size() for t in host["labels"].values())
+
+    # ------------------------------------------------ roofline of the dominant kernel (tcgen05 GEMM) ----------------
+    pk = peaks()
+    gemm_ms, gemm_flops, n_gemm = trainer.profile_gemms(store, batches[0])
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    roofline = {"bound": "tensor", "kernel": "ibm::gemm::gemm_kernel (tcgen05.mma + TMA, all shapes of one training step)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": pk["_source"] + ", sustained figure (kernel timed inside a long step)",
+                "launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms_per_step,
+                "step_model_flops_per_window": 3 * 2.57e9}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": config(world, B),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 160,
+                "ms_per_step": e2e_ms.item() / args.steps, "api": "Trainer.train_step_host(inputs: Dict[str, pinned CPU Tensor], labels)"},
+        "gpu_launches": launches, "roofline": roofline, "final_loss": final_loss, "loss_host": loss_host,
+    }
+    if rank == 0:
+        out["clocks"] = clock_info
+    if not args.no_aux:
+        out["aux"] = trainer.aux_measurements(store, batches[0], pk, world)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_leg()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -176,6 +176,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp >= kEpiWarp0) {
     // ======================================= epilogue ========================================
     constexpr int CW = kOutF32 ? 32 : 64;           // columns per 128-byte staging row
+    static_assert(BN >= CW, "an epilogue chunk must not be wider than the accumulator tile");
     const int q = warp & 3;                         // TMEM lane quadrant this warp may access
     const int et = threadIdx.x - kEpiWarp0 * 32;    // 0..127
     const int r_local = q * 32 + lane;              // tile row == TMEM lane
@@ -401,7 +402,9 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   if (taps < 1) taps = 1;
   IBM_CHECK_ARG(taps == 1 || (!a_mn_major && K % taps == 0 && (K / taps) % 8 == 0), "gemm: taps needs K-major A and K/taps %% 8 == 0");
 
-  const int bn = pick_bn(N);
+  int bn = pick_bn(N);
+  if (b_mn_major && bn < 64) bn = 64;     // an MN-major SWIZZLE_128B atom is 64 elements wide
+  if (out_dtype == IBM_BF16 && bn < 64) bn = 64;   // bf16 epilogue chunks are 64 columns (one 128-byte staging row)
   const int64_t k_tap = K / taps;
   Args args;
   args.M = M; args.N = N;
@@ -454,7 +457,9 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
     case 256: IBM_GEMM_DISPATCH(256);
     case 128: IBM_GEMM_DISPATCH(128);
     case 64: IBM_GEMM_DISPATCH(64);
-    default: IBM_GEMM_DISPATCH(32);
+    default:                          // BN = 32 exists for fp32 outputs only (bf16 chunks are 64 columns wide)
+      if (accumulate) return launch<32, true, true>(ta, tb, td, args, grid, s);
+      return launch<32, true, false>(ta, tb, td, args, grid, s);
   }
 #undef IBM_GEMM_DISPATCH
 }

@@ -45,6 +45,10 @@ def _check(out, ref, bf16_out, what):
     (640, 512, 2048, "none", False),
     (130, 128, 208, "elu", False),
     (4096, 64, 72, "silu", False),
+    (6, 40, 1470, "tanh", False),            # narrow bf16 outputs (hidden sizes 40 / 24 of the golden FeedForward case)
+    (6, 24, 40, "tanh", False),
+    (200, 8, 64, "none", False),
+    (200, 12, 64, "none", True),
 ])
 def test_gemm_forward(M, N, K, act, out_f32):
     from inferbiomechanics_b200 import ops
@@ -82,7 +86,7 @@ def test_gemm_residual_and_dact():
         _check(out, ref, True, f"dact {act}")
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 128, 192), (1000, 1470, 512), (333, 512, 300), (640, 208, 512)])
+@pytest.mark.parametrize("M,N,K", [(256, 128, 192), (1000, 1470, 512), (333, 512, 300), (640, 208, 512), (6, 32, 30), (70, 24, 40)])
 def test_gemm_dgrad_b_mn_major(M, N, K):
     """dX[M,N] = dY[M,K] · W[K,N]  with W stored row-major [K, N] (MN-major B operand)."""
     from inferbiomechanics_b200 import ops
@@ -95,7 +99,7 @@ def test_gemm_dgrad_b_mn_major(M, N, K):
 
 
 @pytest.mark.parametrize("Mtok,Nout,Kin,split", [(512, 128, 256, 1), (4000, 512, 512, 0), (1111, 300, 512, 3),
-                                                 (2048, 512, 1472, 0), (6400, 30, 512, 0)])
+                                                 (2048, 512, 1472, 0), (6400, 30, 512, 0), (6, 30, 32, 0), (33, 48, 24, 0)])
 def test_gemm_wgrad_mn_mn_accumulate(Mtok, Nout, Kin, split):
     """dW[Nout,Kin] += dY[Mtok,Nout]^T · X[Mtok,Kin]: both operands MN-major, split-K TMA reduce-add."""
     from inferbiomechanics_b200 import ops
