@@ -89,7 +89,9 @@ loss_fwd_kernel(const LossParams p, float* __restrict__ result, float* __restric
   float rep[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   {
     const long long f = p.F - 1;
-    for (long long b = (long long)blockIdx.x * kLossThreads + t; b < p.B; b += (long long)gridDim.x * kLossThreads) {
+    // windows are dealt round-robin over BLOCKS (thread t of block j takes window j + t*grid), so every SM
+    // carries a few of these latency-bound rows next to its streaming work instead of a few blocks carrying all
+    for (long long b = (long long)blockIdx.x + (long long)t * gridDim.x; b < p.B; b += (long long)gridDim.x * kLossThreads) {
       float d[30];
       float of[6], lf[6];
 #pragma unroll

@@ -151,3 +151,197 @@ class Trainer:
         store.pack_feedforward(idx, self.eng.input_buffer(B))
         out = self.eng.forward(B)
         return ops.regression_loss_fwd(_views_ff(out, B, self.model.num_output_frames), _views30(lab), self.weights)
+
+
+# =====================================================================================================
+# Host-fed step (the e2e path), profiling helpers used by bench.py
+# =====================================================================================================
+def _make_host_batch(self, B: int, seed: int = 0):
+    """Synthetic pinned host tensors shaped like a reference DataLoader batch."""
+    from .keys import MODEL_INPUT_ORDER
+    g = torch.Generator().manual_seed(seed)
+    F = self.eng.F if self.is_denoiser else self.model.num_frames
+    hist = self.model.root_history_len * 3 if self.is_denoiser else self.model.stride * 3
+    widths = {"pos": 23, "vel": 23, "acc": 23, "rootLinearVelInRootFrame": 3, "rootAngularVelInRootFrame": 3,
+              "rootLinearAccInRootFrame": 3, "rootAngularAccInRootFrame": 3, "jointCentersInRootFrame": 36,
+              "rootPosHistoryInRootFrame": hist, "rootEulerHistoryInRootFrame": hist}
+    inputs = {k: torch.randn(B, F, widths[k], generator=g).pin_memory() for k in MODEL_INPUT_ORDER}
+    Fo = F if self.is_denoiser else self.model.num_output_frames
+    scale = {LOSS_QUANTITIES[0]: 1.0, LOSS_QUANTITIES[1]: 10.0, LOSS_QUANTITIES[2]: 1.0, LOSS_QUANTITIES[3]: 1.0}
+    labels = {k: (torch.randn(B, Fo, 12 if i == 3 else 6, generator=g) * scale[k]).pin_memory() for i, k in enumerate(LOSS_QUANTITIES)}
+    return {"inputs": inputs, "labels": labels}
+
+
+def _train_step_host(self, inputs, labels) -> float:
+    """One optimisation step fed from (pinned) host tensors: per-key async H2D copies, one packing kernel for the
+    ten inputs and one for the four label tensors, the native step, then a D2H read of the loss."""
+    from .keys import MODEL_INPUT_ORDER
+    dev = self.arena.device
+    B = inputs[MODEL_INPUT_ORDER[0]].shape[0]
+    key = ("host", B)
+    if key not in self._lab:
+        self._lab[key] = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in {**inputs, **labels}.items()}
+    stage = self._lab[key]
+    for k, v in {**inputs, **labels}.items():
+        stage[k].copy_(v, non_blocking=True)
+    F = stage[MODEL_INPUT_ORDER[0]].shape[1]
+    Fo = stage[LOSS_QUANTITIES[0]].shape[1]
+    if ("lab", B) not in self._lab:
+        self._lab[("lab", B)] = torch.empty(B, Fo, 30, dtype=torch.float32, device=dev)
+    lab = self._lab[("lab", B)]
+    ops.pack_inputs([stage[k].view(B * Fo, -1) for k in LOSS_QUANTITIES], B * Fo, Fo, out_f32=lab.view(B * Fo, 30))
+    srcs = [stage[k].view(B * F, -1) for k in MODEL_INPUT_ORDER]
+    self.arena.zero_grad()
+    self.bucketer.begin_step()
+    if self.is_denoiser:
+        eng = self.eng
+        xc = eng.xc(B, True)
+        ops.pack_inputs(srcs, B * F, F, out_bf16=xc, frame_stride=eng.ld_in, win_extra=0, col0=30)
+        result = self._finish_denoiser_step(B, lab)
+    else:
+        eng = self.eng
+        ops.pack_inputs(srcs, B * F, F, out_bf16=eng.input_buffer(B), frame_stride=self.model.frame_width,
+                        win_extra=eng.in_ld - self.model.input_size, col0=0)
+        result = self._finish_ff_step(B, lab)
+    return float(result[0].item())
+
+
+def _finish_denoiser_step(self, B: int, lab: torch.Tensor) -> torch.Tensor:
+    eng = self.eng
+    xc = eng.xc(B, True)
+    t = eng.t_buffer(B, True)
+    t.copy_(torch.randint(0, self.diffusion.T, (B,), device=t.device, generator=self._gen, dtype=torch.int32))
+    self.diffusion.q_sample(lab.view(B, -1), t, None, xt_bf16=xc, bf16_ld=eng.ld_in, seed=self.seed + self.rank, offset=self.step_count)
+    out = eng.forward(B, train=True)
+    outs, labs = _views30(out.view(B, eng.F, 32)), _views30(lab)
+    gviews = _views30(eng.dout(B).view(B, eng.F, 32))
+    result = self._result_ring[self.step_count % len(self._result_ring)]
+    ops.regression_loss_fwd(outs, labs, self.weights, COP_FORCE_THRESHOLD, result=result)
+    ops.regression_loss_bwd(outs, labs, self.weights, gviews, threshold=COP_FORCE_THRESHOLD)
+    eng.backward(B)
+    self.bucketer.finish()
+    self.optimizer_step()
+    return result
+
+
+def _finish_ff_step(self, B: int, lab: torch.Tensor) -> torch.Tensor:
+    eng = self.eng
+    out = eng.forward(B)
+    Fo = self.model.num_output_frames
+    outs, labs = _views_ff(out, B, Fo), _views30(lab)
+    gviews = _views_ff(eng.dout_buffer(B), B, Fo)
+    result = self._result_ring[self.step_count % len(self._result_ring)]
+    ops.regression_loss_fwd(outs, labs, self.weights, COP_FORCE_THRESHOLD, result=result)
+    ops.regression_loss_bwd(outs, labs, self.weights, gviews, threshold=COP_FORCE_THRESHOLD)
+    eng.backward(B)
+    self.bucketer.finish()
+    self.optimizer_step()
+    return result
+
+
+def _profile_gemms(self, store, idx):
+    """One extra training step with CUDA events around every tcgen05 GEMM launch (on the launching stream):
+    returns (total GEMM ms, total algorithmic FLOPs = 2*M*N*K per launch, number of launches)."""
+    real = ops.gemm
+    recs = []
+
+    def timed(A, Bm, out, M, N, K, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = real(A, Bm, out, M, N, K, **kw)
+        e1.record()
+        recs.append((e0, e1, 2.0 * M * N * K, (M, N, K)))
+        return r
+
+    ops.gemm = timed
+    try:
+        self.train_step(store, idx)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = real
+    self.last_gemm_records = [(e0.elapsed_time(e1), fl, shp) for e0, e1, fl, shp in recs]
+    return sum(r[0] for r in self.last_gemm_records), sum(r[1] for r in self.last_gemm_records), len(recs)
+
+
+def _time_kernel(fn, iters: int = 20) -> float:
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def _aux_measurements(self, store, idx, pk, world):
+    """HBM-bound kernels against the measured copy bandwidth, and reverse-sampling throughput
+    (BASELINE configs[3]: 512 windows per GPU, graph-replayed steps).  Inputs (>= 300 MB) exceed L2."""
+    B = idx.numel()
+    dev = self.arena.device
+    hbm = pk["hbm_gbs"]
+    out = {}
+    if self.is_denoiser:
+        eng, F = self.eng, self.eng.F
+        # stream of 16384 windows (819 200 rows): every operand set is > 200 MB, i.e. larger than the 126 MB L2,
+        # so consecutive timed launches cannot re-use each other's lines
+        Bb = 16384
+        M = Bb * F
+        rows = torch.randn(M, 32, device=dev)
+        lab = torch.randn(Bb, F, 30, device=dev) * 5
+        outs, labs = _views30(rows.view(Bb, F, 32)), _views30(lab)
+        res = torch.zeros(40, device=dev)
+        g16buf = torch.zeros(M, 32, dtype=torch.bfloat16, device=dev)
+        g16 = _views30(g16buf.view(Bb, F, 32))
+
+        def entry(ms, by):
+            return {"bound": "hbm", "ms": ms, "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm,
+                    "algorithmic_bytes": by, "rows": M}
+
+        out["loss_fwd"] = entry(_time_kernel(lambda: ops.regression_loss_fwd(outs, labs, self.weights, result=res)), M * 240.0)
+        out["loss_bwd_bf16"] = entry(_time_kernel(lambda: ops.regression_loss_bwd(outs, labs, self.weights, g16)), M * 300.0)
+        x0 = lab.view(Bb, -1)
+        eps = torch.randn_like(x0)
+        xt = torch.empty_like(x0)
+        t = torch.randint(0, 1000, (Bb,), device=dev, dtype=torch.int32)
+        d = self.diffusion
+        out["q_sample"] = entry(_time_kernel(lambda: ops.q_sample(x0, eps, t, d.sqrt_abar, d.sqrt_one_minus_abar, xt_f32=xt)), M * 360.0)
+        tdev = torch.full((1,), 500, dtype=torch.int32, device=dev)
+        xp = torch.empty(M, 30, device=dev)
+        out["posterior_step"] = entry(_time_kernel(lambda: ops.posterior_step(rows, 32, x0.view(M, 30), eps.view(M, 30), tdev, d.coef_x0,
+                                                                              d.coef_xt, d.sigma, M, x_prev=xp)), M * 480.0)
+        del rows, lab, g16buf, eps, xt, xp
+        # per-shape table of the GEMM launches of one training step (from profile_gemms)
+        shapes = {}
+        for ms, fl, shp in getattr(self, "last_gemm_records", []):
+            e = shapes.setdefault("x".join(str(v) for v in shp), [0, 0.0, 0.0])
+            e[0] += 1; e[1] += ms; e[2] += fl
+        out["gemm_shapes_MxNxK"] = {k: {"launches": v[0], "ms": round(v[1], 4), "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1)}
+                                    for k, v in shapes.items()}
+        # reverse sampling: 512 windows per GPU, CUDA-graph replays (2 steps per replay), no collective
+        from .diffusion import GaussianDiffusion
+        sb, steps = 512, 200
+        gd = GaussianDiffusion(num_timesteps=steps, device=dev)
+        eng.xc(sb, False)[:, 30:30 + eng.c_in] = torch.randn(sb * F, eng.c_in, device=dev).to(torch.bfloat16)
+        gd.sample(self.model, sb, seed=1)                       # builds the graph
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gd.sample(self.model, sb, seed=1)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out["sampling"] = {"metric": "denoise_window_steps_per_sec", "value": world * sb * steps / (ms * 1e-3), "unit": "window-steps/s",
+                           "windows_per_gpu": sb, "steps_timed": steps, "ms_per_step": ms / steps,
+                           "note": "BASELINE configs[3] shape (512 windows/GPU); 1000-step run = 5x this loop; weak scaling, no collective"}
+    return out
+
+
+Trainer.make_host_batch = _make_host_batch
+Trainer.train_step_host = _train_step_host
+Trainer._finish_denoiser_step = _finish_denoiser_step
+Trainer._finish_ff_step = _finish_ff_step
+Trainer.profile_gemms = _profile_gemms
+Trainer.aux_measurements = _aux_measurements
