@@ -28,19 +28,21 @@ using namespace ptx;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;      // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 384;      // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kEpiWarp0 = 4;
 constexpr uint32_t kEpiBarrier = 1;
 constexpr int kStageA = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int kOutStage = BLOCK_M * 128;                // 128 rows x 128 B = 16 KB
 
-template <int BN>
+template <int BN, bool AUX>
 struct Cfg {
   static constexpr int kStageB = BN * BLOCK_K * 2;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  // AUX kernels give one operand stage up for a 3-deep ring of aux chunk buffers (prefetched 2-3 chunks ahead)
+  static constexpr int kStages = AUX ? ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int kAuxBufs = AUX ? 3 : 0;
   static constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmem = 1024 /*align slack*/ + kStages * (kStageA + kStageB) + 2 * kOutStage + BN * 4 + 256;
+  static constexpr int kSmem = 1024 /*align slack*/ + kStages * (kStageA + kStageB) + (2 + kAuxBufs) * kOutStage + BN * 4 + 256;
 };
 
 struct Args {
@@ -61,22 +63,95 @@ __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int nstages
   if (++stage == nstages) { stage = 0; phase ^= 1u; }
 }
 
-template <int BN, bool kOutF32, bool kAccum>
+
+// ---- epilogue math, specialised at compile time on the activation (no per-element switch) ----------
+template <int ACT> __device__ __forceinline__ float act_t(float x) { return act_apply(x, ACT); }
+template <int ACT> __device__ __forceinline__ float dact_t(float y) { return act_grad_from_output(y, ACT); }
+
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int ACT, int PT>
+__device__ __forceinline__ void epi_plain(float (&v)[PT], const float* bs) {
+#pragma unroll
+  for (int j = 0; j < PT; ++j) v[j] = act_t<ACT>(v[j] + bs[j]);
+}
+template <int PT>
+__device__ __forceinline__ void epi_dispatch_plain(float (&v)[PT], const float* bs, int act) {
+  switch (act) {
+    case IBM_ACT_NONE: epi_plain<IBM_ACT_NONE, PT>(v, bs); break;
+    case IBM_ACT_RELU: epi_plain<IBM_ACT_RELU, PT>(v, bs); break;
+    case IBM_ACT_SIGMOID: epi_plain<IBM_ACT_SIGMOID, PT>(v, bs); break;
+    case IBM_ACT_TANH: epi_plain<IBM_ACT_TANH, PT>(v, bs); break;
+    case IBM_ACT_ELU: epi_plain<IBM_ACT_ELU, PT>(v, bs); break;
+    default: epi_plain<IBM_ACT_SILU, PT>(v, bs); break;
+  }
+}
+// MODE 1: out = act(acc + bias) + aux;  MODE 2: out = (acc + bias) * act'(aux).  aux: bf16, 8 per 16-byte piece.
+template <int ACT, int MODE, int PT>
+__device__ __forceinline__ void epi_aux(float (&v)[PT], const float* bs, uint32_t xrow, int half, int rsw) {
+#pragma unroll
+  for (int jj = 0; jj < PT / 8; ++jj) {
+    const uint4 u = ld_shared_v4(xrow + (((half * (PT / 8) + jj) ^ rsw) << 4));
+    float y[8];
+    float2 t;
+    t = unpack_bf16x2(u.x); y[0] = t.x; y[1] = t.y;
+    t = unpack_bf16x2(u.y); y[2] = t.x; y[3] = t.y;
+    t = unpack_bf16x2(u.z); y[4] = t.x; y[5] = t.y;
+    t = unpack_bf16x2(u.w); y[6] = t.x; y[7] = t.y;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x = v[8 * jj + e] + bs[8 * jj + e];
+      v[8 * jj + e] = MODE == 1 ? act_t<ACT>(x) + y[e] : x * dact_t<ACT>(y[e]);
+    }
+  }
+}
+template <int PT>
+__device__ __forceinline__ void epi_dispatch_aux(float (&v)[PT], const float* bs, uint32_t xrow, int half, int rsw, int act, int mode) {
+  if constexpr (PT % 8 == 0) {
+    if (mode == 1) {
+      switch (act) {
+        case IBM_ACT_NONE: epi_aux<IBM_ACT_NONE, 1, PT>(v, bs, xrow, half, rsw); break;
+        case IBM_ACT_RELU: epi_aux<IBM_ACT_RELU, 1, PT>(v, bs, xrow, half, rsw); break;
+        default: epi_aux<IBM_ACT_ELU, 1, PT>(v, bs, xrow, half, rsw); break;
+      }
+    } else {
+      switch (act) {
+        case IBM_ACT_NONE: epi_aux<IBM_ACT_NONE, 2, PT>(v, bs, xrow, half, rsw); break;
+        case IBM_ACT_RELU: epi_aux<IBM_ACT_RELU, 2, PT>(v, bs, xrow, half, rsw); break;
+        case IBM_ACT_SIGMOID: epi_aux<IBM_ACT_SIGMOID, 2, PT>(v, bs, xrow, half, rsw); break;
+        case IBM_ACT_TANH: epi_aux<IBM_ACT_TANH, 2, PT>(v, bs, xrow, half, rsw); break;
+        default: epi_aux<IBM_ACT_ELU, 2, PT>(v, bs, xrow, half, rsw); break;
+      }
+    }
+  }
+}
+
+template <int BN, bool kOutF32, bool kAccum, bool kAux>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmD, const Args args) {
-  using C = Cfg<BN>;
+            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const Args args) {
+  using C = Cfg<BN, kAux>;
+  static_assert(!kAux || (!kOutF32 && !kAccum), "TMA-staged aux tiles exist for bf16 outputs only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + C::kStages * kStageA;
   uint8_t* smem_out = smem_b + C::kStages * C::kStageB;              // 2 x 16 KB, 1024-aligned
-  float* smem_bias = reinterpret_cast<float*>(smem_out + 2 * kOutStage);
+  uint8_t* smem_aux = smem_out + 2 * kOutStage;                      // kAuxBufs x 16 KB, 1024-aligned
+  float* smem_bias = reinterpret_cast<float*>(smem_aux + C::kAuxBufs * kOutStage);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_bias + BN);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tfull_bar = empty_bar + C::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -84,10 +159,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmD);
+    prefetch_tmap(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads / 32); }
+    for (int i = 0; i < 3; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -104,6 +181,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = kStageA + C::kStageB;
+      const bool prefetch_aux = kAux;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int split = w % args.splits;
         const int tile = w / args.splits;
@@ -111,6 +189,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int m0 = tm * BLOCK_M, n0 = tn * BN;
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
+        if (prefetch_aux) {
+          // the epilogue of this tile runs ~1.5 tile-times from now: pull its aux tile into L2 so the
+          // epilogue's one-chunk-ahead TMA loads see L2 latency, not DRAM latency
+          for (int c = 0; c < BN && n0 + c < args.N; c += 64) tma_prefetch_l2_2d(&tmX, n0 + c, m0);
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -175,14 +258,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= kEpiWarp0) {
     // ======================================= epilogue ========================================
+    // 8 warps: warp w may touch TMEM lanes [32*(w%4), +32); the two warps of a lane quadrant split each
+    // 128-byte chunk row between them (PT columns each), so the per-chunk instruction stream is half as long.
     constexpr int CW = kOutF32 ? 32 : 64;           // columns per 128-byte staging row
+    constexpr int PT = CW / 2;                      // columns per thread per chunk
     static_assert(BN >= CW, "an epilogue chunk must not be wider than the accumulator tile");
     const int q = warp & 3;                         // TMEM lane quadrant this warp may access
-    const int et = threadIdx.x - kEpiWarp0 * 32;    // 0..127
+    const int half = (warp - kEpiWarp0) >> 2;       // which half of the chunk's columns
+    const int et = threadIdx.x - kEpiWarp0 * 32;    // 0..255
     const int r_local = q * 32 + lane;              // tile row == TMEM lane
+    const int rsw = r_local & 7;                    // SWIZZLE_128B: 16-byte piece j of row r lives at piece j ^ (r & 7)
     const bool leader = (et == 0);
+    // bf16 aux tiles (residual / saved activation) stream through a 3-deep ring of TMA-loaded chunk buffers,
+    // issued 3 chunks ahead by the epilogue leader (and pulled into L2 a tile ahead by the producer), so the
+    // epilogue never waits on a global load nor on the completion of its own stores
     int as = 0, ob = 0;
     uint32_t aphase = 0;
+    int xg = 0;                                     // chunks consumed so far by this CTA (aux ring position)
+    int pw = blockIdx.x, pch = 0;                   // prefetch cursor: (work item, chunk) of the next aux load
+    auto chunks_of = [&](int w) {
+      const int n0w = ((w / args.splits) % args.tiles_n) * BN;
+      return ((int)min((int64_t)BN, args.N - n0w) + CW - 1) / CW;
+    };
+    auto issue_aux = [&](int buf) {                 // leader only
+      if (pw >= total_work) return;
+      const int t2 = pw / args.splits;
+      mbar_arrive_expect_tx(&aux_bar[buf], kOutStage);
+      tma_load_2d(smem_aux + buf * kOutStage, &tmX, &aux_bar[buf], (t2 % args.tiles_n) * BN + pch * CW, (t2 / args.tiles_n) * BLOCK_M);
+      if (++pch == chunks_of(pw)) { pch = 0; pw += gridDim.x; }
+    };
+    if (kAux && leader) {
+      for (int i = 0; i < 3; ++i) issue_aux(i);
+    }
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int tile = w / args.splits;
       const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
@@ -201,9 +308,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
 
       for (int ch = 0; ch < n_chunks; ++ch) {
-        float v[CW];
-        tmem_ld_32x32(tmem_acc + ch * CW, reinterpret_cast<uint32_t*>(v));
-        if (CW == 64) tmem_ld_32x32(tmem_acc + ch * CW + 32, reinterpret_cast<uint32_t*>(v) + 32);
+        float v[PT];
+        if (kOutF32) tmem_ld_32x16(tmem_acc + ch * CW + half * PT, reinterpret_cast<uint32_t*>(v));
+        else tmem_ld_32x32(tmem_acc + ch * CW + half * PT, reinterpret_cast<uint32_t*>(v));
+        const int c0 = n0 + ch * CW;               // global column of the chunk
+        const uint32_t srow = smem_u32(smem_out + ob * kOutStage + r_local * 128);
+        const int xb = xg % 3;
+        const uint32_t xrow = smem_u32(smem_aux + xb * kOutStage + r_local * 128);
+        if (kAux) mbar_wait(&aux_bar[xb], (uint32_t)((xg / 3) & 1));     // this chunk's aux tile has landed
         tmem_ld_wait();
         if (ch == n_chunks - 1) {
           // all TMEM reads of this accumulator are done → hand the buffer back to the MMA warp
@@ -216,80 +328,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (leader) tma_wait_group_read<1>();
         named_bar_sync(kEpiBarrier, kEpiThreads);
 
-        const int c0 = n0 + ch * CW;               // global column of v[0]
         if (!kAccum) {
-          const float* bs = smem_bias + ch * CW;
-          const int act = args.act;
-          if (args.aux_mode == 2) {
-            // dgrad through an activation: out = (acc + bias) * act'(aux), aux = saved activation output
-            const __nv_bfloat16* ap = args.aux + row * args.ldaux + c0;
-#pragma unroll
-            for (int j = 0; j < CW; j += 8) {
-              float y[8];
-              if (row < args.M && c0 + j + 8 <= args.N) {
-                uint4 u = *reinterpret_cast<const uint4*>(ap + j);
-                float2 t;
-                t = unpack_bf16x2(u.x); y[0] = t.x; y[1] = t.y;
-                t = unpack_bf16x2(u.y); y[2] = t.x; y[3] = t.y;
-                t = unpack_bf16x2(u.z); y[4] = t.x; y[5] = t.y;
-                t = unpack_bf16x2(u.w); y[6] = t.x; y[7] = t.y;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) y[e] = (row < args.M && c0 + j + e < args.N) ? __bfloat162float(ap[j + e]) : 0.f;
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[j + e] = (v[j + e] + bs[j + e]) * act_grad_from_output(y[e], act);
-            }
+          const float* bs = smem_bias + ch * CW + half * PT;
+          if (kAux) {
+            epi_dispatch_aux<PT>(v, bs, xrow, half, rsw, args.act, args.aux_mode);
           } else {
-            switch (act) {
-              case IBM_ACT_RELU:
+            epi_dispatch_plain<PT>(v, bs, args.act);
+            if (args.aux_mode != 0) {
+              // fp32-output fallback: aux read straight from global memory (not on the training path)
+              const __nv_bfloat16* ap = args.aux + row * args.ldaux + c0 + half * PT;
 #pragma unroll
-                for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j] + bs[j], 0.f);
-                break;
-              case IBM_ACT_NONE:
-#pragma unroll
-                for (int j = 0; j < CW; ++j) v[j] = v[j] + bs[j];
-                break;
-              default:
-#pragma unroll
-                for (int j = 0; j < CW; ++j) v[j] = act_apply(v[j] + bs[j], act);
-                break;
-            }
-            if (args.aux_mode == 1) {
-              // residual: out = act(acc + bias) + aux
-              const __nv_bfloat16* ap = args.aux + row * args.ldaux + c0;
-#pragma unroll
-              for (int j = 0; j < CW; j += 8) {
-                if (row < args.M && c0 + j + 8 <= args.N) {
-                  uint4 u = *reinterpret_cast<const uint4*>(ap + j);
-                  float2 t;
-                  t = unpack_bf16x2(u.x); v[j + 0] += t.x; v[j + 1] += t.y;
-                  t = unpack_bf16x2(u.y); v[j + 2] += t.x; v[j + 3] += t.y;
-                  t = unpack_bf16x2(u.z); v[j + 4] += t.x; v[j + 5] += t.y;
-                  t = unpack_bf16x2(u.w); v[j + 6] += t.x; v[j + 7] += t.y;
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (row < args.M && c0 + j + e < args.N) v[j + e] += __bfloat162float(ap[j + e]);
-                }
+              for (int j = 0; j < PT; ++j) {
+                const float y = (row < args.M && c0 + half * PT + j < args.N) ? __bfloat162float(ap[j]) : 0.f;
+                v[j] = args.aux_mode == 1 ? v[j] + y : v[j] * act_grad_from_output(y, args.act);
               }
             }
           }
         }
-        // registers → swizzled staging rows (16-byte chunk index XOR (row & 7): conflict-free, and
-        // exactly the SWIZZLE_128B pattern the store tensor map expects)
-        uint8_t* srow = smem_out + ob * kOutStage + r_local * 128;
+        // registers → swizzled staging rows: this thread owns 16-byte pieces half*4 … half*4+3 of its row
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int jj = 0; jj < 4; ++jj) {
           uint4 pk;
           if (kOutF32) {
-            pk = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                            __float_as_uint(v[4 * j + 3]));
+            pk = make_uint4(__float_as_uint(v[4 * jj]), __float_as_uint(v[4 * jj + 1]), __float_as_uint(v[4 * jj + 2]),
+                            __float_as_uint(v[4 * jj + 3]));
           } else {
-            pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            pk = make_uint4(pack_bf16x2(v[8 * jj], v[8 * jj + 1]), pack_bf16x2(v[8 * jj + 2], v[8 * jj + 3]),
+                            pack_bf16x2(v[8 * jj + 4], v[8 * jj + 5]), pack_bf16x2(v[8 * jj + 6], v[8 * jj + 7]));
           }
-          *reinterpret_cast<uint4*>(srow + ((j ^ (r_local & 7)) << 4)) = pk;
+          st_shared_v4(srow + (((half * 4 + jj) ^ rsw) << 4), pk);
         }
         fence_proxy_async_smem();
         named_bar_sync(kEpiBarrier, kEpiThreads);
@@ -297,8 +364,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (kAccum) tma_reduce_add_2d(&tmD, smem_out + ob * kOutStage, c0, m0);
           else tma_store_2d(&tmD, smem_out + ob * kOutStage, c0, m0);
           tma_commit_group();
+          if (kAux) issue_aux(xb);                // every thread is past the barrier: aux buffer xb is free again
         }
         ob ^= 1;
+        ++xg;
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
@@ -354,15 +423,16 @@ static int make_map(CUtensorMap* map, const void* base, bool f32, int64_t inner,
   return IBM_OK;
 }
 
-template <int BN, bool F32, bool ACC>
-static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const Args& args, int grid, cudaStream_t s) {
+template <int BN, bool F32, bool ACC, bool AUX = false>
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& x, const Args& args, int grid,
+                  cudaStream_t s) {
   static bool attr_set = false;     // per instantiation
-  auto kern = gemm_kernel<BN, F32, ACC>;
+  auto kern = gemm_kernel<BN, F32, ACC, AUX>;
   if (!attr_set) {
-    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, AUX>::kSmem));
     attr_set = true;
   }
-  kern<<<grid, kThreads, Cfg<BN>::kSmem, s>>>(a, b, d, args);
+  kern<<<grid, kThreads, Cfg<BN, AUX>::kSmem, s>>>(a, b, d, x, args);
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }
@@ -443,23 +513,29 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   const bool f32 = out_dtype == IBM_F32;
   rc = make_map(&td, D, f32, N, M, ldd, f32 ? 32 : 64, BLOCK_M);
   if (rc) return rc;
+  CUtensorMap tx = td;                       // aux tile map (bf16 [M,N], same 64 x 128 box as the bf16 store)
+  if (aux_mode != 0 && !f32 && !accumulate) {
+    rc = make_map(&tx, aux, false, N, M, ldaux, 64, BLOCK_M);
+    if (rc) return rc;
+  }
 
   const int64_t work = (int64_t)args.tiles_m * args.tiles_n * args.splits;
   const int grid = (int)(work < sms ? work : sms);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define IBM_GEMM_DISPATCH(BNV)                                                   \
   do {                                                                           \
-    if (accumulate) return launch<BNV, true, true>(ta, tb, td, args, grid, s);   \
-    if (f32) return launch<BNV, true, false>(ta, tb, td, args, grid, s);         \
-    return launch<BNV, false, false>(ta, tb, td, args, grid, s);                 \
+    if (accumulate) return launch<BNV, true, true>(ta, tb, td, tx, args, grid, s);   \
+    if (f32) return launch<BNV, true, false>(ta, tb, td, tx, args, grid, s);         \
+    if (aux_mode != 0) return launch<BNV, false, false, true>(ta, tb, td, tx, args, grid, s); \
+    return launch<BNV, false, false>(ta, tb, td, tx, args, grid, s);                 \
   } while (0)
   switch (bn) {
     case 256: IBM_GEMM_DISPATCH(256);
     case 128: IBM_GEMM_DISPATCH(128);
     case 64: IBM_GEMM_DISPATCH(64);
     default:                          // BN = 32 exists for fp32 outputs only (bf16 chunks are 64 columns wide)
-      if (accumulate) return launch<32, true, true>(ta, tb, td, args, grid, s);
-      return launch<32, true, false>(ta, tb, td, args, grid, s);
+      if (accumulate) return launch<32, true, true>(ta, tb, td, tx, args, grid, s);
+      return launch<32, true, false>(ta, tb, td, tx, args, grid, s);
   }
 #undef IBM_GEMM_DISPATCH
 }

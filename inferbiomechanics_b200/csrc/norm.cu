@@ -9,8 +9,10 @@ namespace ibm {
 constexpr int kThreads = 256;          // 8 rows per block-iteration
 constexpr int kMaxChunks = 4;          // row length <= 4 * 32 lanes * 8 = 1024 columns
 
-// each lane owns chunks of 8 consecutive columns: columns (k*32 + lane)*8 … +7
-template <int CH>
+// each lane owns chunks of 8 consecutive columns: columns (k*32 + lane)*8 … +7.  A warp handles RPW
+// rows per iteration with all their loads issued before the first reduction (memory-level parallelism:
+// one row per warp left the kernel latency-bound at ~30 % of HBM bandwidth, see profiles/r01a_*).
+template <int CH, int RPW>
 __global__ void __launch_bounds__(kThreads)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ y, long long ld,
                      const float* __restrict__ gamma, const float* __restrict__ beta, long long M, int d, float eps,
@@ -18,45 +20,72 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float inv_d = 1.f / (float)d;
-  for (long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
-    float v[CH][8];
-    float sum = 0.f;
+  // gamma/beta of this lane's columns live in registers for the whole kernel (re-loading them per row made the
+  // kernel LSU-bound: 32 scalar loads per row per lane, see profiles/r01a)
+  float gm[CH][8], bt[CH][8];
 #pragma unroll
-    for (int k = 0; k < CH; ++k) {
-      const int c = (k * 32 + lane) * 8;
-      if (c < ld) {
-        uint4 u = ld_stream16(s + m * ld + c);
-        float2 a;
-        a = unpack_bf16x2(u.x); v[k][0] = a.x; v[k][1] = a.y;
-        a = unpack_bf16x2(u.y); v[k][2] = a.x; v[k][3] = a.y;
-        a = unpack_bf16x2(u.z); v[k][4] = a.x; v[k][5] = a.y;
-        a = unpack_bf16x2(u.w); v[k][6] = a.x; v[k][7] = a.y;
+  for (int k = 0; k < CH; ++k) {
+    const int c = (k * 32 + lane) * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { if (c + j >= d) v[k][j] = 0.f; sum += v[k][j]; }
-      } else {
+    for (int j = 0; j < 8; ++j) {
+      gm[k][j] = (c + j < d) ? __ldg(gamma + c + j) : 0.f;
+      bt[k][j] = (c + j < d) ? __ldg(beta + c + j) : 0.f;
+    }
+  }
+  for (long long m0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW; m0 < M; m0 += warps * RPW) {
+    float v[RPW][CH][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
+    for (int r = 0; r < RPW; ++r) {
+      const long long m = m0 + r;
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const int c = (k * 32 + lane) * 8;
+        if (m < M && c < ld) {
+          uint4 u = ld_stream16(s + m * ld + c);
+          float2 a;
+          a = unpack_bf16x2(u.x); v[r][k][0] = a.x; v[r][k][1] = a.y;
+          a = unpack_bf16x2(u.y); v[r][k][2] = a.x; v[r][k][3] = a.y;
+          a = unpack_bf16x2(u.z); v[r][k][4] = a.x; v[r][k][5] = a.y;
+          a = unpack_bf16x2(u.w); v[r][k][6] = a.x; v[r][k][7] = a.y;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[r][k][j] = 0.f;
+        }
       }
     }
-    const float mu = warp_sum(sum) * inv_d;
-    float sq = 0.f;
 #pragma unroll
-    for (int k = 0; k < CH; ++k) {
-      const int c = (k * 32 + lane) * 8;
+    for (int r = 0; r < RPW; ++r) {
+      const long long m = m0 + r;
+      float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (c + j < d) { float t = v[k][j] - mu; sq = fmaf(t, t, sq); }
-    }
-    const float rs = rsqrtf(warp_sum(sq) * inv_d + eps);
-    if (lane == 0) { if (mean) mean[m] = mu; if (rstd) rstd[m] = rs; }
+      for (int k = 0; k < CH; ++k) {
+        const int c = (k * 32 + lane) * 8;
 #pragma unroll
-    for (int k = 0; k < CH; ++k) {
-      const int c = (k * 32 + lane) * 8;
-      if (c < ld) {
-        float o[8];
+        for (int j = 0; j < 8; ++j) { if (c + j >= d) v[r][k][j] = 0.f; sum += v[r][k][j]; }
+      }
+      const float mu = warp_sum(sum) * inv_d;
+      float sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (c + j < d) ? fmaf((v[k][j] - mu) * rs, __ldg(gamma + c + j), __ldg(beta + c + j)) : 0.f;
-        st_stream16(y + m * ld + c, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                               pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+      for (int k = 0; k < CH; ++k) {
+        const int c = (k * 32 + lane) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (c + j < d) { float t = v[r][k][j] - mu; sq = fmaf(t, t, sq); }
+      }
+      const float rs = rsqrtf(warp_sum(sq) * inv_d + eps);
+      if (m < M) {
+        if (lane == 0) { if (mean) mean[m] = mu; if (rstd) rstd[m] = rs; }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          const int c = (k * 32 + lane) * 8;
+          if (c < ld) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = (c + j < d) ? fmaf((v[r][k][j] - mu) * rs, gm[k][j], bt[k][j]) : 0.f;
+            st_stream16(y + m * ld + c, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                   pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+          }
+        }
       }
     }
   }
@@ -175,10 +204,10 @@ extern "C" int ibm_layernorm_fwd(const void* s, void* y, int64_t ld, const float
   auto* yp = static_cast<__nv_bfloat16*>(y);
   const int grid = rows_grid(M);
   switch (ch) {
-    case 1: layernorm_fwd_kernel<1><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
-    case 2: layernorm_fwd_kernel<2><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
-    case 3: layernorm_fwd_kernel<3><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
-    default: layernorm_fwd_kernel<4><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
+    case 1: layernorm_fwd_kernel<1, 4><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
+    case 2: layernorm_fwd_kernel<2, 2><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
+    case 3: layernorm_fwd_kernel<3, 1><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
+    default: layernorm_fwd_kernel<4, 1><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
   }
   IBM_LAUNCH_CHECK();
   return IBM_OK;

@@ -1,0 +1,197 @@
+"""Drop-in ``TransformerBaseline`` (forward / analysis pass) on libibm_b200.
+
+Constructor signature, sub-module names and ``state_dict`` keys follow
+``/root/reference/src/models/TransformerBaseline.py:8-148`` (``temporal_embedding.embedding.weight``,
+``transformer_layers.{l}.multihead_attention.in_proj_weight`` …, ``fc.*``,
+``com_attention.{query,key}_linear.*``; fp64 parameters by default) so a reference checkpoint loads
+unchanged.  ``forward`` reproduces lines 104-148: inputs are (B, C, T) tensors keyed ``pos, vel, acc,
+comPos, comVel, comAcc`` (the three COM keys do not exist in the reference's ``InputDataKeys`` — SURVEY
+§0.3 — and are defined in ``inferbiomechanics_b200.keys``), learned temporal embedding concatenated,
+3 post-LN encoder layers, ``fc`` head, unscaled single-head "CoM blend" attention.
+
+B200 mapping: d = 108 is padded to 112 columns and each 36-wide head to 48 so every row is a
+16-byte multiple (TMA-legal) and head slices are 16-byte aligned; the pads carry exact zeros (zero
+weight rows/columns), so results are those of the unpadded model.  GEMMs run in bf16 on tcgen05 with
+fp32 accumulation; the reference computes in fp64 — tolerance stated in tests/test_gpu_transformer.py.
+The whole sequence (T <= 256) of a (window, head) stays in shared memory; long streams shard by window.
+
+Scope: inference (BASELINE configs[4], the analyze pass).  Training this model is not wired in the
+reference CLI either (it is imported nowhere); outputs carry no autograd graph.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+from ..keys import InputDataKeys, OutputDataKeys
+
+BF16 = torch.bfloat16
+
+
+class TransformerLayer(nn.Module):
+    """Parameter container with the reference layer's module names (TransformerBaseline.py:8-22)."""
+
+    def __init__(self, timestep_vector_dim: int, num_heads: int, dim_feedforward: int, dropout: float, dtype=torch.float64):
+        super().__init__()
+        self.multihead_attention = nn.MultiheadAttention(timestep_vector_dim, num_heads, dropout=dropout, batch_first=True, dtype=dtype)
+        self.feedforward = nn.Sequential(nn.Linear(timestep_vector_dim, dim_feedforward, dtype=dtype), nn.ReLU(),
+                                         nn.Linear(dim_feedforward, timestep_vector_dim, dtype=dtype))
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(timestep_vector_dim, dtype=dtype)
+        self.norm2 = nn.LayerNorm(timestep_vector_dim, dtype=dtype)
+
+
+class TemporalEmbedding(nn.Module):
+    def __init__(self, window_size: int, embedding_dim: int, dtype=torch.float64):
+        super().__init__()
+        self.embedding = nn.Embedding(window_size, embedding_dim, dtype=dtype)
+
+
+class SimpleAttention(nn.Module):
+    def __init__(self, key_query_dim: int, dtype=torch.float64):
+        super().__init__()
+        self.query_linear = nn.Linear(key_query_dim, key_query_dim, dtype=dtype)
+        self.key_linear = nn.Linear(key_query_dim, key_query_dim, dtype=dtype)
+
+
+def _pad_head(n: int) -> int:
+    for c in (32, 48, 64):
+        if n <= c:
+            return c
+    raise NotImplementedError(f"head_dim {n} > 64 is not supported by the attention kernel")
+
+
+class TransformerBaseline(nn.Module):
+    timestep_vector_dim: int
+    window_size: int
+    temporal_embedding_dim: int
+    output_vector_dim: int
+
+    def __init__(self, dofs: int, window_size: int, temporal_embedding_dim: int = 30, num_layers: int = 3, num_heads: int = 3,
+                 dim_feedforward: int = 60, dropout: float = 0.0, dtype=torch.float64):
+        super().__init__()
+        self.timestep_vector_dim = (dofs * 3) + (3 * 3) + temporal_embedding_dim
+        self.output_vector_dim = (2 + 3 + 6)
+        self.window_size = window_size
+        self.temporal_embedding_dim = temporal_embedding_dim
+        self.num_heads, self.dim_feedforward, self.num_layers, self.dofs = num_heads, dim_feedforward, num_layers, dofs
+        self.temporal_embedding = TemporalEmbedding(window_size, temporal_embedding_dim, dtype=dtype)
+        self.transformer_layers = nn.ModuleList([
+            TransformerLayer(self.timestep_vector_dim, num_heads, dim_feedforward, dropout, dtype=dtype) for _ in range(num_layers)])
+        self.fc = nn.Linear(self.timestep_vector_dim, self.output_vector_dim, dtype=dtype)
+        self.contact_sigmoid = nn.Sigmoid()
+        self.com_attention = SimpleAttention(self.timestep_vector_dim)          # reference leaves this at its fp64 default
+        self._prep = None
+        self._prep_version = None
+        self._bufs: Dict[int, Dict[str, torch.Tensor]] = {}
+
+    # ---- padded bf16 weights --------------------------------------------------------------------------
+    def _prepare(self, dev):
+        ver = sum(p._version for p in self.parameters()) + sum(hash(p.data_ptr()) % 1000003 for p in self.parameters())
+        if self._prep is not None and self._prep_version == ver:
+            return self._prep
+        d, H, ff = self.timestep_vector_dim, self.num_heads, self.dim_feedforward
+        hd = d // H
+        dp, hp, fp = ops.round_up(d, 8), _pad_head(hd), ops.round_up(ff, 8)
+        if dp != 112:
+            raise NotImplementedError(f"the CoM-blend attention kernel is built for d=108 (padded 112); got d={d}")
+
+        def padw(w, rows, cols):
+            out = torch.zeros(rows, cols, dtype=BF16, device=dev)
+            out[:w.shape[0], :w.shape[1]] = w.detach().to(dev, torch.float32).to(BF16)
+            return out
+
+        def padb(b, n):
+            out = torch.zeros(n, dtype=torch.float32, device=dev)
+            out[:b.shape[0]] = b.detach().to(dev, torch.float32)
+            return out
+
+        layers = []
+        for L in self.transformer_layers:
+            m = L.multihead_attention
+            wi = m.in_proj_weight.detach().to(dev, torch.float32).view(3, H, hd, d)
+            bi = m.in_proj_bias.detach().to(dev, torch.float32).view(3, H, hd)
+            wqkv = torch.zeros(3, H, hp, dp, dtype=torch.float32, device=dev)
+            wqkv[:, :, :hd, :d] = wi                                     # head h of q/k/v → 48-wide padded slot
+            bqkv = torch.zeros(3, H, hp, dtype=torch.float32, device=dev)
+            bqkv[:, :, :hd] = bi
+            wo = torch.zeros(dp, H, hp, dtype=torch.float32, device=dev)
+            wo[:d, :, :hd] = m.out_proj.weight.detach().to(dev, torch.float32).view(d, H, hd)
+            layers.append(dict(
+                wqkv=wqkv.view(3 * H * hp, dp).to(BF16), bqkv=bqkv.view(-1), wo=wo.view(dp, H * hp).to(BF16),
+                bo=padb(m.out_proj.bias, dp), w1=padw(L.feedforward[0].weight, fp, dp), b1=padb(L.feedforward[0].bias, fp),
+                w2=padw(L.feedforward[2].weight, dp, fp), b2=padb(L.feedforward[2].bias, dp),
+                g1=L.norm1.weight.detach().to(dev, torch.float32).contiguous(), be1=L.norm1.bias.detach().to(dev, torch.float32).contiguous(),
+                g2=L.norm2.weight.detach().to(dev, torch.float32).contiguous(), be2=L.norm2.bias.detach().to(dev, torch.float32).contiguous()))
+        self._prep = dict(
+            d=d, dp=dp, hd=hd, hp=hp, fp=fp, layers=layers,
+            fc_w=padw(self.fc.weight, self.output_vector_dim, dp), fc_b=self.fc.bias.detach().to(dev, torch.float32).contiguous(),
+            wq=padw(self.com_attention.query_linear.weight, dp, dp), bq=padb(self.com_attention.query_linear.bias, dp),
+            wk=padw(self.com_attention.key_linear.weight, dp, dp), bk=padb(self.com_attention.key_linear.bias, dp),
+            emb=self.temporal_embedding.embedding.weight.detach().to(dev, torch.float32).contiguous())
+        self._prep_version = ver
+        return self._prep
+
+    def _buffers(self, M: int, dev, P) -> Dict[str, torch.Tensor]:
+        if M not in self._bufs:
+            if len(self._bufs) >= 4:
+                self._bufs.pop(next(iter(self._bufs)))
+            H, hp, dp, fp = self.num_heads, P["hp"], P["dp"], P["fp"]
+            z = lambda c, dt=BF16: torch.zeros(M, c, dtype=dt, device=dev)
+            self._bufs[M] = dict(xa=z(dp), xb=z(dp), qkv=z(3 * H * hp), o=z(H * hp), s=z(dp), x1=z(dp), h=z(fp), q=z(dp), k=z(dp),
+                                 v=z(8), blend=z(8), out=z(12, torch.float32), x32=z(dp, torch.float32))
+        return self._bufs[M]
+
+    # ---- forward (TransformerBaseline.py:104-148) ---------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: Dict[str, torch.Tensor]):
+        p0 = next(self.parameters())
+        if not p0.is_cuda:
+            raise _lib.IbmError("TransformerBaseline runs only on a B200: move it to CUDA (no CPU fallback)")
+        dev = p0.device
+        P = self._prepare(dev)
+        d, dp, H, hp = P["d"], P["dp"], self.num_heads, P["hp"]
+        batch_size = x[InputDataKeys.POS].size(0)
+        # (q, dq, ddq, com_pos, com_vel, com_acc) per timestep; inputs are (B, C, T) → (B, T, C)   (…:108-116)
+        parts = [x[k].to(dev, torch.float32) for k in (InputDataKeys.POS, InputDataKeys.VEL, InputDataKeys.ACC, InputDataKeys.COM_POS,
+                                                       InputDataKeys.COM_VEL, InputDataKeys.COM_ACC)]
+        T = parts[0].size(2)
+        assert T == self.window_size, "TemporalEmbedding.expand needs T == window_size (…:121-123)"
+        M = batch_size * T
+        b = self._buffers(M, dev, P)
+        x32 = b["x32"].view(batch_size, T, dp)
+        c0 = 0
+        for t in parts:                                            # transpose(1,2) + concat, written straight into the padded rows
+            x32[:, :, c0:c0 + t.size(1)] = t.transpose(1, 2)
+            c0 += t.size(1)
+        x32[:, :, c0:c0 + self.temporal_embedding_dim] = P["emb"][:T].unsqueeze(0)     # embedding concatenated, not added (…:119-126)
+        ops.cast_f32_bf16(b["x32"], b["xa"])
+        cur, nxt = b["xa"], b["xb"]
+        scale = 1.0 / math.sqrt(P["hd"])
+        for L in P["layers"]:
+            ops.gemm(cur, L["wqkv"], b["qkv"], M, 3 * H * hp, dp, bias=L["bqkv"])
+            ops.attention_fwd_fused(b["qkv"], H * hp, b["o"], batch_size, T, H, hp, scale)
+            ops.gemm(b["o"], L["wo"], b["s"], M, dp, H * hp, bias=L["bo"], aux=cur, aux_mode=1)
+            ops.layernorm_fwd(b["s"], b["x1"], L["g1"], L["be1"], M, d)
+            ops.gemm(b["x1"], L["w1"], b["h"], M, P["fp"], dp, bias=L["b1"], act="relu")
+            ops.gemm(b["h"], L["w2"], b["s"], M, dp, P["fp"], bias=L["b2"], aux=b["x1"], aux_mode=1)
+            ops.layernorm_fwd(b["s"], nxt, L["g2"], L["be2"], M, d)
+            cur, nxt = nxt, cur
+        ops.gemm(cur, P["fc_w"], b["out"], M, self.output_vector_dim, dp, bias=P["fc_b"])
+        # CoM acceleration as an (unscaled) attention blend over the input CoM accelerations (…:51-70, 135-137)
+        ops.gemm(cur, P["wq"], b["q"], M, dp, dp, bias=P["bq"])
+        ops.gemm(cur, P["wk"], b["k"], M, dp, dp, bias=P["bk"])
+        b["v"][:, :3] = parts[5].transpose(1, 2).reshape(M, 3).to(BF16)
+        ops.attention_fwd(b["q"], b["k"], b["v"], b["blend"], batch_size, T, 1, dp, 8, 1.0)
+        out = b["out"].view(batch_size, T, 12)
+        dt = self.fc.weight.dtype
+        return {
+            OutputDataKeys.CONTACT: torch.sigmoid(out[:, :, :2]).transpose(1, 2).to(dt),
+            OutputDataKeys.COM_ACC: b["blend"].view(batch_size, T, 8)[:, :, :3].transpose(1, 2).to(dt),
+            OutputDataKeys.CONTACT_FORCES: out[:, :, 5:11].transpose(1, 2).to(dt),
+        }

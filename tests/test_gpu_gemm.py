@@ -68,9 +68,9 @@ def test_gemm_forward(M, N, K, act, out_f32):
         assert torch.all(out[:, n_touched:].float() == 7.0)
 
 
-def test_gemm_residual_and_dact():
+@pytest.mark.parametrize("M,N,K", [(515, 512, 256), (300, 200, 128), (40000, 512, 512), (1000, 2048, 512)])
+def test_gemm_residual_and_dact(M, N, K):
     from inferbiomechanics_b200 import ops
-    M, N, K = 515, 512, 256
     A, B = _mk(M, K, K, 4), _mk(N, K, K, 5, 1.0 / math.sqrt(K))
     bias = torch.randn(N, generator=torch.Generator().manual_seed(6))
     aux = _mk(M, N, N, 7)
