@@ -166,23 +166,24 @@ template <int HD>
 __global__ void __launch_bounds__(kThreads)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_off, const __nv_bfloat16* __restrict__ dout,
                 int64_t ldo, __nv_bfloat16* __restrict__ dqkv, int T, int H, float scale) {
-  constexpr int LD = HD + kPad;       // operand tiles [64][LD]
-  constexpr int LP = 64 + kPad;       // P / dS tiles  [64][LP]
+  constexpr int LD = HD + kPad;       // Q / dO tiles [64][LD]
+  constexpr int LP = 64 + kPad;       // P / dS tiles [64][LP]
+  constexpr int LX = LD > LP ? LD : LP;   // K and V tiles use this stride: P and dS later overwrite them in place
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-  __nv_bfloat16* Ks = Qs + 64 * LD;
-  __nv_bfloat16* Vs = Ks + 64 * LD;
-  __nv_bfloat16* dOs = Vs + 64 * LD;
-  __nv_bfloat16* Ps = dOs + 64 * LD;
-  __nv_bfloat16* dSs = Ps + 64 * LP;
+  __nv_bfloat16* dOs = Qs + 64 * LD;
+  __nv_bfloat16* Ks = dOs + 64 * LD;
+  __nv_bfloat16* Vs = Ks + 64 * LX;
+  __nv_bfloat16* Ps = Ks;             // valid after the barrier that ends phase 1 (K, V no longer needed)
+  __nv_bfloat16* dSs = Vs;
 
   const int h = blockIdx.x % H;
   const int64_t win = blockIdx.x / H;
   const int64_t row0 = win * T;
   const __nv_bfloat16* base = qkv + row0 * ld + h * HD;
   load_tile<HD, LD>(Qs, base, ld, 64, T);
-  load_tile<HD, LD>(Ks, base + kv_off, ld, 64, T);
-  load_tile<HD, LD>(Vs, base + 2 * kv_off, ld, 64, T);
+  load_tile<HD, LX>(Ks, base + kv_off, ld, 64, T);
+  load_tile<HD, LX>(Vs, base + 2 * kv_off, ld, 64, T);
   load_tile<HD, LD>(dOs, dout + row0 * ldo + h * HD, ldo, 64, T);
   __syncthreads();
 
@@ -205,8 +206,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_of
     da[2] = *reinterpret_cast<const uint32_t*>(dpp + 8);     da[3] = *reinterpret_cast<const uint32_t*>(dpp + 8 * LD + 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const __nv_bfloat16* kp = Ks + (j * 8 + g) * LD + kk * 16 + 2 * t;
-      const __nv_bfloat16* vp = Vs + (j * 8 + g) * LD + kk * 16 + 2 * t;
+      const __nv_bfloat16* kp = Ks + (j * 8 + g) * LX + kk * 16 + 2 * t;
+      const __nv_bfloat16* vp = Vs + (j * 8 + g) * LX + kk * 16 + 2 * t;
       mma16816(s[j], qa, *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
       mma16816(dp[j], da, *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
     }
@@ -243,16 +244,15 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_of
   d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
   d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
   uint32_t dsa[4][4];                                  // scale*dS as A fragments for dQ = dS K
+  uint32_t ppk[8][2];                                  // P (bf16 pairs), parked in registers until K/V are dead
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float e0 = scale * s[j][0] * (dp[j][0] - d0), e1 = scale * s[j][1] * (dp[j][1] - d0);
     const float e2 = scale * s[j][2] * (dp[j][2] - d1), e3 = scale * s[j][3] * (dp[j][3] - d1);
     const uint32_t p01 = pack_bf16x2(s[j][0], s[j][1]), p23 = pack_bf16x2(s[j][2], s[j][3]);
     const uint32_t s01 = pack_bf16x2(e0, e1), s23 = pack_bf16x2(e2, e3);
-    *reinterpret_cast<uint32_t*>(Ps + r0 * LP + j * 8 + 2 * t) = p01;
-    *reinterpret_cast<uint32_t*>(Ps + (r0 + 8) * LP + j * 8 + 2 * t) = p23;
-    *reinterpret_cast<uint32_t*>(dSs + r0 * LP + j * 8 + 2 * t) = s01;
-    *reinterpret_cast<uint32_t*>(dSs + (r0 + 8) * LP + j * 8 + 2 * t) = s23;
+    ppk[j][0] = p01;
+    ppk[j][1] = p23;
     dsa[j >> 1][(j & 1) * 2] = s01;
     dsa[j >> 1][(j & 1) * 2 + 1] = s23;
   }
@@ -265,7 +265,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_of
 #pragma unroll
       for (int j = 0; j < HD / 8; ++j) {
         uint32_t b0, b1;
-        ldsm_x2_trans(b0, b1, Ks + (kk * 16 + (lane & 15)) * LD + j * 8);
+        ldsm_x2_trans(b0, b1, Ks + (kk * 16 + (lane & 15)) * LX + j * 8);
         mma16816(dq[j], dsa[kk], b0, b1);
       }
     }
@@ -276,6 +276,14 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_of
       if (r0 < T) *reinterpret_cast<uint32_t*>(g0 + j * 8) = pack_bf16x2(dq[j][0], dq[j][1]);
       if (r0 + 8 < T) *reinterpret_cast<uint32_t*>(g1 + j * 8) = pack_bf16x2(dq[j][2], dq[j][3]);
     }
+  }
+  __syncthreads();                                     // every warp is done reading K and V
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<uint32_t*>(Ps + r0 * LP + j * 8 + 2 * t) = ppk[j][0];
+    *reinterpret_cast<uint32_t*>(Ps + (r0 + 8) * LP + j * 8 + 2 * t) = ppk[j][1];
+    *reinterpret_cast<uint32_t*>(dSs + r0 * LP + j * 8 + 2 * t) = dsa[j >> 1][(j & 1) * 2];
+    *reinterpret_cast<uint32_t*>(dSs + (r0 + 8) * LP + j * 8 + 2 * t) = dsa[j >> 1][(j & 1) * 2 + 1];
   }
   __syncthreads();
 
@@ -342,7 +350,7 @@ static int launch_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, co
 template <int HD>
 static int launch_bwd(const void* qkv, int64_t ld, int64_t kv_off, const void* d_o, int64_t ldo, void* dqkv, int64_t n_win, int T,
                       int H, float scale, cudaStream_t s) {
-  const size_t smem = (size_t)(4 * 64 * (HD + kPad) + 2 * 64 * (64 + kPad)) * 2;
+  const size_t smem = (size_t)(2 * 64 * (HD + kPad) + 2 * 64 * (64 + kPad)) * 2;     // Q, dO + K/P, V/dS (HD <= 64)
   auto kern = attn_bwd_kernel<HD>;
   static bool attr_set = false;
   if (!attr_set) {
