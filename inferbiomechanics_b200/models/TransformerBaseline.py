@@ -137,7 +137,7 @@ class TransformerBaseline(nn.Module):
         self._prep_version = ver
         return self._prep
 
-    def _buffers(self, M: int, dev, P) -> Dict[str, torch.Tensor]:
+    def _act_buffers(self, M: int, dev, P) -> Dict[str, torch.Tensor]:
         if M not in self._bufs:
             if len(self._bufs) >= 4:
                 self._bufs.pop(next(iter(self._bufs)))
@@ -163,7 +163,7 @@ class TransformerBaseline(nn.Module):
         T = parts[0].size(2)
         assert T == self.window_size, "TemporalEmbedding.expand needs T == window_size (…:121-123)"
         M = batch_size * T
-        b = self._buffers(M, dev, P)
+        b = self._act_buffers(M, dev, P)
         x32 = b["x32"].view(batch_size, T, dp)
         c0 = 0
         for t in parts:                                            # transpose(1,2) + concat, written straight into the padded rows

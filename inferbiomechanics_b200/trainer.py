@@ -285,13 +285,21 @@ def _profile_gemms(self, store, idx):
 
 
 def _time_kernel(fn, iters: int = 20) -> float:
+    """Average GPU time of one launch: `iters` launches are captured in a CUDA graph and the replay is timed with
+    events, so host-side launch overhead (ctypes marshalling is ~50-100 us per call, longer than these kernels)
+    is not part of the number."""
     for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()                                   # warm replay
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
