@@ -195,6 +195,18 @@ int ibm_conv_weight_to_gemm(const float* w, int32_t cout, int32_t cin, int32_t k
 int ibm_conv_wgrad_from_gemm(const float* g, int32_t cout, int32_t cin, int32_t kt, int32_t cin_pad,
                              float* dw, int32_t accumulate, void* stream);
 
+/* Temporal replicate padding for the implicit-GEMM convolution (Groundlink.py:41, padding_mode="replicate").
+ * Padded row layout: window b owns rows [b*Tp, (b+1)*Tp), Tp = T + 2*pad, frame t at row b*Tp + pad + t.
+ * replicate: pad rows <- first / last frame row.  fold (its adjoint): edge frame rows += pad rows, pad rows <- 0. */
+int ibm_replicate_pad_rows(void* X_bf16, int64_t ld, int64_t n_win, int32_t T, int32_t pad, int32_t cols, void* stream);
+int ibm_fold_pad_rows(void* G_bf16, int64_t ld, int64_t n_win, int32_t T, int32_t pad, int32_t cols, void* stream);
+/* Inverted dropout (nn.Dropout, Groundlink.py:53,59): y = x * keep/(1-p), keep from Philox4x32-10(seed, offset);
+ * the backward pass calls it on dy with the same (seed, offset).  n % 4 == 0. */
+int ibm_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+/* Conv1d weight (Cout,Cin,Kt) fp32 -> bf16 dgrad layout [Cin, Kt*cout_pad]: B[ci, j*cout_pad+co] = W[co,ci,Kt-1-j] */
+int ibm_conv_weight_to_dgrad(const float* w, int32_t cout, int32_t cin, int32_t kt, int32_t cout_pad,
+                             void* dst_bf16, void* stream);
+
 /* ---- residual + LayerNorm  (src/models/TransformerBaseline.py:31,36; nn.LayerNorm eps=1e-5) ---- */
 
 /* y = LN(s) * gamma + beta over the first d columns of each row (columns d..ld are written 0).

@@ -42,6 +42,10 @@ SIGNATURES = {
     "ibm_cast_pad_f32_bf16": [P, _i64, P, _i64, _i64, _i64, P],
     "ibm_conv_weight_to_gemm": [P, _i32, _i32, _i32, _i32, P, P],
     "ibm_conv_wgrad_from_gemm": [P, _i32, _i32, _i32, _i32, P, _i32, P],
+    "ibm_replicate_pad_rows": [P, _i64, _i64, _i32, _i32, _i32, P],
+    "ibm_fold_pad_rows": [P, _i64, _i64, _i32, _i32, _i32, P],
+    "ibm_dropout_bf16": [P, P, _i64, _f, _u64, _u64, P],
+    "ibm_conv_weight_to_dgrad": [P, _i32, _i32, _i32, _i32, P, P],
     "ibm_layernorm_fwd": [P, P, _i64, P, P, _i64, _i32, _f, P, P, P],
     "ibm_layernorm_bwd": [P, P, _i64, P, P, P, _i64, _i32, P, P, P, P, P],
     "ibm_attention_fwd": [P, _i64, P, _i64, P, _i64, P, _i64, _i64, _i32, _i32, _i32, _i32, _f, P],

@@ -202,3 +202,135 @@ extern "C" int ibm_conv_wgrad_from_gemm(const float* g, int32_t cout, int32_t ci
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }
+
+// ---- temporal replicate padding for the implicit-GEMM convolution (Groundlink.py:41, padding_mode="replicate") ----
+// Activations live in a padded row layout: window b owns rows [b*Tp, (b+1)*Tp), Tp = T + 2*pad, frame t at row
+// b*Tp + pad + t.  replicate_pad copies the first/last frame rows into the pad rows; fold_pad is its adjoint
+// (pad-row gradients are added into the edge frames, then the pad rows are zeroed so they cannot leak into the
+// shifted dgrad/wgrad GEMMs).
+namespace ibm {
+__global__ void __launch_bounds__(kThreads)
+replicate_pad_kernel(__nv_bfloat16* __restrict__ X, long long ld, long long n_win, int T, int pad, int cols8) {
+  const long long n = n_win * 2 * pad * cols8;
+  const int Tp = T + 2 * pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols8) * 8;
+    const long long r = i / cols8;
+    const int k = (int)(r % (2 * pad));
+    const long long b = r / (2 * pad);
+    const int dst = k < pad ? k : T + k;                       // pad rows 0..pad-1 and T+pad..Tp-1
+    const int src = k < pad ? pad : T + pad - 1;
+    *reinterpret_cast<uint4*>(X + (b * Tp + dst) * ld + c) = *reinterpret_cast<const uint4*>(X + (b * Tp + src) * ld + c);
+  }
+}
+__global__ void __launch_bounds__(kThreads)
+fold_pad_kernel(__nv_bfloat16* __restrict__ G, long long ld, long long n_win, int T, int pad, int cols8) {
+  const long long n = n_win * 2 * cols8;
+  const int Tp = T + 2 * pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols8) * 8;
+    const long long r = i / cols8;
+    const int side = (int)(r & 1);
+    const long long b = r >> 1;
+    const int edge = side ? T + pad - 1 : pad;
+    float acc[8];
+    {
+      uint4 u = *reinterpret_cast<const uint4*>(G + (b * Tp + edge) * ld + c);
+      float2 t;
+      t = unpack_bf16x2(u.x); acc[0] = t.x; acc[1] = t.y;
+      t = unpack_bf16x2(u.y); acc[2] = t.x; acc[3] = t.y;
+      t = unpack_bf16x2(u.z); acc[4] = t.x; acc[5] = t.y;
+      t = unpack_bf16x2(u.w); acc[6] = t.x; acc[7] = t.y;
+    }
+    for (int k = 0; k < pad; ++k) {
+      const int prow = side ? T + pad + k : k;
+      __nv_bfloat16* pp = G + (b * Tp + prow) * ld + c;
+      uint4 u = *reinterpret_cast<const uint4*>(pp);
+      float2 t;
+      t = unpack_bf16x2(u.x); acc[0] += t.x; acc[1] += t.y;
+      t = unpack_bf16x2(u.y); acc[2] += t.x; acc[3] += t.y;
+      t = unpack_bf16x2(u.z); acc[4] += t.x; acc[5] += t.y;
+      t = unpack_bf16x2(u.w); acc[6] += t.x; acc[7] += t.y;
+      *reinterpret_cast<uint4*>(pp) = make_uint4(0, 0, 0, 0);
+    }
+    *reinterpret_cast<uint4*>(G + (b * Tp + edge) * ld + c) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// inverted dropout with a counter-based mask: element i is kept iff Philox(seed, offset)[i] >= p; kept values are
+// scaled by 1/(1-p).  Forward and backward call the same kernel with the same (seed, offset), so the mask is never stored.
+__global__ void __launch_bounds__(kThreads)
+dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n, float p, float scale,
+               uint64_t seed, uint64_t offset) {
+  const long long n4 = n >> 2;
+  const uint32_t thresh = (uint32_t)(p * 4294967296.0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint2 u = *reinterpret_cast<const uint2*>(x + 4 * i);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    a.x = r.x >= thresh ? a.x * scale : 0.f;
+    a.y = r.y >= thresh ? a.y * scale : 0.f;
+    b.x = r.z >= thresh ? b.x * scale : 0.f;
+    b.y = r.w >= thresh ? b.y * scale : 0.f;
+    *reinterpret_cast<uint2*>(y + 4 * i) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(b.x, b.y));
+  }
+}
+
+// Conv1d weight (Cout,Cin,Kt) fp32 → bf16 dgrad-GEMM layout [Cin, Kt*cout_pad]: B[ci, j'*cout_pad + co] = W[co, ci, Kt-1-j']
+__global__ void __launch_bounds__(kThreads)
+conv_w_to_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int kt, int cout_pad, __nv_bfloat16* __restrict__ dst) {
+  const long long n = (long long)cin * kt * cout_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout_pad);
+    const long long r = i / cout_pad;
+    const int jp = (int)(r % kt);
+    const int ci = (int)(r / kt);
+    dst[i] = __float2bfloat16_rn(co < cout ? __ldg(w + ((long long)co * cin + ci) * kt + (kt - 1 - jp)) : 0.f);
+  }
+}
+}  // namespace ibm
+
+extern "C" int ibm_replicate_pad_rows(void* X, int64_t ld, int64_t n_win, int32_t T, int32_t pad, int32_t cols, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(X && n_win > 0 && T > 0 && pad > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && ld >= cols && aligned16(X),
+                "replicate_pad_rows: bad argument (cols and ld must be multiples of 8)");
+  replicate_pad_kernel<<<ew_grid(n_win * 2 * pad * (cols / 8)), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(X), ld, n_win, T, pad, cols / 8);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+extern "C" int ibm_fold_pad_rows(void* G, int64_t ld, int64_t n_win, int32_t T, int32_t pad, int32_t cols, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(G && n_win > 0 && T > 0 && pad > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && ld >= cols && aligned16(G),
+                "fold_pad_rows: bad argument (cols and ld must be multiples of 8)");
+  fold_pad_kernel<<<ew_grid(n_win * 2 * (cols / 8)), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(G), ld, n_win, T, pad, cols / 8);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+extern "C" int ibm_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(x && y && n > 0 && n % 4 == 0 && p >= 0.f && p < 1.f, "dropout: bad argument (n %% 4 == 0, 0 <= p < 1)");
+  dropout_kernel<<<ew_grid(n / 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, p, 1.f / (1.f - p), seed, offset);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+extern "C" int ibm_conv_weight_to_dgrad(const float* w, int32_t cout, int32_t cin, int32_t kt, int32_t cout_pad, void* dst_bf16,
+                                        void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(w && dst_bf16 && cout > 0 && cin > 0 && kt > 0 && cout_pad >= cout, "conv_weight_to_dgrad: bad argument");
+  conv_w_to_dgrad_kernel<<<ew_grid((long long)cin * kt * cout_pad), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, cin, kt, cout_pad, static_cast<__nv_bfloat16*>(dst_bf16));
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}

@@ -97,6 +97,23 @@ def conv_wgrad_from_gemm(g: torch.Tensor, dw: torch.Tensor, cin_pad: int, accumu
     call("ibm_conv_wgrad_from_gemm", _p(g), cout, cin, kt, cin_pad, _p(dw), int(accumulate), stream_ptr())
 
 
+def replicate_pad_rows(X, n_win, T, pad, cols):
+    call("ibm_replicate_pad_rows", _p(X), X.stride(0), n_win, T, pad, cols, stream_ptr())
+
+
+def fold_pad_rows(G, n_win, T, pad, cols):
+    call("ibm_fold_pad_rows", _p(G), G.stride(0), n_win, T, pad, cols, stream_ptr())
+
+
+def dropout(x, y, p, seed, offset):
+    call("ibm_dropout_bf16", _p(x), _p(y), x.numel(), p, seed, offset, stream_ptr())
+
+
+def conv_weight_to_dgrad(w: torch.Tensor, dst: torch.Tensor, cout_pad: int):
+    cout, cin, kt = w.shape
+    call("ibm_conv_weight_to_dgrad", _p(w), cout, cin, kt, cout_pad, _p(dst), stream_ptr())
+
+
 # ---- LayerNorm ----------------------------------------------------------------------------------
 def layernorm_fwd(s, y, gamma, beta, M, d, eps=1e-5, mean=None, rstd=None, ld=None):
     call("ibm_layernorm_fwd", _p(s), _p(y), s.stride(0) if ld is None else ld, _p(gamma), _p(beta), M, d, eps, _p(mean),
