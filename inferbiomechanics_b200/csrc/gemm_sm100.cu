@@ -15,6 +15,8 @@
 // Tile 128 x BN x 64, UMMA 128 x BN x 16, cta_group::1; operand tiles in SWIZZLE_128B layout.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -35,11 +37,17 @@ constexpr uint32_t kEpiBarrier = 1;
 constexpr int kStageA = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int kOutStage = BLOCK_M * 128;                // 128 rows x 128 B = 16 KB
 
-template <int BN, bool AUX>
+// CG = CTAs per MMA (cta_group): 1 = one 128 x BN tile per CTA; 2 = a CTA pair computes a 256 x BN tile, each CTA
+// holding its own 128 rows of A and HALF of the B tile (BN / 2 rows), which halves the B traffic through shared memory
+// (at 128 x 256 with cta_group::1 the operand reads + TMA writes exceed the 128 B/clk shared-memory port: 64 % tensor
+// pipe, profiles/r01a; the pair brings it under the port limit).
+template <int BN, bool AUX, int CG>
 struct Cfg {
-  static constexpr int kStageB = BN * BLOCK_K * 2;
-  // AUX kernels give one operand stage up for a 3-deep ring of aux chunk buffers (prefetched 2-3 chunks ahead)
-  static constexpr int kStages = AUX ? ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int kStageB = (BN / CG) * BLOCK_K * 2;
+  // AUX kernels give operand stages up for a 3-deep ring of aux chunk buffers (prefetched 2-3 chunks ahead)
+  static constexpr int kStages =
+      CG == 2 ? (AUX ? (BN == 256 ? 4 : 6) : (BN == 256 ? 6 : 8))
+              : (AUX ? ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int kAuxBufs = AUX ? 3 : 0;
   static constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int kSmem = 1024 /*align slack*/ + kStages * (kStageA + kStageB) + (2 + kAuxBufs) * kOutStage + BN * 4 + 256;
@@ -133,11 +141,12 @@ __device__ __forceinline__ void epi_dispatch_aux(float (&v)[PT], const float* bs
   }
 }
 
-template <int BN, bool kOutF32, bool kAccum, bool kAux>
+template <int BN, bool kOutF32, bool kAccum, bool kAux, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const Args args) {
-  using C = Cfg<BN, kAux>;
+  using C = Cfg<BN, kAux, CG>;
+  static_assert(CG == 1 || BN >= 128, "a CTA pair splits B into two halves of at least one 64-wide swizzle atom");
   static_assert(!kAux || (!kOutF32 && !kAccum), "TMA-staged aux tiles exist for bf16 outputs only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -163,30 +172,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads / 32); }
+    // the leader's MMA thread waits for the epilogue warps of BOTH CTAs of a pair before reusing an accumulator
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CG * kEpiThreads / 32); }
     for (int i = 0; i < 3; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+    else tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // peer barriers are initialised before any remote arrive / TMA completion
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_work = args.tiles_m * args.tiles_n * args.splits;
+  // work item = (row block of CG*128 rows, column tile, k split); a pair walks the same list, CTA `rank` owning
+  // rows [rank*128, +128) of the row block and B rows [rank*BN/2, +BN/2) of the column tile
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int worker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_work = args.tiles_m * args.tiles_n * args.splits;     // tiles_m counts CG*128-row blocks
+  constexpr int BN_LOAD = BN / CG;
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kStageA + C::kStageB;
+      const uint32_t tx_bytes = CG * (kStageA + C::kStageB);     // the pair's loads all complete on the leader's barrier
       const bool prefetch_aux = kAux;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = worker; w < total_work; w += n_workers) {
         const int split = w % args.splits;
         const int tile = w / args.splits;
         const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
-        const int m0 = tm * BLOCK_M, n0 = tn * BN;
+        const int m0 = (tm * CG + rank) * BLOCK_M, n0 = tn * BN;
+        const int nb0 = n0 + rank * BN_LOAD;                      // first B row this CTA loads
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
         if (prefetch_aux) {
@@ -196,25 +217,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           uint8_t* sa = smem_a + stage * kStageA;
           uint8_t* sb = smem_b + stage * C::kStageB;
           const int tap = kb / args.kb_per_tap;
           const int k0a = (kb - tap * args.kb_per_tap) * BLOCK_K;      // k coordinate inside A
           const int k0b = kb * BLOCK_K;                                 // k coordinate inside B
+          auto load = [&](void* dst, const CUtensorMap* tm_, int c0, int c1) {
+            if constexpr (CG == 2) tma_load_2d_pair(dst, tm_, &full_bar[stage], c0, c1);
+            else tma_load_2d(dst, tm_, &full_bar[stage], c0, c1);
+          };
           if (!args.a_mn) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], k0a, m0 + tap);
+            load(sa, &tmA, k0a, m0 + tap);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d(sa + i * (BLOCK_K * 128), &tmA, &full_bar[stage], m0 + 64 * i, k0a);
+            for (int i = 0; i < BLOCK_M / 64; ++i) load(sa + i * (BLOCK_K * 128), &tmA, m0 + 64 * i, k0a);
           }
           if (!args.b_mn) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0b, n0);
+            load(sb, &tmB, k0b, nb0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(sb + i * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + 64 * i, k0b);
+            for (int i = 0; i < BN_LOAD / 64; ++i) load(sb + i * (BLOCK_K * 128), &tmB, nb0 + 64 * i, k0b);
           }
           advance(stage, phase, C::kStages);
         }
@@ -222,8 +245,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer =======================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, args.a_mn, args.b_mn);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(CG * BLOCK_M, BN, args.a_mn, args.b_mn);
       // K-major: 8-row groups are 1024 B apart (SBO); LBO unused.  MN-major: 64-wide MN atoms are
       // BLOCK_K*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
       const uint32_t a_lbo = args.a_mn ? BLOCK_K * 128 : 0, b_lbo = args.b_mn ? BLOCK_K * 128 : 0;
@@ -231,7 +254,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t b_kstep = args.b_mn ? UMMA_K * 128 : UMMA_K * 2;
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = worker; w < total_work; w += n_workers) {
         const int split = w % args.splits;
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
@@ -247,12 +270,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           advance(stage, phase, C::kStages);
         }
-        umma_commit(&tfull_bar[as]);               // accumulator complete → epilogue
+        // accumulator complete → epilogue (of both CTAs)
+        if constexpr (CG == 2) umma_commit_pair(&tfull_bar[as]);
+        else umma_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -275,7 +303,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int as = 0, ob = 0;
     uint32_t aphase = 0;
     int xg = 0;                                     // chunks consumed so far by this CTA (aux ring position)
-    int pw = blockIdx.x, pch = 0;                   // prefetch cursor: (work item, chunk) of the next aux load
+    int pw = worker, pch = 0;                       // prefetch cursor: (work item, chunk) of the next aux load
     auto chunks_of = [&](int w) {
       const int n0w = ((w / args.splits) % args.tiles_n) * BN;
       return ((int)min((int64_t)BN, args.N - n0w) + CW - 1) / CW;
@@ -284,16 +312,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (pw >= total_work) return;
       const int t2 = pw / args.splits;
       mbar_arrive_expect_tx(&aux_bar[buf], kOutStage);
-      tma_load_2d(smem_aux + buf * kOutStage, &tmX, &aux_bar[buf], (t2 % args.tiles_n) * BN + pch * CW, (t2 / args.tiles_n) * BLOCK_M);
-      if (++pch == chunks_of(pw)) { pch = 0; pw += gridDim.x; }
+      tma_load_2d(smem_aux + buf * kOutStage, &tmX, &aux_bar[buf], (t2 % args.tiles_n) * BN + pch * CW,
+                  ((t2 / args.tiles_n) * CG + rank) * BLOCK_M);
+      if (++pch == chunks_of(pw)) { pch = 0; pw += n_workers; }
     };
     if (kAux && leader) {
       for (int i = 0; i < 3; ++i) issue_aux(i);
     }
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = worker; w < total_work; w += n_workers) {
       const int tile = w / args.splits;
       const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
-      const int m0 = tm * BLOCK_M, n0 = tn * BN;
+      const int m0 = (tm * CG + rank) * BLOCK_M, n0 = tn * BN;
       const int64_t row = (int64_t)m0 + r_local;
       const int n_valid = (int)min((int64_t)BN, args.N - n0);
       const int n_chunks = (n_valid + CW - 1) / CW;
@@ -321,7 +350,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // all TMEM reads of this accumulator are done → hand the buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[as], 0);
+            else mbar_arrive(&tempty_bar[as]);
+          }
         }
         // make sure the staging buffer `ob` is no longer being read by the store issued 2 chunks ago,
         // and (first chunk) that the bias slice is visible
@@ -376,10 +408,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // no CTA retires while its peer can still signal into it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+    else tmem_dealloc<C::kTmemCols>(tmem_base);
   }
 }
 
@@ -423,18 +457,45 @@ static int make_map(CUtensorMap* map, const void* base, bool f32, int64_t inner,
   return IBM_OK;
 }
 
-template <int BN, bool F32, bool ACC, bool AUX = false>
+template <int BN, bool F32, bool ACC, bool AUX, int CG>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& x, const Args& args, int grid,
                   cudaStream_t s) {
   static bool attr_set = false;     // per instantiation
-  auto kern = gemm_kernel<BN, F32, ACC, AUX>;
+  auto kern = gemm_kernel<BN, F32, ACC, AUX, CG>;
   if (!attr_set) {
-    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, AUX>::kSmem));
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, AUX, CG>::kSmem));
     attr_set = true;
   }
-  kern<<<grid, kThreads, Cfg<BN, AUX>::kSmem, s>>>(a, b, d, x, args);
+  if constexpr (CG == 1) {
+    kern<<<grid, kThreads, Cfg<BN, AUX, CG>::kSmem, s>>>(a, b, d, x, args);
+  } else {
+    // CTA pairs: clusters of 2 along x so both CTAs of a pair sit on the two SMs of one TPC
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<BN, AUX, CG>::kSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    IBM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a, b, d, x, args));
+  }
   IBM_LAUNCH_CHECK();
   return IBM_OK;
+}
+
+// IBM_GEMM_CG=1 forces single-CTA MMAs everywhere (A/B measurements, tools/gemm_probe.py)
+static int forced_cg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IBM_GEMM_CG");
+    v = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 0);
+  }
+  return v;
 }
 
 static int pick_bn(int64_t N) {
@@ -480,13 +541,16 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   args.M = M; args.N = N;
   args.kb_per_tap = (int32_t)ceil_div(k_tap, BLOCK_K);
   args.kb_total = args.kb_per_tap * taps;
-  args.tiles_m = (int32_t)ceil_div(M, BLOCK_M);
+  // CTA pairs (256-row blocks) whenever there are at least two 128-row blocks and B splits into whole swizzle atoms
+  int cg = (ceil_div(M, BLOCK_M) >= 2 && bn >= 128) ? 2 : 1;
+  if (forced_cg() == 1) cg = 1;
+  args.tiles_m = (int32_t)ceil_div(M, (int64_t)cg * BLOCK_M);
   args.tiles_n = (int32_t)ceil_div(N, bn);
   const int sms = sm_count();
   int splits = 1;
   if (accumulate) {
     const int64_t tiles = (int64_t)args.tiles_m * args.tiles_n;
-    splits = split_k > 0 ? split_k : (int)ceil_div(2 * sms, tiles);
+    splits = split_k > 0 ? split_k : (int)ceil_div(2 * (sms / cg), tiles);
     int max_splits = args.kb_total / 8 > 0 ? args.kb_total / 8 : 1;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -507,7 +571,7 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   if (!args.a_mn) rc = make_map(&ta, A, false, k_tap, M + (taps - 1), lda, BLOCK_K, BLOCK_M);
   else rc = make_map(&ta, A, false, M, K, lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!args.b_mn) rc = make_map(&tb, B, false, Kb, N, ldb, BLOCK_K, (uint32_t)bn);
+  if (!args.b_mn) rc = make_map(&tb, B, false, Kb, N, ldb, BLOCK_K, (uint32_t)(bn / cg));
   else rc = make_map(&tb, B, false, N, K, ldb, 64, BLOCK_K);
   if (rc) return rc;
   const bool f32 = out_dtype == IBM_F32;
@@ -520,22 +584,27 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   }
 
   const int64_t work = (int64_t)args.tiles_m * args.tiles_n * args.splits;
-  const int grid = (int)(work < sms ? work : sms);
+  const int workers = sms / cg;
+  const int grid = (int)(work < workers ? work : workers) * cg;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define IBM_GEMM_DISPATCH(BNV)                                                   \
-  do {                                                                           \
-    if (accumulate) return launch<BNV, true, true>(ta, tb, td, tx, args, grid, s);   \
-    if (f32) return launch<BNV, true, false>(ta, tb, td, tx, args, grid, s);         \
-    if (aux_mode != 0) return launch<BNV, false, false, true>(ta, tb, td, tx, args, grid, s); \
-    return launch<BNV, false, false>(ta, tb, td, tx, args, grid, s);                 \
+#define IBM_GEMM_DISPATCH(BNV, CGV)                                                        \
+  do {                                                                                     \
+    if (accumulate) return launch<BNV, true, true, false, CGV>(ta, tb, td, tx, args, grid, s);   \
+    if (f32) return launch<BNV, true, false, false, CGV>(ta, tb, td, tx, args, grid, s);         \
+    if (aux_mode != 0) return launch<BNV, false, false, true, CGV>(ta, tb, td, tx, args, grid, s); \
+    return launch<BNV, false, false, false, CGV>(ta, tb, td, tx, args, grid, s);                 \
   } while (0)
+  if (cg == 2) {
+    if (bn == 256) IBM_GEMM_DISPATCH(256, 2);
+    IBM_GEMM_DISPATCH(128, 2);
+  }
   switch (bn) {
-    case 256: IBM_GEMM_DISPATCH(256);
-    case 128: IBM_GEMM_DISPATCH(128);
-    case 64: IBM_GEMM_DISPATCH(64);
+    case 256: IBM_GEMM_DISPATCH(256, 1);
+    case 128: IBM_GEMM_DISPATCH(128, 1);
+    case 64: IBM_GEMM_DISPATCH(64, 1);
     default:                          // BN = 32 exists for fp32 outputs only (bf16 chunks are 64 columns wide)
-      if (accumulate) return launch<32, true, true>(ta, tb, td, tx, args, grid, s);
-      return launch<32, true, false>(ta, tb, td, tx, args, grid, s);
+      if (accumulate) return launch<32, true, true, false, 1>(ta, tb, td, tx, args, grid, s);
+      return launch<32, true, false, false, 1>(ta, tb, td, tx, args, grid, s);
   }
 #undef IBM_GEMM_DISPATCH
 }
