@@ -10,9 +10,13 @@
 //                backward: dgrad = dY·W, wgrad = dYᵀ·X)
 //   nn.Conv1d  — /root/reference/src/models/Groundlink.py:41 (taps > 1: implicit GEMM over row-shifted A)
 //
-// Roles (256 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM → registers → swizzled smem → TMA store).
-// Tile 128 x BN x 64, UMMA 128 x BN x 16, cta_group::1; operand tiles in SWIZZLE_128B layout.
+// Roles (384 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4-11 = epilogue.  Each epilogue warp is an independent pipeline over
+// its own 32 accumulator rows (TMEM lane quadrant) and every other 128-byte column chunk: TMEM →
+// registers → its private swizzled staging rows → its own 32-row TMA store, with its own TMA-fed ring
+// of aux (residual / saved-activation) tiles — no block-wide barrier anywhere in the epilogue.
+// Tile 128 x BN x 64 per CTA; UMMA 128 x BN x 16 (cta_group::1) or 256 x BN x 16 across a CTA pair
+// (cta_group::2); operand tiles in SWIZZLE_128B layout.
 #include <cuda.h>
 
 #include <stdlib.h>
@@ -31,11 +35,11 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;      // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 384;      // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
-constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = 8;
 constexpr int kEpiWarp0 = 4;
-constexpr uint32_t kEpiBarrier = 1;
 constexpr int kStageA = BLOCK_M * BLOCK_K * 2;          // 16 KB
-constexpr int kOutStage = BLOCK_M * 128;                // 128 rows x 128 B = 16 KB
+constexpr int kWarpStage = 32 * 128;                    // one epilogue warp's staging tile: 32 rows x 128 B = 4 KB
+constexpr int kSmemCap = 227 * 1024;                    // opt-in dynamic shared memory per CTA on sm_100
 
 // CG = CTAs per MMA (cta_group): 1 = one 128 x BN tile per CTA; 2 = a CTA pair computes a 256 x BN tile, each CTA
 // holding its own 128 rows of A and HALF of the B tile (BN / 2 rows), which halves the B traffic through shared memory
@@ -44,13 +48,17 @@ constexpr int kOutStage = BLOCK_M * 128;                // 128 rows x 128 B = 16
 template <int BN, bool AUX, int CG>
 struct Cfg {
   static constexpr int kStageB = (BN / CG) * BLOCK_K * 2;
-  // AUX kernels give operand stages up for a 3-deep ring of aux chunk buffers (prefetched 2-3 chunks ahead)
-  static constexpr int kStages =
-      CG == 2 ? (AUX ? (BN == 256 ? 4 : 6) : (BN == 256 ? 6 : 8))
-              : (AUX ? ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8)));
-  static constexpr int kAuxBufs = AUX ? 3 : 0;
+  // per epilogue warp: output staging tiles (double-buffered; single when the aux ring also needs room) and a
+  // 2-deep ring of aux tiles, each loaded one of the warp's chunks ahead
+  static constexpr int kOutBufs = AUX ? 1 : 2;
+  static constexpr int kAuxBufs = AUX ? 2 : 0;
+  static constexpr int kEpiBytes = kEpiWarps * (kOutBufs + kAuxBufs) * kWarpStage;
+  static constexpr int kFixed = 1024 /*align slack*/ + kEpiBytes + 512 /*mbarriers, tmem slot*/;
+  static constexpr int kFit = (kSmemCap - kFixed) / (kStageA + kStageB);
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;                  // operand ring: whatever is left, at most 8
+  static_assert(kStages >= 2, "operand ring needs at least two stages");
   static constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmem = 1024 /*align slack*/ + kStages * (kStageA + kStageB) + (2 + kAuxBufs) * kOutStage + BN * 4 + 256;
+  static constexpr int kSmem = kFixed + kStages * (kStageA + kStageB);
 };
 
 struct Args {
@@ -85,28 +93,30 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// v holds acc + bias on entry
 template <int ACT, int PT>
-__device__ __forceinline__ void epi_plain(float (&v)[PT], const float* bs) {
+__device__ __forceinline__ void epi_plain(float (&v)[PT]) {
 #pragma unroll
-  for (int j = 0; j < PT; ++j) v[j] = act_t<ACT>(v[j] + bs[j]);
+  for (int j = 0; j < PT; ++j) v[j] = act_t<ACT>(v[j]);
 }
 template <int PT>
-__device__ __forceinline__ void epi_dispatch_plain(float (&v)[PT], const float* bs, int act) {
+__device__ __forceinline__ void epi_dispatch_plain(float (&v)[PT], int act) {
   switch (act) {
-    case IBM_ACT_NONE: epi_plain<IBM_ACT_NONE, PT>(v, bs); break;
-    case IBM_ACT_RELU: epi_plain<IBM_ACT_RELU, PT>(v, bs); break;
-    case IBM_ACT_SIGMOID: epi_plain<IBM_ACT_SIGMOID, PT>(v, bs); break;
-    case IBM_ACT_TANH: epi_plain<IBM_ACT_TANH, PT>(v, bs); break;
-    case IBM_ACT_ELU: epi_plain<IBM_ACT_ELU, PT>(v, bs); break;
-    default: epi_plain<IBM_ACT_SILU, PT>(v, bs); break;
+    case IBM_ACT_NONE: break;
+    case IBM_ACT_RELU: epi_plain<IBM_ACT_RELU, PT>(v); break;
+    case IBM_ACT_SIGMOID: epi_plain<IBM_ACT_SIGMOID, PT>(v); break;
+    case IBM_ACT_TANH: epi_plain<IBM_ACT_TANH, PT>(v); break;
+    case IBM_ACT_ELU: epi_plain<IBM_ACT_ELU, PT>(v); break;
+    default: epi_plain<IBM_ACT_SILU, PT>(v); break;
   }
 }
-// MODE 1: out = act(acc + bias) + aux;  MODE 2: out = (acc + bias) * act'(aux).  aux: bf16, 8 per 16-byte piece.
+// MODE 1: out = act(acc + bias) + aux;  MODE 2: out = (acc + bias) * act'(aux).  aux: bf16, 8 per 16-byte piece of
+// this thread's swizzled 128-byte row.
 template <int ACT, int MODE, int PT>
-__device__ __forceinline__ void epi_aux(float (&v)[PT], const float* bs, uint32_t xrow, int half, int rsw) {
+__device__ __forceinline__ void epi_aux(float (&v)[PT], uint32_t xrow, int rsw) {
 #pragma unroll
   for (int jj = 0; jj < PT / 8; ++jj) {
-    const uint4 u = ld_shared_v4(xrow + (((half * (PT / 8) + jj) ^ rsw) << 4));
+    const uint4 u = ld_shared_v4(xrow + ((jj ^ rsw) << 4));
     float y[8];
     float2 t;
     t = unpack_bf16x2(u.x); y[0] = t.x; y[1] = t.y;
@@ -115,27 +125,27 @@ __device__ __forceinline__ void epi_aux(float (&v)[PT], const float* bs, uint32_
     t = unpack_bf16x2(u.w); y[6] = t.x; y[7] = t.y;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float x = v[8 * jj + e] + bs[8 * jj + e];
+      const float x = v[8 * jj + e];
       v[8 * jj + e] = MODE == 1 ? act_t<ACT>(x) + y[e] : x * dact_t<ACT>(y[e]);
     }
   }
 }
 template <int PT>
-__device__ __forceinline__ void epi_dispatch_aux(float (&v)[PT], const float* bs, uint32_t xrow, int half, int rsw, int act, int mode) {
+__device__ __forceinline__ void epi_dispatch_aux(float (&v)[PT], uint32_t xrow, int rsw, int act, int mode) {
   if constexpr (PT % 8 == 0) {
     if (mode == 1) {
       switch (act) {
-        case IBM_ACT_NONE: epi_aux<IBM_ACT_NONE, 1, PT>(v, bs, xrow, half, rsw); break;
-        case IBM_ACT_RELU: epi_aux<IBM_ACT_RELU, 1, PT>(v, bs, xrow, half, rsw); break;
-        default: epi_aux<IBM_ACT_ELU, 1, PT>(v, bs, xrow, half, rsw); break;
+        case IBM_ACT_NONE: epi_aux<IBM_ACT_NONE, 1, PT>(v, xrow, rsw); break;
+        case IBM_ACT_RELU: epi_aux<IBM_ACT_RELU, 1, PT>(v, xrow, rsw); break;
+        default: epi_aux<IBM_ACT_ELU, 1, PT>(v, xrow, rsw); break;
       }
     } else {
       switch (act) {
-        case IBM_ACT_NONE: epi_aux<IBM_ACT_NONE, 2, PT>(v, bs, xrow, half, rsw); break;
-        case IBM_ACT_RELU: epi_aux<IBM_ACT_RELU, 2, PT>(v, bs, xrow, half, rsw); break;
-        case IBM_ACT_SIGMOID: epi_aux<IBM_ACT_SIGMOID, 2, PT>(v, bs, xrow, half, rsw); break;
-        case IBM_ACT_TANH: epi_aux<IBM_ACT_TANH, 2, PT>(v, bs, xrow, half, rsw); break;
-        default: epi_aux<IBM_ACT_ELU, 2, PT>(v, bs, xrow, half, rsw); break;
+        case IBM_ACT_NONE: epi_aux<IBM_ACT_NONE, 2, PT>(v, xrow, rsw); break;
+        case IBM_ACT_RELU: epi_aux<IBM_ACT_RELU, 2, PT>(v, xrow, rsw); break;
+        case IBM_ACT_SIGMOID: epi_aux<IBM_ACT_SIGMOID, 2, PT>(v, xrow, rsw); break;
+        case IBM_ACT_TANH: epi_aux<IBM_ACT_TANH, 2, PT>(v, xrow, rsw); break;
+        default: epi_aux<IBM_ACT_ELU, 2, PT>(v, xrow, rsw); break;
       }
     }
   }
@@ -152,15 +162,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + C::kStages * kStageA;
-  uint8_t* smem_out = smem_b + C::kStages * C::kStageB;              // 2 x 16 KB, 1024-aligned
-  uint8_t* smem_aux = smem_out + 2 * kOutStage;                      // kAuxBufs x 16 KB, 1024-aligned
-  float* smem_bias = reinterpret_cast<float*>(smem_aux + C::kAuxBufs * kOutStage);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_bias + BN);
+  uint8_t* smem_out = smem_b + C::kStages * C::kStageB;              // [8 warps][kOutBufs] x 4 KB, 1024-aligned
+  uint8_t* smem_aux = smem_out + kEpiWarps * C::kOutBufs * kWarpStage;   // [8 warps][kAuxBufs] x 4 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_aux + kEpiWarps * C::kAuxBufs * kWarpStage);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tfull_bar = empty_bar + C::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* aux_bar = tempty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 3);
+  uint64_t* aux_bar = tempty_bar + 2;                                // [8 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps * 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -173,8 +182,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     // the leader's MMA thread waits for the epilogue warps of BOTH CTAs of a pair before reusing an accumulator
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CG * kEpiThreads / 32); }
-    for (int i = 0; i < 3; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CG * kEpiWarps); }
+    for (int i = 0; i < kEpiWarps * 2; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -192,7 +201,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int worker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_workers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int total_work = args.tiles_m * args.tiles_n * args.splits;     // tiles_m counts CG*128-row blocks
+  // work w = split * n_tiles + tile: the work items in flight together are the tiles of ONE k split, so they stream the
+  // same rows of both operands at the same pace and share them through L2 (split-K weight gradients)
+  const int n_tiles = args.tiles_m * args.tiles_n;                       // tiles_m counts CG*128-row blocks
+  const int total_work = n_tiles * args.splits;
   constexpr int BN_LOAD = BN / CG;
 
   if (warp == 0) {
@@ -203,8 +215,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t tx_bytes = CG * (kStageA + C::kStageB);     // the pair's loads all complete on the leader's barrier
       const bool prefetch_aux = kAux;
       for (int w = worker; w < total_work; w += n_workers) {
-        const int split = w % args.splits;
-        const int tile = w / args.splits;
+        const int split = w / n_tiles;
+        const int tile = w - split * n_tiles;
         const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
         const int m0 = (tm * CG + rank) * BLOCK_M, n0 = tn * BN;
         const int nb0 = n0 + rank * BN_LOAD;                      // first B row this CTA loads
@@ -213,7 +225,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (prefetch_aux) {
           // the epilogue of this tile runs ~1.5 tile-times from now: pull its aux tile into L2 so the
           // epilogue's one-chunk-ahead TMA loads see L2 latency, not DRAM latency
-          for (int c = 0; c < BN && n0 + c < args.N; c += 64) tma_prefetch_l2_2d(&tmX, n0 + c, m0);
+          for (int c = 0; c < BN && n0 + c < args.N; c += 64)
+            for (int r = 0; r < BLOCK_M; r += 32) tma_prefetch_l2_2d(&tmX, n0 + c, m0 + r);
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -255,7 +268,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int w = worker; w < total_work; w += n_workers) {
-        const int split = w % args.splits;
+        const int split = w / n_tiles;
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
         mbar_wait(&tempty_bar[as], aphase ^ 1u);
@@ -286,100 +299,105 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= kEpiWarp0) {
     // ======================================= epilogue ========================================
-    // 8 warps: warp w may touch TMEM lanes [32*(w%4), +32); the two warps of a lane quadrant split each
-    // 128-byte chunk row between them (PT columns each), so the per-chunk instruction stream is half as long.
-    constexpr int CW = kOutF32 ? 32 : 64;           // columns per 128-byte staging row
-    constexpr int PT = CW / 2;                      // columns per thread per chunk
+    // warp (q, half): TMEM lanes [32q, +32) = tile rows [32q, +32); column chunks half, half+2, … of the tile.
+    // A chunk is one 128-byte staging row per thread: 64 bf16 or 32 fp32 columns.
+    constexpr int CW = kOutF32 ? 32 : 64;           // columns per chunk == columns per thread per chunk
+    constexpr int PT = CW;
     static_assert(BN >= CW, "an epilogue chunk must not be wider than the accumulator tile");
+    const int ew = warp - kEpiWarp0;                // 0..7
     const int q = warp & 3;                         // TMEM lane quadrant this warp may access
-    const int half = (warp - kEpiWarp0) >> 2;       // which half of the chunk's columns
-    const int et = threadIdx.x - kEpiWarp0 * 32;    // 0..255
-    const int r_local = q * 32 + lane;              // tile row == TMEM lane
-    const int rsw = r_local & 7;                    // SWIZZLE_128B: 16-byte piece j of row r lives at piece j ^ (r & 7)
-    const bool leader = (et == 0);
-    // bf16 aux tiles (residual / saved activation) stream through a 3-deep ring of TMA-loaded chunk buffers,
-    // issued 3 chunks ahead by the epilogue leader (and pulled into L2 a tile ahead by the producer), so the
-    // epilogue never waits on a global load nor on the completion of its own stores
+    const int half = ew >> 2;
+    const int rsw = lane & 7;                       // SWIZZLE_128B: 16-byte piece j of row r lives at piece j ^ (r & 7)
+    uint8_t* my_out = smem_out + ew * (C::kOutBufs * kWarpStage);
+    uint8_t* my_aux = smem_aux + ew * (C::kAuxBufs * kWarpStage);
+    uint64_t* my_aux_bar = aux_bar + ew * 2;
     int as = 0, ob = 0;
     uint32_t aphase = 0;
-    int xg = 0;                                     // chunks consumed so far by this CTA (aux ring position)
-    int pw = worker, pch = 0;                       // prefetch cursor: (work item, chunk) of the next aux load
+    int xg = 0;                                     // chunks consumed so far by this warp (aux ring position)
+    int pw = worker, pch = half;                    // prefetch cursor: (work item, chunk) of this warp's next aux load
     auto chunks_of = [&](int w) {
-      const int n0w = ((w / args.splits) % args.tiles_n) * BN;
+      const int n0w = ((w % n_tiles) % args.tiles_n) * BN;
       return ((int)min((int64_t)BN, args.N - n0w) + CW - 1) / CW;
     };
-    auto issue_aux = [&](int buf) {                 // leader only
+    auto issue_aux = [&](int buf) {                 // lane 0 only
+      while (pw < total_work && pch >= chunks_of(pw)) { pw += n_workers; pch = half; }
       if (pw >= total_work) return;
-      const int t2 = pw / args.splits;
-      mbar_arrive_expect_tx(&aux_bar[buf], kOutStage);
-      tma_load_2d(smem_aux + buf * kOutStage, &tmX, &aux_bar[buf], (t2 % args.tiles_n) * BN + pch * CW,
-                  ((t2 / args.tiles_n) * CG + rank) * BLOCK_M);
-      if (++pch == chunks_of(pw)) { pch = 0; pw += n_workers; }
+      const int t2 = pw % n_tiles;
+      mbar_arrive_expect_tx(&my_aux_bar[buf], kWarpStage);
+      tma_load_2d(my_aux + buf * kWarpStage, &tmX, &my_aux_bar[buf], (t2 % args.tiles_n) * BN + pch * CW,
+                  ((t2 / args.tiles_n) * CG + rank) * BLOCK_M + q * 32);
+      pch += 2;
     };
-    if (kAux && leader) {
-      for (int i = 0; i < 3; ++i) issue_aux(i);
+    if (kAux && lane == 0) {
+      issue_aux(0);
+      issue_aux(1);
     }
+    auto release_tmem = [&]() {                     // this warp has read everything it needs from accumulator `as`
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[as], 0);
+        else mbar_arrive(&tempty_bar[as]);
+      }
+    };
     for (int w = worker; w < total_work; w += n_workers) {
-      const int tile = w / args.splits;
+      const int tile = w % n_tiles;
       const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
-      const int m0 = (tm * CG + rank) * BLOCK_M, n0 = tn * BN;
-      const int64_t row = (int64_t)m0 + r_local;
+      const int m0 = (tm * CG + rank) * BLOCK_M + q * 32, n0 = tn * BN;       // this warp's first row
       const int n_valid = (int)min((int64_t)BN, args.N - n0);
       const int n_chunks = (n_valid + CW - 1) / CW;
 
-      // stage this tile's bias slice (previous tile's readers are past their last named barrier)
-      if (!kAccum) {
-        for (int i = et; i < BN; i += kEpiThreads)
-          smem_bias[i] = (args.bias != nullptr && n0 + i < args.N) ? __ldg(args.bias + n0 + i) : 0.f;
-      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
+      if (half >= n_chunks) release_tmem();         // narrow tile: nothing for this warp, but the MMA warp counts it
 
-      for (int ch = 0; ch < n_chunks; ++ch) {
+      for (int ch = half; ch < n_chunks; ch += 2) {
         float v[PT];
-        if (kOutF32) tmem_ld_32x16(tmem_acc + ch * CW + half * PT, reinterpret_cast<uint32_t*>(v));
-        else tmem_ld_32x32(tmem_acc + ch * CW + half * PT, reinterpret_cast<uint32_t*>(v));
+#pragma unroll
+        for (int i = 0; i < PT / 32; ++i) tmem_ld_32x32(tmem_acc + ch * CW + i * 32, reinterpret_cast<uint32_t*>(v) + i * 32);
         const int c0 = n0 + ch * CW;               // global column of the chunk
-        const uint32_t srow = smem_u32(smem_out + ob * kOutStage + r_local * 128);
-        const int xb = xg % 3;
-        const uint32_t xrow = smem_u32(smem_aux + xb * kOutStage + r_local * 128);
-        if (kAux) mbar_wait(&aux_bar[xb], (uint32_t)((xg / 3) & 1));     // this chunk's aux tile has landed
+        const int xb = xg & 1;
+        if (kAux) mbar_wait(&my_aux_bar[xb], (uint32_t)((xg >> 1) & 1));     // this chunk's aux tile has landed
         tmem_ld_wait();
-        if (ch == n_chunks - 1) {
-          // all TMEM reads of this accumulator are done → hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[as], 0);
-            else mbar_arrive(&tempty_bar[as]);
-          }
-        }
-        // make sure the staging buffer `ob` is no longer being read by the store issued 2 chunks ago,
-        // and (first chunk) that the bias slice is visible
-        if (leader) tma_wait_group_read<1>();
-        named_bar_sync(kEpiBarrier, kEpiThreads);
+        if (ch + 2 >= n_chunks) release_tmem();
 
         if (!kAccum) {
-          const float* bs = smem_bias + ch * CW + half * PT;
+          if (args.bias != nullptr) {
+            if (c0 + PT <= args.N) {
+              const float4* b4 = reinterpret_cast<const float4*>(args.bias + c0);
+#pragma unroll
+              for (int j = 0; j < PT / 4; ++j) {
+                const float4 b = __ldg(b4 + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < PT; ++j) v[j] += (c0 + j < args.N) ? __ldg(args.bias + c0 + j) : 0.f;
+            }
+          }
           if (kAux) {
-            epi_dispatch_aux<PT>(v, bs, xrow, half, rsw, args.act, args.aux_mode);
+            epi_dispatch_aux<PT>(v, smem_u32(my_aux + xb * kWarpStage + lane * 128), rsw, args.act, args.aux_mode);
           } else {
-            epi_dispatch_plain<PT>(v, bs, args.act);
+            epi_dispatch_plain<PT>(v, args.act);
             if (args.aux_mode != 0) {
               // fp32-output fallback: aux read straight from global memory (not on the training path)
-              const __nv_bfloat16* ap = args.aux + row * args.ldaux + c0 + half * PT;
+              const int64_t row = (int64_t)m0 + lane;
+              const __nv_bfloat16* ap = args.aux + row * args.ldaux + c0;
 #pragma unroll
               for (int j = 0; j < PT; ++j) {
-                const float y = (row < args.M && c0 + half * PT + j < args.N) ? __bfloat162float(ap[j]) : 0.f;
+                const float y = (row < args.M && c0 + j < args.N) ? __bfloat162float(ap[j]) : 0.f;
                 v[j] = args.aux_mode == 1 ? v[j] + y : v[j] * act_grad_from_output(y, args.act);
               }
             }
           }
         }
-        // registers → swizzled staging rows: this thread owns 16-byte pieces half*4 … half*4+3 of its row
+        // the staging tile `ob` must no longer be read by the store issued kOutBufs chunks ago
+        if (lane == 0) tma_wait_group_read<C::kOutBufs - 1>();
+        __syncwarp();
+        const uint32_t srow = smem_u32(my_out + ob * kWarpStage + lane * 128);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < 8; ++jj) {
           uint4 pk;
           if (kOutF32) {
             pk = make_uint4(__float_as_uint(v[4 * jj]), __float_as_uint(v[4 * jj + 1]), __float_as_uint(v[4 * jj + 2]),
@@ -388,22 +406,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             pk = make_uint4(pack_bf16x2(v[8 * jj], v[8 * jj + 1]), pack_bf16x2(v[8 * jj + 2], v[8 * jj + 3]),
                             pack_bf16x2(v[8 * jj + 4], v[8 * jj + 5]), pack_bf16x2(v[8 * jj + 6], v[8 * jj + 7]));
           }
-          st_shared_v4(srow + (((half * 4 + jj) ^ rsw) << 4), pk);
+          st_shared_v4(srow + ((jj ^ rsw) << 4), pk);
         }
         fence_proxy_async_smem();
-        named_bar_sync(kEpiBarrier, kEpiThreads);
-        if (leader) {
-          if (kAccum) tma_reduce_add_2d(&tmD, smem_out + ob * kOutStage, c0, m0);
-          else tma_store_2d(&tmD, smem_out + ob * kOutStage, c0, m0);
+        __syncwarp();
+        if (lane == 0) {
+          if (kAccum) tma_reduce_add_2d(&tmD, my_out + ob * kWarpStage, c0, m0);
+          else tma_store_2d(&tmD, my_out + ob * kWarpStage, c0, m0);
           tma_commit_group();
-          if (kAux) issue_aux(xb);                // every thread is past the barrier: aux buffer xb is free again
+          if (kAux) issue_aux(xb);                // every lane is past its reads of aux tile xb
         }
-        ob ^= 1;
+        if (++ob == C::kOutBufs) ob = 0;
         ++xg;
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
-    if (leader) tma_wait_group<0>();      // all global writes issued by this CTA are complete
+    if (lane == 0) tma_wait_group<0>();   // all global writes issued by this warp are complete
   }
 
   // ---- teardown ----
@@ -550,7 +568,19 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   int splits = 1;
   if (accumulate) {
     const int64_t tiles = (int64_t)args.tiles_m * args.tiles_n;
-    splits = split_k > 0 ? split_k : (int)ceil_div(2 * (sms / cg), tiles);
+    if (split_k > 0) {
+      splits = split_k;
+    } else {
+      // fill whole rounds of the persistent grid: most work per round among 1..4 rounds, fewest splits on a tie
+      const int workers = sms / cg;
+      double best = 0.0;
+      for (int rounds = 1; rounds <= 4; ++rounds) {
+        const int sp = (int)((int64_t)rounds * workers / tiles) > 0 ? (int)((int64_t)rounds * workers / tiles) : 1;
+        const int64_t wk = tiles * sp;
+        const double eff = (double)wk / (double)(ceil_div(wk, workers) * workers);
+        if (eff > best + 0.02) { best = eff; splits = sp; }
+      }
+    }
     int max_splits = args.kb_total / 8 > 0 ? args.kb_total / 8 : 1;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -575,11 +605,11 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   else rc = make_map(&tb, B, false, N, K, ldb, 64, BLOCK_K);
   if (rc) return rc;
   const bool f32 = out_dtype == IBM_F32;
-  rc = make_map(&td, D, f32, N, M, ldd, f32 ? 32 : 64, BLOCK_M);
+  rc = make_map(&td, D, f32, N, M, ldd, f32 ? 32 : 64, 32);           // one epilogue warp's 32-row tile
   if (rc) return rc;
-  CUtensorMap tx = td;                       // aux tile map (bf16 [M,N], same 64 x 128 box as the bf16 store)
+  CUtensorMap tx = td;                       // aux tile map (bf16 [M,N], same 64 x 32 box as the bf16 store)
   if (aux_mode != 0 && !f32 && !accumulate) {
-    rc = make_map(&tx, aux, false, N, M, ldaux, 64, BLOCK_M);
+    rc = make_map(&tx, aux, false, N, M, ldaux, 64, 32);
     if (rc) return rc;
   }
 
