@@ -232,10 +232,12 @@ int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, co
                       void* o, int64_t ldo, int64_t n_win, int32_t T, int32_t H, int32_t hd_qk,
                       int32_t hd_v, float scale, void* stream);
 /* dqkv (same layout as qkv: q | k | v blocks kv_off columns apart) from d_o; probabilities are
- * recomputed on chip.  T <= 64, head_dim in {32,48,64}. */
+ * recomputed on chip.  T <= 64, head_dim in {32,48,64}.  dbias_qkv (may be NULL): fp32
+ * [2*kv_off + H*head_dim] vector that the column sums of dqkv are ADDED to — the gradient of
+ * nn.MultiheadAttention.in_proj_bias (TransformerBaseline.py:12) without a second pass over dqkv. */
 int ibm_attention_bwd(const void* qkv, int64_t ld_qkv, int64_t kv_off, const void* d_o, int64_t ld_o,
                       void* dqkv, int64_t n_win, int32_t T, int32_t H, int32_t head_dim, float scale,
-                      void* stream);
+                      float* dbias_qkv, void* stream);
 
 /* ---- optimizers  (src/cli/train.py:183-197, 284; torch.optim defaults) ------------------------ */
 

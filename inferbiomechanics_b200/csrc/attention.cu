@@ -160,167 +160,359 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfl
   }
 }
 
-// ---------------------------------------- backward (T <= 64) -----------------------------------
-// dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(P o dP)), dQ = scale dS K, dK = scale dS^T Q.
+// ------------------------------- pipelined kernels (T <= 64) -----------------------------------
+// One CTA = 4 warps = the 64 (padded) query rows of one (window, head).  CTAs are persistent over the windows of ONE
+// head: the Q/K/V (and dO) tiles of the next window stream into the other half of a two-stage shared-memory ring with
+// cp.async while the current window is computed, so the kernel is bound by HBM rather than by load latency (the
+// one-shot kernels above/before measured 2.5 TB/s forward, 2.0 TB/s backward; profiles/r01a).  Rows >= T of every
+// tile are zero for the whole kernel: they are cleared once and the loads only touch rows < T.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int W, int LDS>
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t ld, int T) {
+  constexpr int CPR = W / 8;
+  for (int i = threadIdx.x; i < T * CPR; i += kThreads) {
+    const int r = i / CPR, c = (i - r * CPR) * 8;
+    cp_async16(dst + r * LDS + c, src + (int64_t)r * ld + c);
+  }
+}
+// a warp's 16 staged rows (row stride LDS) → global rows, 16 bytes per lane, whole 128-byte lines per 8 lanes
+template <int W, int LDS>
+__device__ __forceinline__ void store_rows16(const __nv_bfloat16* stage, __nv_bfloat16* dst, int64_t ld, int r_first, int T, int lane) {
+  constexpr int CPR = W / 8;
+#pragma unroll
+  for (int i = lane; i < 16 * CPR; i += 32) {
+    const int r = i / CPR, c = (i - r * CPR) * 8;
+    if (r_first + r < T)
+      st_stream16(dst + (int64_t)(r_first + r) * ld + c, *reinterpret_cast<const uint4*>(stage + (r_first + r) * LDS + c));
+  }
+}
+
 template <int HD>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
+attn_fwd_pipe_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
+                     const __nv_bfloat16* __restrict__ v, int64_t ldv, __nv_bfloat16* __restrict__ o, int64_t ldo, int T,
+                     int H, int64_t n_win, float scale_log2) {
+  constexpr int LD = HD + kPad;
+  constexpr int TILE = 64 * LD;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(smem_attn);          // [2 stages][Q | K | V]
+  const int h = blockIdx.x % H;
+  const int64_t cta = blockIdx.x / H, ctas = gridDim.x / H;
+  for (int i = threadIdx.x; i < 2 * 3 * TILE / 8; i += kThreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  auto load_item = [&](int64_t win, int stage) {
+    const int64_t row0 = win * T;
+    __nv_bfloat16* Qs = base + stage * 3 * TILE;
+    load_tile_async<HD, LD>(Qs, q + row0 * ldq + h * HD, ldq, T);
+    load_tile_async<HD, LD>(Qs + TILE, k + row0 * ldk + h * HD, ldk, T);
+    load_tile_async<HD, LD>(Qs + 2 * TILE, v + row0 * ldv + h * HD, ldv, T);
+  };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = warp * 16 + g;                      // this thread's query rows: r0 and r0 + 8
+  int64_t win = cta;
+  if (win < n_win) load_item(win, 0);
+  cp_async_commit();
+  for (int it = 0; win < n_win; win += ctas, ++it) {
+    const int st = it & 1;
+    if (win + ctas < n_win) load_item(win + ctas, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    __nv_bfloat16* Qs = base + st * 3 * TILE;
+    const __nv_bfloat16* Ks = Qs + TILE;
+    const __nv_bfloat16* Vs = Qs + 2 * TILE;
+
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t qa[4];
+      const __nv_bfloat16* qp = Qs + r0 * LD + kk * 16 + 2 * t;
+      qa[0] = *reinterpret_cast<const uint32_t*>(qp);          qa[1] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD);
+      qa[2] = *reinterpret_cast<const uint32_t*>(qp + 8);      qa[3] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD + 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat16* kp = Ks + (j * 8 + g) * LD + kk * 16 + 2 * t;
+        mma16816(s[j], qa, *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = j * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = (key + (e & 1) < T) ? s[j][e] * scale_log2 : -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f(s[j][0] - mx0); s[j][1] = exp2f(s[j][1] - mx0);
+      s[j][2] = exp2f(s[j][2] - mx1); s[j][3] = exp2f(s[j][3] - mx1);
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    float oacc[HD / 8][4];
+#pragma unroll
+    for (int j = 0; j < HD / 8; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int j = 0; j < HD / 8; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, Vs + (kk * 16 + (lane & 15)) * LD + j * 8);
+        mma16816(oacc[j], pa, b0, b1);
+      }
+    }
+    // O → this warp's own (now dead) Q rows → coalesced 16-byte stores.  Rows >= T stay zero.
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < HD / 8; ++j) {
+      if (r0 < T) *reinterpret_cast<uint32_t*>(Qs + r0 * LD + j * 8 + 2 * t) = pack_bf16x2(oacc[j][0] * inv0, oacc[j][1] * inv0);
+      if (r0 + 8 < T) *reinterpret_cast<uint32_t*>(Qs + (r0 + 8) * LD + j * 8 + 2 * t) = pack_bf16x2(oacc[j][2] * inv1, oacc[j][3] * inv1);
+    }
+    __syncwarp();
+    store_rows16<HD, LD>(Qs, o + win * T * ldo + h * HD, ldo, warp * 16, T, lane);
+    __syncthreads();                                 // stage st is free for the load issued next iteration
+  }
+}
+
+// dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(P o dP)), dQ = scale dS K, dK = scale dS^T Q.
+// dbias (optional): fp32 [3 * kv_off'] accumulators of the column sums of dqkv — the in-projection bias gradient
+// (TransformerBaseline.py:12 in_proj_bias) — kept in registers over all windows of this CTA's head.
+template <int HD>
+__global__ void __launch_bounds__(kThreads, 3)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_off, const __nv_bfloat16* __restrict__ dout,
-                int64_t ldo, __nv_bfloat16* __restrict__ dqkv, int T, int H, float scale) {
+                int64_t ldo, __nv_bfloat16* __restrict__ dqkv, int T, int H, int64_t n_win, float scale,
+                float* __restrict__ dbias) {
   constexpr int LD = HD + kPad;       // Q / dO tiles [64][LD]
   constexpr int LP = 64 + kPad;       // P / dS tiles [64][LP]
   constexpr int LX = LD > LP ? LD : LP;   // K and V tiles use this stride: P and dS later overwrite them in place
+  constexpr int STAGE = 2 * 64 * LD + 2 * 64 * LX;
   extern __shared__ __align__(16) uint8_t smem_attn[];
-  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-  __nv_bfloat16* dOs = Qs + 64 * LD;
-  __nv_bfloat16* Ks = dOs + 64 * LD;
-  __nv_bfloat16* Vs = Ks + 64 * LX;
-  __nv_bfloat16* Ps = Ks;             // valid after the barrier that ends phase 1 (K, V no longer needed)
-  __nv_bfloat16* dSs = Vs;
-
+  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(smem_attn);          // [2 stages][Q | dO | K | V]
   const int h = blockIdx.x % H;
-  const int64_t win = blockIdx.x / H;
-  const int64_t row0 = win * T;
-  const __nv_bfloat16* base = qkv + row0 * ld + h * HD;
-  load_tile<HD, LD>(Qs, base, ld, 64, T);
-  load_tile<HD, LX>(Ks, base + kv_off, ld, 64, T);
-  load_tile<HD, LX>(Vs, base + 2 * kv_off, ld, 64, T);
-  load_tile<HD, LD>(dOs, dout + row0 * ldo + h * HD, ldo, 64, T);
+  const int64_t cta = blockIdx.x / H, ctas = gridDim.x / H;
+  for (int i = threadIdx.x; i < 2 * STAGE / 8; i += kThreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  auto load_item = [&](int64_t win, int stage) {
+    const int64_t row0 = win * T;
+    __nv_bfloat16* Qs = base + stage * STAGE;
+    const __nv_bfloat16* src = qkv + row0 * ld + h * HD;
+    load_tile_async<HD, LD>(Qs, src, ld, T);
+    load_tile_async<HD, LD>(Qs + 64 * LD, dout + row0 * ldo + h * HD, ldo, T);
+    load_tile_async<HD, LX>(Qs + 2 * 64 * LD, src + kv_off, ld, T);
+    load_tile_async<HD, LX>(Qs + 2 * 64 * LD + 64 * LX, src + 2 * kv_off, ld, T);
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int r0 = warp * 16 + g;                      // rows r0, r0+8 (queries in phase 1, keys in phase 2)
   const float scale_log2 = scale * 1.4426950408889634f;
+  float cq[HD / 8][2], ck[HD / 8][2], cv[HD / 8][2];  // column sums of dq / dk / dv over this thread's rows, all windows
+#pragma unroll
+  for (int j = 0; j < HD / 8; ++j) { cq[j][0] = cq[j][1] = ck[j][0] = ck[j][1] = cv[j][0] = cv[j][1] = 0.f; }
 
-  // ---- phase 1: this warp owns 16 query rows ----
-  float s[8][4], dp[8][4];
+  int64_t win = cta;
+  if (win < n_win) load_item(win, 0);
+  cp_async_commit();
+  for (int it = 0; win < n_win; win += ctas, ++it) {
+    const int st = it & 1;
+    if (win + ctas < n_win) load_item(win + ctas, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    __nv_bfloat16* Qs = base + st * STAGE;
+    __nv_bfloat16* dOs = Qs + 64 * LD;
+    __nv_bfloat16* Ks = dOs + 64 * LD;
+    __nv_bfloat16* Vs = Ks + 64 * LX;
+    __nv_bfloat16* Ps = Ks;             // valid after the barrier that ends phase 1 (K, V no longer needed)
+    __nv_bfloat16* dSs = Vs;
+    const int64_t row0 = win * T;
+
+    // ---- phase 1: this warp owns 16 query rows ----
+    float s[8][4], dp[8][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+    for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
 #pragma unroll
-  for (int kk = 0; kk < HD / 16; ++kk) {
-    uint32_t qa[4], da[4];
-    const __nv_bfloat16* qp = Qs + r0 * LD + kk * 16 + 2 * t;
-    const __nv_bfloat16* dpp = dOs + r0 * LD + kk * 16 + 2 * t;
-    qa[0] = *reinterpret_cast<const uint32_t*>(qp);          qa[1] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD);
-    qa[2] = *reinterpret_cast<const uint32_t*>(qp + 8);      qa[3] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD + 8);
-    da[0] = *reinterpret_cast<const uint32_t*>(dpp);         da[1] = *reinterpret_cast<const uint32_t*>(dpp + 8 * LD);
-    da[2] = *reinterpret_cast<const uint32_t*>(dpp + 8);     da[3] = *reinterpret_cast<const uint32_t*>(dpp + 8 * LD + 8);
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t qa[4], da[4];
+      const __nv_bfloat16* qp = Qs + r0 * LD + kk * 16 + 2 * t;
+      const __nv_bfloat16* dpp = dOs + r0 * LD + kk * 16 + 2 * t;
+      qa[0] = *reinterpret_cast<const uint32_t*>(qp);          qa[1] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD);
+      qa[2] = *reinterpret_cast<const uint32_t*>(qp + 8);      qa[3] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD + 8);
+      da[0] = *reinterpret_cast<const uint32_t*>(dpp);         da[1] = *reinterpret_cast<const uint32_t*>(dpp + 8 * LD);
+      da[2] = *reinterpret_cast<const uint32_t*>(dpp + 8);     da[3] = *reinterpret_cast<const uint32_t*>(dpp + 8 * LD + 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat16* kp = Ks + (j * 8 + g) * LX + kk * 16 + 2 * t;
+        const __nv_bfloat16* vp = Vs + (j * 8 + g) * LX + kk * 16 + 2 * t;
+        mma16816(s[j], qa, *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+        mma16816(dp[j], da, *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const __nv_bfloat16* kp = Ks + (j * 8 + g) * LX + kk * 16 + 2 * t;
-      const __nv_bfloat16* vp = Vs + (j * 8 + g) * LX + kk * 16 + 2 * t;
-      mma16816(s[j], qa, *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
-      mma16816(dp[j], da, *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
+      const int key = j * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = (key + (e & 1) < T) ? s[j][e] * scale_log2 : -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
-  }
-  float mx0 = -INFINITY, mx1 = -INFINITY;
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int key = j * 8 + 2 * t;
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f(s[j][0] - mx0); s[j][1] = exp2f(s[j][1] - mx0);
+      s[j][2] = exp2f(s[j][2] - mx1); s[j][3] = exp2f(s[j][3] - mx1);
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // padded query rows (>= T) get P = 0 so that the K tile they later alias keeps zero pad rows
+    const float inv0 = r0 < T ? 1.f / l0 : 0.f, inv1 = r0 + 8 < T ? 1.f / l1 : 0.f;
+    float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) s[j][e] = (key + (e & 1) < T) ? s[j][e] * scale_log2 : -INFINITY;
-    mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-    mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
-  }
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  float l0 = 0.f, l1 = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] *= inv0; s[j][1] *= inv0; s[j][2] *= inv1; s[j][3] *= inv1;      // P
+      d0 += s[j][0] * dp[j][0] + s[j][1] * dp[j][1];
+      d1 += s[j][2] * dp[j][2] + s[j][3] * dp[j][3];
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    uint32_t dsa[4][4];                                  // scale*dS as A fragments for dQ = dS K
+    uint32_t ppk[8][2];                                  // P (bf16 pairs), parked in registers until K/V are dead
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    s[j][0] = exp2f(s[j][0] - mx0); s[j][1] = exp2f(s[j][1] - mx0);
-    s[j][2] = exp2f(s[j][2] - mx1); s[j][3] = exp2f(s[j][3] - mx1);
-    l0 += s[j][0] + s[j][1];
-    l1 += s[j][2] + s[j][3];
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-  float d0 = 0.f, d1 = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const float e0 = scale * s[j][0] * (dp[j][0] - d0), e1 = scale * s[j][1] * (dp[j][1] - d0);
+      const float e2 = scale * s[j][2] * (dp[j][2] - d1), e3 = scale * s[j][3] * (dp[j][3] - d1);
+      ppk[j][0] = pack_bf16x2(s[j][0], s[j][1]);
+      ppk[j][1] = pack_bf16x2(s[j][2], s[j][3]);
+      dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(e0, e1);
+      dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(e2, e3);
+    }
+    {
+      float dq[HD / 8][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    s[j][0] *= inv0; s[j][1] *= inv0; s[j][2] *= inv1; s[j][3] *= inv1;      // P
-    d0 += s[j][0] * dp[j][0] + s[j][1] * dp[j][1];
-    d1 += s[j][2] * dp[j][2] + s[j][3] * dp[j][3];
-  }
-  d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
-  d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-  uint32_t dsa[4][4];                                  // scale*dS as A fragments for dQ = dS K
-  uint32_t ppk[8][2];                                  // P (bf16 pairs), parked in registers until K/V are dead
+      for (int j = 0; j < HD / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float e0 = scale * s[j][0] * (dp[j][0] - d0), e1 = scale * s[j][1] * (dp[j][1] - d0);
-    const float e2 = scale * s[j][2] * (dp[j][2] - d1), e3 = scale * s[j][3] * (dp[j][3] - d1);
-    const uint32_t p01 = pack_bf16x2(s[j][0], s[j][1]), p23 = pack_bf16x2(s[j][2], s[j][3]);
-    const uint32_t s01 = pack_bf16x2(e0, e1), s23 = pack_bf16x2(e2, e3);
-    ppk[j][0] = p01;
-    ppk[j][1] = p23;
-    dsa[j >> 1][(j & 1) * 2] = s01;
-    dsa[j >> 1][(j & 1) * 2 + 1] = s23;
-  }
-  {
-    float dq[HD / 8][4];
+      for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-    for (int j = 0; j < HD / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+        for (int j = 0; j < HD / 8; ++j) {
+          uint32_t b0, b1;
+          ldsm_x2_trans(b0, b1, Ks + (kk * 16 + (lane & 15)) * LX + j * 8);
+          mma16816(dq[j], dsa[kk], b0, b1);
+        }
+      }
+      __nv_bfloat16* g0 = dqkv + (row0 + r0) * ld + h * HD + 2 * t;
+      __nv_bfloat16* g1 = g0 + 8 * ld;
 #pragma unroll
       for (int j = 0; j < HD / 8; ++j) {
-        uint32_t b0, b1;
-        ldsm_x2_trans(b0, b1, Ks + (kk * 16 + (lane & 15)) * LX + j * 8);
-        mma16816(dq[j], dsa[kk], b0, b1);
+        const uint32_t lo = pack_bf16x2(dq[j][0], dq[j][1]), hi = pack_bf16x2(dq[j][2], dq[j][3]);
+        if (r0 < T) *reinterpret_cast<uint32_t*>(g0 + j * 8) = lo;
+        if (r0 + 8 < T) *reinterpret_cast<uint32_t*>(g1 + j * 8) = hi;
+        // bias gradient sums the ROUNDED values (what the in-projection weight-gradient GEMM reads); rows >= T are 0
+        const float2 a = unpack_bf16x2(lo), b = unpack_bf16x2(hi);
+        cq[j][0] += a.x + b.x;
+        cq[j][1] += a.y + b.y;
       }
     }
-    __nv_bfloat16* g0 = dqkv + (row0 + r0) * ld + h * HD + 2 * t;
-    __nv_bfloat16* g1 = g0 + 8 * ld;
+    __syncthreads();                                     // every warp is done reading K and V
 #pragma unroll
-    for (int j = 0; j < HD / 8; ++j) {
-      if (r0 < T) *reinterpret_cast<uint32_t*>(g0 + j * 8) = pack_bf16x2(dq[j][0], dq[j][1]);
-      if (r0 + 8 < T) *reinterpret_cast<uint32_t*>(g1 + j * 8) = pack_bf16x2(dq[j][2], dq[j][3]);
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<uint32_t*>(Ps + r0 * LP + j * 8 + 2 * t) = ppk[j][0];
+      *reinterpret_cast<uint32_t*>(Ps + (r0 + 8) * LP + j * 8 + 2 * t) = ppk[j][1];
+      *reinterpret_cast<uint32_t*>(dSs + r0 * LP + j * 8 + 2 * t) = dsa[j >> 1][(j & 1) * 2];
+      *reinterpret_cast<uint32_t*>(dSs + (r0 + 8) * LP + j * 8 + 2 * t) = dsa[j >> 1][(j & 1) * 2 + 1];
     }
-  }
-  __syncthreads();                                     // every warp is done reading K and V
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    *reinterpret_cast<uint32_t*>(Ps + r0 * LP + j * 8 + 2 * t) = ppk[j][0];
-    *reinterpret_cast<uint32_t*>(Ps + (r0 + 8) * LP + j * 8 + 2 * t) = ppk[j][1];
-    *reinterpret_cast<uint32_t*>(dSs + r0 * LP + j * 8 + 2 * t) = dsa[j >> 1][(j & 1) * 2];
-    *reinterpret_cast<uint32_t*>(dSs + (r0 + 8) * LP + j * 8 + 2 * t) = dsa[j >> 1][(j & 1) * 2 + 1];
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- phase 2: this warp owns 16 key rows: dV = P^T dO, dK = (scale dS)^T Q ----
-  {
-    float dv[HD / 8][4], dk[HD / 8][4];
+    // ---- phase 2: this warp owns 16 key rows: dV = P^T dO, dK = (scale dS)^T Q ----
+    {
+      float dv[HD / 8][4], dk[HD / 8][4];
 #pragma unroll
-    for (int j = 0; j < HD / 8; ++j) { dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f; dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f; }
-    const int kr = warp * 16;
-    // x4.trans address pattern: matrices (q-rows 0-7 | keys 0-7), (q 0-7 | keys 8-15), (q 8-15 | keys 0-7), (q 8-15 | keys 8-15)
-    const int qoff = (lane & 7) + ((lane >> 4) << 3);
-    const int koff = ((lane >> 3) & 1) << 3;
+      for (int j = 0; j < HD / 8; ++j) { dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f; dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f; }
+      const int kr = warp * 16;
+      // x4.trans address pattern: matrices (q-rows 0-7 | keys 0-7), (q 0-7 | keys 8-15), (q 8-15 | keys 0-7), (q 8-15 | keys 8-15)
+      const int qoff = (lane & 7) + ((lane >> 4) << 3);
+      const int koff = ((lane >> 3) & 1) << 3;
 #pragma unroll
-    for (int kq = 0; kq < 4; ++kq) {
-      uint32_t pa[4], sa[4];
-      ldsm_x4_trans(pa, Ps + (kq * 16 + qoff) * LP + kr + koff);
-      ldsm_x4_trans(sa, dSs + (kq * 16 + qoff) * LP + kr + koff);
+      for (int kq = 0; kq < 4; ++kq) {
+        uint32_t pa[4], sa[4];
+        ldsm_x4_trans(pa, Ps + (kq * 16 + qoff) * LP + kr + koff);
+        ldsm_x4_trans(sa, dSs + (kq * 16 + qoff) * LP + kr + koff);
+#pragma unroll
+        for (int j = 0; j < HD / 8; ++j) {
+          uint32_t b0, b1;
+          ldsm_x2_trans(b0, b1, dOs + (kq * 16 + (lane & 15)) * LD + j * 8);
+          mma16816(dv[j], pa, b0, b1);
+          ldsm_x2_trans(b0, b1, Qs + (kq * 16 + (lane & 15)) * LD + j * 8);
+          mma16816(dk[j], sa, b0, b1);
+        }
+      }
+      __nv_bfloat16* gk0 = dqkv + (row0 + r0) * ld + kv_off + h * HD + 2 * t;
+      __nv_bfloat16* gv0 = gk0 + kv_off;
 #pragma unroll
       for (int j = 0; j < HD / 8; ++j) {
-        uint32_t b0, b1;
-        ldsm_x2_trans(b0, b1, dOs + (kq * 16 + (lane & 15)) * LD + j * 8);
-        mma16816(dv[j], pa, b0, b1);
-        ldsm_x2_trans(b0, b1, Qs + (kq * 16 + (lane & 15)) * LD + j * 8);
-        mma16816(dk[j], sa, b0, b1);
+        const uint32_t klo = pack_bf16x2(dk[j][0], dk[j][1]), khi = pack_bf16x2(dk[j][2], dk[j][3]);
+        const uint32_t vlo = pack_bf16x2(dv[j][0], dv[j][1]), vhi = pack_bf16x2(dv[j][2], dv[j][3]);
+        if (r0 < T) {
+          *reinterpret_cast<uint32_t*>(gk0 + j * 8) = klo;
+          *reinterpret_cast<uint32_t*>(gv0 + j * 8) = vlo;
+        }
+        if (r0 + 8 < T) {
+          *reinterpret_cast<uint32_t*>(gk0 + 8 * ld + j * 8) = khi;
+          *reinterpret_cast<uint32_t*>(gv0 + 8 * ld + j * 8) = vhi;
+        }
+        float2 a = unpack_bf16x2(klo), b = unpack_bf16x2(khi);
+        ck[j][0] += a.x + b.x; ck[j][1] += a.y + b.y;
+        a = unpack_bf16x2(vlo); b = unpack_bf16x2(vhi);
+        cv[j][0] += a.x + b.x; cv[j][1] += a.y + b.y;
       }
     }
-    __nv_bfloat16* gk0 = dqkv + (row0 + r0) * ld + kv_off + h * HD + 2 * t;
-    __nv_bfloat16* gv0 = gk0 + kv_off;
+    __syncthreads();                                     // stage st (incl. the P / dS aliases) is free again
+  }
+
+  if (dbias != nullptr) {
+    // reduce over the 8 row groups of the warp (lanes that share t), then one atomic per column per warp
 #pragma unroll
     for (int j = 0; j < HD / 8; ++j) {
-      if (r0 < T) {
-        *reinterpret_cast<uint32_t*>(gk0 + j * 8) = pack_bf16x2(dk[j][0], dk[j][1]);
-        *reinterpret_cast<uint32_t*>(gv0 + j * 8) = pack_bf16x2(dv[j][0], dv[j][1]);
-      }
-      if (r0 + 8 < T) {
-        *reinterpret_cast<uint32_t*>(gk0 + 8 * ld + j * 8) = pack_bf16x2(dk[j][2], dk[j][3]);
-        *reinterpret_cast<uint32_t*>(gv0 + 8 * ld + j * 8) = pack_bf16x2(dv[j][2], dv[j][3]);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float a = cq[j][e], b = ck[j][e], c = cv[j][e];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+          c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if (g == 0) {
+          const int col = h * HD + j * 8 + 2 * t + e;
+          atomicAdd(dbias + col, a);
+          atomicAdd(dbias + kv_off + col, b);
+          atomicAdd(dbias + 2 * kv_off + col, c);
+        }
       }
     }
   }
@@ -347,20 +539,57 @@ static int launch_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, co
   return IBM_OK;
 }
 
+// persistent grid: as many CTAs as fit on the device, a multiple of H so that a CTA keeps one head
+template <typename K>
+static int pipe_grid(K kern, size_t smem, int64_t n_win, int H, int* grid) {
+  int per_sm = 0;
+  IBM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t g = (int64_t)sm_count() * per_sm / H * H;
+  if (g < H) g = H;
+  if (g > n_win * H) g = n_win * H;
+  *grid = (int)g;
+  return IBM_OK;
+}
+
+template <int HD>
+static int launch_fwd_pipe(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                           int64_t n_win, int T, int H, float scale, cudaStream_t s) {
+  const size_t smem = (size_t)2 * 3 * 64 * (HD + kPad) * 2;
+  auto kern = attn_fwd_pipe_kernel<HD>;
+  static int grid_cache_key = -1, grid_cached = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  (void)grid_cache_key; (void)grid_cached;
+  int grid = 0;
+  int rc = pipe_grid(kern, smem, n_win, H, &grid);
+  if (rc) return rc;
+  kern<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
+                                    static_cast<const __nv_bfloat16*>(v), ldv, static_cast<__nv_bfloat16*>(o), ldo, T, H, n_win,
+                                    scale * 1.4426950408889634f);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
 template <int HD>
 static int launch_bwd(const void* qkv, int64_t ld, int64_t kv_off, const void* d_o, int64_t ldo, void* dqkv, int64_t n_win, int T,
-                      int H, float scale, cudaStream_t s) {
-  const size_t smem = (size_t)(2 * 64 * (HD + kPad) + 2 * 64 * (64 + kPad)) * 2;     // Q, dO + K/P, V/dS (HD <= 64)
+                      int H, float scale, float* dbias, cudaStream_t s) {
+  constexpr int LD = HD + kPad, LP = 64 + kPad, LX = LD > LP ? LD : LP;
+  const size_t smem = (size_t)2 * (2 * 64 * LD + 2 * 64 * LX) * 2;          // 2 stages x (Q, dO, K/P, V/dS)
   auto kern = attn_bwd_kernel<HD>;
   static bool attr_set = false;
   if (!attr_set) {
     IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int64_t grid = n_win * H;
-  IBM_CHECK_ARG(grid < (1ll << 31), "attention_bwd: grid too large");
-  kern<<<(unsigned)grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv), ld, kv_off,
-                                              static_cast<const __nv_bfloat16*>(d_o), ldo, static_cast<__nv_bfloat16*>(dqkv), T, H, scale);
+  int grid = 0;
+  int rc = pipe_grid(kern, smem, n_win, H, &grid);
+  if (rc) return rc;
+  kern<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv), ld, kv_off, static_cast<const __nv_bfloat16*>(d_o), ldo,
+                                    static_cast<__nv_bfloat16*>(dqkv), T, H, n_win, scale, dbias);
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }
@@ -378,6 +607,12 @@ extern "C" int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int6
   IBM_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0 && aligned16(q) && aligned16(k) && aligned16(v),
                 "attention_fwd: leading dimensions must be multiples of 8 and pointers 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // short windows (the denoiser's T = 50): persistent, double-buffered kernel
+  if (T <= 64 && hd_qk == hd_v && ldo % 8 == 0 && aligned16(o)) {
+    if (hd_qk == 64) return attn::launch_fwd_pipe<64>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+    if (hd_qk == 48) return attn::launch_fwd_pipe<48>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+    if (hd_qk == 32) return attn::launch_fwd_pipe<32>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+  }
   if (hd_qk == 64 && hd_v == 64) return attn::launch_fwd<64, 64>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
   if (hd_qk == 48 && hd_v == 48) return attn::launch_fwd<48, 48>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
   if (hd_qk == 32 && hd_v == 32) return attn::launch_fwd<32, 32>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
@@ -387,7 +622,8 @@ extern "C" int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int6
 }
 
 extern "C" int ibm_attention_bwd(const void* qkv, int64_t ld_qkv, int64_t kv_off, const void* d_o, int64_t ld_o, void* dqkv,
-                                 int64_t n_win, int32_t T, int32_t H, int32_t head_dim, float scale, void* stream) {
+                                 int64_t n_win, int32_t T, int32_t H, int32_t head_dim, float scale, float* dbias_qkv,
+                                 void* stream) {
   using namespace ibm;
   IBM_CHECK_ARCH();
   IBM_CHECK_ARG(qkv && d_o && dqkv && n_win > 0 && T > 0 && H > 0, "attention_bwd: bad argument");
@@ -395,9 +631,9 @@ extern "C" int ibm_attention_bwd(const void* qkv, int64_t ld_qkv, int64_t kv_off
   IBM_CHECK_ARG(ld_qkv % 8 == 0 && ld_o % 8 == 0 && kv_off % 8 == 0 && aligned16(qkv) && aligned16(d_o) && aligned16(dqkv),
                 "attention_bwd: leading dimensions must be multiples of 8 and pointers 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (head_dim == 64) return attn::launch_bwd<64>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, s);
-  if (head_dim == 48) return attn::launch_bwd<48>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, s);
-  if (head_dim == 32) return attn::launch_bwd<32>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, s);
+  if (head_dim == 64) return attn::launch_bwd<64>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, dbias_qkv, s);
+  if (head_dim == 48) return attn::launch_bwd<48>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, dbias_qkv, s);
+  if (head_dim == 32) return attn::launch_bwd<32>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, dbias_qkv, s);
   set_error("attention_bwd: unsupported head dim %d; supported 32, 48, 64", head_dim);
   return IBM_E_UNSUPPORTED;
 }

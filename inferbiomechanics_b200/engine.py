@@ -191,12 +191,12 @@ class EncoderLayerPlan:
         ops.gemm(ds, a["o"], g(n("multihead_attention.out_proj.weight"), (d, d)), d, d, M, a_mn=True, b_mn=True,
                  accumulate=True)
         ops.gemm(ds, A.shadow_of(n("multihead_attention.out_proj.weight"), (d, d)), do, M, d, d, b_mn=True)
-        # attention backward → dqkv
-        ops.attention_bwd(a["qkv"], d, do, dqkv, n_win, T, self.H, self.hd, 1.0 / math.sqrt(self.hd))
-        # in-proj: dWqkv += dqkv^T x ; dbqkv = colsum(dqkv) ; dx = dqkv · Wqkv + ds (residual)
+        # attention backward → dqkv, with dbqkv = colsum(dqkv) accumulated by the same kernel
+        ops.attention_bwd(a["qkv"], d, do, dqkv, n_win, T, self.H, self.hd, 1.0 / math.sqrt(self.hd),
+                          dbias=g(n("multihead_attention.in_proj_bias")))
+        # in-proj: dWqkv += dqkv^T x ; dx = dqkv · Wqkv + ds (residual)
         ops.gemm(dqkv, x, g(n("multihead_attention.in_proj_weight"), (3 * d, d)), 3 * d, d, M, a_mn=True, b_mn=True,
                  accumulate=True)
-        ops.colsum(dqkv, M, 3 * d, g(n("multihead_attention.in_proj_bias")))
         ops.gemm(dqkv, A.shadow_of(n("multihead_attention.in_proj_weight"), (3 * d, d)), dx_out, M, d, 3 * d, b_mn=True,
                  aux=ds, aux_mode=1)
 

@@ -138,9 +138,10 @@ def attention_fwd(q, k, v, o, n_win, T, H, hd_qk, hd_v, scale):
          hd_qk, hd_v, scale, stream_ptr())
 
 
-def attention_bwd(qkv, kv_off, d_o, dqkv, n_win, T, H, hd, scale):
+def attention_bwd(qkv, kv_off, d_o, dqkv, n_win, T, H, hd, scale, dbias=None):
+    """dbias (fp32 [3*kv_off]): the column sums of dqkv are added to it (in_proj_bias gradient)."""
     call("ibm_attention_bwd", _p(qkv), qkv.stride(0), kv_off, _p(d_o), d_o.stride(0), _p(dqkv), n_win, T, H, hd, scale,
-         stream_ptr())
+         _p(dbias), stream_ptr())
 
 
 # ---- regression loss ------------------------------------------------------------------------------

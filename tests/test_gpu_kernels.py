@@ -250,7 +250,8 @@ def _attn_ref(q, k, v, scale):
     return torch.softmax(s, dim=-1) @ v
 
 
-@pytest.mark.parametrize("n_win,T,H,hd", [(3, 50, 8, 64), (2, 64, 2, 64), (2, 200, 3, 48), (5, 10, 4, 32), (1, 256, 1, 64), (4, 1, 2, 64)])
+@pytest.mark.parametrize("n_win,T,H,hd", [(3, 50, 8, 64), (2, 64, 2, 64), (2, 200, 3, 48), (5, 10, 4, 32), (1, 256, 1, 64), (4, 1, 2, 64),
+                                          (900, 50, 8, 64), (2000, 23, 3, 48)])
 def test_attention_forward(n_win, T, H, hd):
     from inferbiomechanics_b200 import ops
     d = H * hd
@@ -264,7 +265,8 @@ def test_attention_forward(n_win, T, H, hd):
     assert (o.double().cpu() - ref).abs().max().item() <= 2.5e-2
 
 
-@pytest.mark.parametrize("n_win,T,H,hd", [(3, 50, 8, 64), (2, 64, 2, 64), (5, 10, 4, 32), (2, 33, 3, 48)])
+@pytest.mark.parametrize("n_win,T,H,hd", [(3, 50, 8, 64), (2, 64, 2, 64), (5, 10, 4, 32), (2, 33, 3, 48), (700, 50, 8, 64),
+                                          (1500, 17, 4, 32)])
 def test_attention_backward(n_win, T, H, hd):
     from inferbiomechanics_b200 import ops
     d = H * hd
@@ -277,9 +279,17 @@ def test_attention_backward(n_win, T, H, hd):
     out.backward(do.double())
     want = x.grad.permute(1, 3, 0, 2, 4).reshape(n_win * T, 3 * d)
     dqkv = torch.full((n_win * T, 3 * d), float("nan"), dtype=torch.bfloat16, device="cuda")
-    ops.attention_bwd(qkv.cuda(), d, do.cuda(), dqkv, n_win, T, H, hd, scale)
+    dbias = torch.full((3 * d,), 0.5, device="cuda")
+    ops.attention_bwd(qkv.cuda(), d, do.cuda(), dqkv, n_win, T, H, hd, scale, dbias=dbias)
     err = (dqkv.double().cpu() - want).abs().max().item()
     assert err <= 3e-2 * want.abs().max().item() + 1e-3, err
+    # fused in_proj_bias gradient: 0.5 + column sums of the bf16 dqkv the kernel wrote (fp32 atomics: order differs)
+    cs = 0.5 + dqkv.double().sum(0).cpu()
+    torch.testing.assert_close(dbias.double().cpu(), cs, rtol=1e-4, atol=1e-4 * math.sqrt(n_win * T))
+    # without the accumulator the kernel must still run (NULL pointer path)
+    dqkv2 = torch.empty_like(dqkv)
+    ops.attention_bwd(qkv.cuda(), d, do.cuda(), dqkv2, n_win, T, H, hd, scale)
+    assert torch.equal(dqkv, dqkv2)
 
 
 def test_simple_attention_head():
