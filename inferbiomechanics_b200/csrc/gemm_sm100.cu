@@ -73,6 +73,7 @@ struct Args {
   const float* bias;
   const __nv_bfloat16* aux;
   int64_t ldaux;
+  float* colsum;           // optional fp32[N]: += column sums of the (bf16-rounded) output — a bias gradient
 };
 
 __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int nstages) {
@@ -416,6 +417,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tma_commit_group();
           if (kAux) issue_aux(xb);                // every lane is past its reads of aux tile xb
         }
+        if constexpr (!kOutF32) {
+          if (args.colsum != nullptr) {
+            // bias gradient of the layer that produced this tensor: lane l sums columns 2l, 2l+1 of the staged
+            // (rounded) 32 x 64 tile — conflict-free 4-byte reads of the swizzled rows — then two coalesced REDs
+            const int rows = (int)min((int64_t)32, args.M - m0);
+            const uint32_t sbase = smem_u32(my_out + ob * kWarpStage) + (lane & 3) * 4;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) {
+              uint32_t u;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
+              a0 += __uint_as_float(u << 16);
+              a1 += __uint_as_float(u & 0xffff0000u);
+            }
+            const int col = c0 + 2 * lane;
+            if (col < args.N) atomicAdd(args.colsum + col, a0);
+            if (col + 1 < args.N) atomicAdd(args.colsum + col + 1, a1);
+          }
+        }
         if (++ob == C::kOutBufs) ob = 0;
         ++xg;
       }
@@ -532,7 +552,7 @@ static int pick_bn(int64_t N) {
 extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
                              int64_t M, int64_t N, int64_t K, const float* bias, int32_t act, const void* aux, int64_t ldaux,
                              int32_t aux_mode, void* D, int64_t ldd, int32_t out_dtype, int32_t accumulate, int32_t split_k,
-                             int32_t taps, void* stream) {
+                             int32_t taps, float* colsum_out, void* stream) {
   using namespace ibm;
   using namespace ibm::gemm;
   IBM_CHECK_ARCH();
@@ -548,6 +568,7 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   IBM_CHECK_ARG(aux_mode == 0 || (ldaux % 8 == 0 && aligned16(aux)), "gemm: aux must be 16-byte aligned with ld %% 8 == 0");
   IBM_CHECK_ARG(!accumulate || (out_dtype == IBM_F32 && act == IBM_ACT_NONE && aux_mode == 0 && bias == nullptr),
                 "gemm: accumulate mode needs fp32 output and a plain epilogue");
+  IBM_CHECK_ARG(colsum_out == nullptr || (out_dtype == IBM_BF16 && !accumulate), "gemm: colsum_out needs a bf16 output");
   if (taps < 1) taps = 1;
   IBM_CHECK_ARG(taps == 1 || (!a_mn_major && K % taps == 0 && (K / taps) % 8 == 0), "gemm: taps needs K-major A and K/taps %% 8 == 0");
 
@@ -593,6 +614,7 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   args.bias = bias;
   args.aux = static_cast<const __nv_bfloat16*>(aux);
   args.ldaux = ldaux;
+  args.colsum = colsum_out;
   // With taps the B operand is [N, taps * kb_per_tap * 64] (each tap's K padded to whole k blocks).
   const int64_t Kb = taps == 1 ? K : (int64_t)args.kb_total * BLOCK_K;
 

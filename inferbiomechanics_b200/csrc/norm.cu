@@ -3,65 +3,102 @@
 // (the residual add is fused into the producing GEMM's epilogue, see gemm_sm100.cu aux_mode 1).
 // HBM-bound: forward reads s and writes y (2 units); backward reads dy, s and writes ds (3 units).
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace ibm {
 
-constexpr int kThreads = 256;          // 8 rows per block-iteration
-constexpr int kMaxChunks = 4;          // row length <= 4 * 32 lanes * 8 = 1024 columns
+using namespace ptx;
 
-// each lane owns chunks of 8 consecutive columns: columns (k*32 + lane)*8 … +7.  A warp handles RPW
-// rows per iteration with all their loads issued before the first reduction (memory-level parallelism:
-// one row per warp left the kernel latency-bound at ~30 % of HBM bandwidth, see profiles/r01a_*).
-template <int CH, int RPW>
+// Rows stream through shared memory: every warp owns a private ring of kStages row groups filled by bulk async
+// copies (cp.async.bulk → mbarrier complete_tx, issued by lane 0) that run kStages-1 groups ahead of the warp's
+// arithmetic.  The bytes in flight per SM no longer depend on registers per thread (the register-resident
+// predecessors of these kernels sat at 45-50 % of the HBM roofline with 2 blocks per SM; profiles/r01a, r01b).
+constexpr int kThreads = 256;          // 8 warps, each an independent pipeline
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxChunks = 4;          // row length <= 4 * 32 lanes * 8 = 1024 columns
+constexpr int kStages = 4;
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds16(const void* p) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
+  return r;
+}
+__device__ __forceinline__ void unpack8(uint4 u, float (&v)[8]) {
+  float2 a;
+  a = unpack_bf16x2(u.x); v[0] = a.x; v[1] = a.y;
+  a = unpack_bf16x2(u.y); v[2] = a.x; v[3] = a.y;
+  a = unpack_bf16x2(u.z); v[4] = a.x; v[5] = a.y;
+  a = unpack_bf16x2(u.w); v[6] = a.x; v[7] = a.y;
+}
+
+// each lane owns chunks of 8 consecutive columns: columns (k*32 + lane)*8 … +7 for k < CH.  A row group is R
+// consecutive rows (R * ld * 2 contiguous bytes: one bulk copy).
+// FULL: d == ld == CH*256 (no pad columns, every chunk complete) — the column predicates fold away, which halves
+// the instruction count of these issue-bound kernels (profiles/r01c: 355 → ~190 warp instructions per row forward).
+template <int CH, int R, bool FULL>
 __global__ void __launch_bounds__(kThreads)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ y, long long ld,
                      const float* __restrict__ gamma, const float* __restrict__ beta, long long M, int d, float eps,
                      float* __restrict__ mean, float* __restrict__ rstd) {
-  const int lane = threadIdx.x & 31;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const float inv_d = 1.f / (float)d;
-  // gamma/beta of this lane's columns live in registers for the whole kernel (re-loading them per row made the
-  // kernel LSU-bound: 32 scalar loads per row per lane, see profiles/r01a)
-  float gm[CH][8], bt[CH][8];
-#pragma unroll
-  for (int k = 0; k < CH; ++k) {
-    const int c = (k * 32 + lane) * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      gm[k][j] = (c + j < d) ? __ldg(gamma + c + j) : 0.f;
-      bt[k][j] = (c + j < d) ? __ldg(beta + c + j) : 0.f;
-    }
+  extern __shared__ __align__(128) uint8_t smem_ln[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t row_bytes = (uint32_t)ld * 2u;
+  const uint32_t group_bytes = R * row_bytes;
+  // layout: [gamma d fp32][beta d fp32][8 warps][kStages][R rows] then the mbarriers
+  float* sg = reinterpret_cast<float*>(smem_ln);
+  float* sb = sg + CH * 256;
+  uint8_t* ring = reinterpret_cast<uint8_t*>(sb + CH * 256) + (size_t)wid * kStages * group_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sb + CH * 256) + (size_t)kWarps * kStages * group_bytes) + wid * kStages;
+  for (int c = threadIdx.x; c < CH * 256; c += kThreads) {
+    sg[c] = c < d ? __ldg(gamma + c) : 0.f;
+    sb[c] = c < d ? __ldg(beta + c) : 0.f;
   }
-  for (long long m0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW; m0 < M; m0 += warps * RPW) {
-    float v[RPW][CH][8];
+  if (lane == 0) {
+    for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const long long n_groups = (M + R - 1) / R;
+  const long long gw = (long long)blockIdx.x * kWarps + wid, gstride = (long long)gridDim.x * kWarps;
+  auto issue = [&](long long grp, int st) {        // lane 0
+    const long long m0 = grp * R;
+    const uint32_t bytes = (uint32_t)((M - m0 < R ? M - m0 : R)) * row_bytes;
+    mbar_arrive_expect_tx(&bars[st], bytes);
+    bulk_load(ring + (size_t)st * group_bytes, s + m0 * ld, bytes, &bars[st]);
+  };
+  if (lane == 0) {
+    for (int i = 0; i < kStages; ++i)
+      if (gw + i * gstride < n_groups) issue(gw + i * gstride, i);
+  }
+  const float inv_d = 1.f / (float)d;
+  int it = 0;
+  for (long long grp = gw; grp < n_groups; grp += gstride, ++it) {
+    const int st = it % kStages;
+    mbar_wait(&bars[st], (uint32_t)((it / kStages) & 1));
+    const uint8_t* tile = ring + (size_t)st * group_bytes;
 #pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-      const long long m = m0 + r;
-#pragma unroll
-      for (int k = 0; k < CH; ++k) {
-        const int c = (k * 32 + lane) * 8;
-        if (m < M && c < ld) {
-          uint4 u = ld_stream16(s + m * ld + c);
-          float2 a;
-          a = unpack_bf16x2(u.x); v[r][k][0] = a.x; v[r][k][1] = a.y;
-          a = unpack_bf16x2(u.y); v[r][k][2] = a.x; v[r][k][3] = a.y;
-          a = unpack_bf16x2(u.z); v[r][k][4] = a.x; v[r][k][5] = a.y;
-          a = unpack_bf16x2(u.w); v[r][k][6] = a.x; v[r][k][7] = a.y;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[r][k][j] = 0.f;
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-      const long long m = m0 + r;
+    for (int r = 0; r < R; ++r) {
+      const long long m = grp * R + r;
+      if (m >= M) break;
+      float v[CH][8];
       float sum = 0.f;
 #pragma unroll
       for (int k = 0; k < CH; ++k) {
         const int c = (k * 32 + lane) * 8;
+        if (FULL || c < ld) {
+          unpack8(lds16(tile + r * row_bytes + c * 2), v[k]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { if (c + j >= d) v[r][k][j] = 0.f; sum += v[r][k][j]; }
+          for (int j = 0; j < 8; ++j) { if (!FULL && c + j >= d) v[k][j] = 0.f; sum += v[k][j]; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
+        }
       }
       const float mu = warp_sum(sum) * inv_d;
       float sq = 0.f;
@@ -69,71 +106,102 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
       for (int k = 0; k < CH; ++k) {
         const int c = (k * 32 + lane) * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (c + j < d) { float t = v[r][k][j] - mu; sq = fmaf(t, t, sq); }
+        for (int j = 0; j < 8; ++j) if (FULL || c + j < d) { float t = v[k][j] - mu; sq = fmaf(t, t, sq); }
       }
       const float rs = rsqrtf(warp_sum(sq) * inv_d + eps);
-      if (m < M) {
-        if (lane == 0) { if (mean) mean[m] = mu; if (rstd) rstd[m] = rs; }
+      if (lane == 0) { if (mean) mean[m] = mu; if (rstd) rstd[m] = rs; }
 #pragma unroll
-        for (int k = 0; k < CH; ++k) {
-          const int c = (k * 32 + lane) * 8;
-          if (c < ld) {
-            float o[8];
+      for (int k = 0; k < CH; ++k) {
+        const int c = (k * 32 + lane) * 8;
+        if (FULL || c < ld) {
+          const float4 g0 = *reinterpret_cast<const float4*>(sg + c), g1 = *reinterpret_cast<const float4*>(sg + c + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(sb + c), b1 = *reinterpret_cast<const float4*>(sb + c + 4);
+          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o[j] = (c + j < d) ? fmaf((v[r][k][j] - mu) * rs, gm[k][j], bt[k][j]) : 0.f;
-            st_stream16(y + m * ld + c, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                   pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
-          }
+          for (int j = 0; j < 8; ++j) o[j] = (FULL || c + j < d) ? fmaf((v[k][j] - mu) * rs, gm[j], bt[j]) : 0.f;
+          st_stream16(y + m * ld + c, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
         }
       }
     }
+    __syncwarp();                                   // every lane has read this stage
+    if (lane == 0 && grp + kStages * gstride < n_groups) issue(grp + kStages * gstride, st);
   }
 }
 
 // Backward.  ds = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma,  xhat = (s-mu)*rstd.
 // Column reductions (dgamma, dbeta, colsum(ds)) are accumulated in registers over the rows a warp
 // visits, combined across the block's 8 warps in shared memory, then one fp32 atomic per column
-// per block.
-template <int CH>
-__global__ void __launch_bounds__(kThreads)
+// per block.  A ring stage holds one row of dy and one row of s.
+template <int CH, bool FULL>
+__global__ void __launch_bounds__(kThreads, CH <= 2 ? 2 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ s, long long ld,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      long long M, int d, __nv_bfloat16* __restrict__ ds, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dcolsum) {
-  extern __shared__ float sm[];          // [3][8 warps][CH*256]
+  extern __shared__ __align__(128) uint8_t smem_ln[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const uint32_t row_bytes = (uint32_t)ld * 2u;
+  // layout: [gamma CH*256 fp32][8 warps][kStages][dy row | s row] then mbarriers; the ring is re-used for the final
+  // block combine (needs 3 * 8 * CH*256 fp32 = 24 KB * CH, the ring is 8 * kStages * 2 * row_bytes >= that for kStages >= 3
+  // only when rows are full: the launcher sizes the allocation as the max of the two)
+  float* sg = reinterpret_cast<float*>(smem_ln);
+  uint8_t* ring_all = reinterpret_cast<uint8_t*>(sg + CH * 256);
+  uint8_t* ring = ring_all + (size_t)wid * kStages * 2 * row_bytes;
+  const size_t ring_bytes = (size_t)kWarps * kStages * 2 * row_bytes;
+  const size_t comb_bytes = (size_t)3 * kWarps * CH * 256 * sizeof(float);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_all + (ring_bytes > comb_bytes ? ring_bytes : comb_bytes)) + wid * kStages;
+  for (int c = threadIdx.x; c < CH * 256; c += kThreads) sg[c] = c < d ? __ldg(gamma + c) : 0.f;
+  if (lane == 0) {
+    for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const long long gw = (long long)blockIdx.x * kWarps + wid, gstride = (long long)gridDim.x * kWarps;
+  auto issue = [&](long long m, int st) {           // lane 0
+    mbar_arrive_expect_tx(&bars[st], 2 * row_bytes);
+    uint8_t* dst = ring + (size_t)st * 2 * row_bytes;
+    bulk_load(dst, dy + m * ld, row_bytes, &bars[st]);
+    bulk_load(dst + row_bytes, s + m * ld, row_bytes, &bars[st]);
+  };
+  if (lane == 0) {
+    for (int i = 0; i < kStages; ++i)
+      if (gw + i * gstride < M) issue(gw + i * gstride, i);
+  }
   const float inv_d = 1.f / (float)d;
   float ag[CH][8], ab[CH][8], ac[CH][8];
-  float gm[CH][8];
 #pragma unroll
-  for (int k = 0; k < CH; ++k) {
-    const int c = (k * 32 + lane) * 8;
+  for (int k = 0; k < CH; ++k)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ag[k][j] = ab[k][j] = ac[k][j] = 0.f; gm[k][j] = (c + j < d) ? __ldg(gamma + c + j) : 0.f; }
-  }
-  for (long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
-    const float mu = __ldg(mean + m), rs = __ldg(rstd + m);
+    for (int j = 0; j < 8; ++j) ag[k][j] = ab[k][j] = ac[k][j] = 0.f;
+  int it = 0;
+  float mu_n = gw < M ? __ldg(mean + gw) : 0.f, rs_n = gw < M ? __ldg(rstd + gw) : 0.f;
+  for (long long m = gw; m < M; m += gstride, ++it) {
+    const int st = it % kStages;
+    const float mu = mu_n, rs = rs_n;
+    if (m + gstride < M) { mu_n = __ldg(mean + m + gstride); rs_n = __ldg(rstd + m + gstride); }   // next row's statistics
+    mbar_wait(&bars[st], (uint32_t)((it / kStages) & 1));
+    const uint8_t* tile = ring + (size_t)st * 2 * row_bytes;
     float xh[CH][8], g[CH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
       const int c = (k * 32 + lane) * 8;
-      if (c < ld) {
-        uint4 us = ld_stream16(s + m * ld + c), ud = ld_stream16(dy + m * ld + c);
-        float2 a, b;
-        a = unpack_bf16x2(us.x); b = unpack_bf16x2(ud.x); xh[k][0] = a.x; xh[k][1] = a.y; g[k][0] = b.x; g[k][1] = b.y;
-        a = unpack_bf16x2(us.y); b = unpack_bf16x2(ud.y); xh[k][2] = a.x; xh[k][3] = a.y; g[k][2] = b.x; g[k][3] = b.y;
-        a = unpack_bf16x2(us.z); b = unpack_bf16x2(ud.z); xh[k][4] = a.x; xh[k][5] = a.y; g[k][4] = b.x; g[k][5] = b.y;
-        a = unpack_bf16x2(us.w); b = unpack_bf16x2(ud.w); xh[k][6] = a.x; xh[k][7] = a.y; g[k][6] = b.x; g[k][7] = b.y;
+      if (FULL || c < ld) {
+        unpack8(lds16(tile + c * 2), g[k]);
+        unpack8(lds16(tile + row_bytes + c * 2), xh[k]);
+        const float4 g0 = *reinterpret_cast<const float4*>(sg + c), g1 = *reinterpret_cast<const float4*>(sg + c + 4);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (c + j < d) {
+          if (FULL || c + j < d) {
             xh[k][j] = (xh[k][j] - mu) * rs;
             ag[k][j] = fmaf(g[k][j], xh[k][j], ag[k][j]);     // dgamma
             ab[k][j] += g[k][j];                               // dbeta
-            g[k][j] *= gm[k][j];
+            g[k][j] *= gm[j];
             s1 += g[k][j];
             s2 = fmaf(g[k][j], xh[k][j], s2);
           } else { xh[k][j] = 0.f; g[k][j] = 0.f; }
@@ -143,16 +211,18 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         for (int j = 0; j < 8; ++j) { xh[k][j] = 0.f; g[k][j] = 0.f; }
       }
     }
+    __syncwarp();                                   // every lane has read this stage
+    if (lane == 0 && m + kStages * gstride < M) issue(m + kStages * gstride, st);
     s1 = warp_sum(s1) * inv_d;
     s2 = warp_sum(s2) * inv_d;
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
       const int c = (k * 32 + lane) * 8;
-      if (c < ld) {
+      if (FULL || c < ld) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          o[j] = (c + j < d) ? rs * (g[k][j] - s1 - xh[k][j] * s2) : 0.f;
+          o[j] = (FULL || c + j < d) ? rs * (g[k][j] - s1 - xh[k][j] * s2) : 0.f;
           ac[k][j] += o[j];
         }
         st_stream16(ds + m * ld + c, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
@@ -160,7 +230,9 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       }
     }
   }
-  // block combine: sm[q][wid][col]
+  // block combine: sm[q][wid][col] over the (now idle) ring
+  __syncthreads();
+  float* sm = reinterpret_cast<float*>(ring_all);
   constexpr int W = CH * 256;
 #pragma unroll
   for (int k = 0; k < CH; ++k) {
@@ -183,10 +255,54 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   }
 }
 
-static int rows_grid(long long M) {
-  long long need = ceil_div(M, kThreads / 32);
-  long long cap = (long long)sm_count() * 8;
-  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+// persistent grid: blocks per SM from the occupancy calculator, capped by the work
+template <typename K>
+static int ln_grid(K kern, size_t smem, long long units, int* grid) {
+  int per_sm = 0;
+  IBM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long cap = (long long)sm_count() * per_sm;
+  long long need = ceil_div(units, kWarps);
+  *grid = (int)(need < 1 ? 1 : (need < cap ? need : cap));
+  return IBM_OK;
+}
+
+template <int CH, int R, bool FULL>
+static int launch_ln_fwd(const __nv_bfloat16* sp, __nv_bfloat16* yp, int64_t ld, const float* gamma, const float* beta, int64_t M,
+                         int32_t d, float eps, float* mean, float* rstd, cudaStream_t st) {
+  auto kern = layernorm_fwd_kernel<CH, R, FULL>;
+  const size_t smem = (size_t)2 * CH * 256 * sizeof(float) + (size_t)kWarps * kStages * R * ld * 2 + kWarps * kStages * 8;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  int grid = 0;
+  int rc = ln_grid(kern, smem, ceil_div(M, R), &grid);
+  if (rc) return rc;
+  kern<<<grid, kThreads, smem, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+template <int CH, bool FULL>
+static int launch_ln_bwd(const __nv_bfloat16* dyp, const __nv_bfloat16* sp, int64_t ld, const float* gamma, const float* mean,
+                         const float* rstd, int64_t M, int32_t d, __nv_bfloat16* dsp, float* dgamma, float* dbeta, float* dcolsum,
+                         cudaStream_t st) {
+  auto kern = layernorm_bwd_kernel<CH, FULL>;
+  const size_t ring = (size_t)kWarps * kStages * 2 * ld * 2, comb = (size_t)3 * kWarps * CH * 256 * sizeof(float);
+  const size_t smem = (size_t)CH * 256 * sizeof(float) + (ring > comb ? ring : comb) + kWarps * kStages * 8;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  int grid = 0;
+  int rc = ln_grid(kern, smem, M, &grid);
+  if (rc) return rc;
+  kern<<<grid, kThreads, smem, st>>>(dyp, sp, ld, gamma, mean, rstd, M, d, dsp, dgamma, dbeta, dcolsum);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
 }
 
 }  // namespace ibm
@@ -202,15 +318,17 @@ extern "C" int ibm_layernorm_fwd(const void* s, void* y, int64_t ld, const float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto* sp = static_cast<const __nv_bfloat16*>(s);
   auto* yp = static_cast<__nv_bfloat16*>(y);
-  const int grid = rows_grid(M);
+  const bool full = d == ld && ld == (int64_t)ch * 256;
+#define IBM_LN_FWD(CHV, RV)                                                                              \
+  return full ? launch_ln_fwd<CHV, RV, true>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd, st)         \
+              : launch_ln_fwd<CHV, RV, false>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd, st)
   switch (ch) {
-    case 1: layernorm_fwd_kernel<1, 4><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
-    case 2: layernorm_fwd_kernel<2, 2><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
-    case 3: layernorm_fwd_kernel<3, 1><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
-    default: layernorm_fwd_kernel<4, 1><<<grid, kThreads, 0, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd); break;
+    case 1: IBM_LN_FWD(1, 4);
+    case 2: IBM_LN_FWD(2, 2);
+    case 3: IBM_LN_FWD(3, 1);
+    default: IBM_LN_FWD(4, 1);
   }
-  IBM_LAUNCH_CHECK();
-  return IBM_OK;
+#undef IBM_LN_FWD
 }
 
 extern "C" int ibm_layernorm_bwd(const void* dy, const void* s, int64_t ld, const float* gamma, const float* mean,
@@ -226,27 +344,15 @@ extern "C" int ibm_layernorm_bwd(const void* dy, const void* s, int64_t ld, cons
   auto* dyp = static_cast<const __nv_bfloat16*>(dy);
   auto* sp = static_cast<const __nv_bfloat16*>(s);
   auto* dsp = static_cast<__nv_bfloat16*>(ds);
-  // fewer, fatter blocks than forward: every block ends with d*3 atomics
-  long long need = ceil_div(M, kThreads / 32);
-  long long cap = (long long)sm_count() * 2;
-  const int grid = (int)(need < cap ? need : cap);
-  const size_t smem = (size_t)3 * 8 * ch * 256 * sizeof(float);
-#define IBM_LN_BWD(CHV)                                                                                          \
-  do {                                                                                                           \
-    static bool attr_set_##CHV = false;                                                                          \
-    if (!attr_set_##CHV) {                                                                                       \
-      IBM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_set_##CHV = true;                                                                                     \
-    }                                                                                                            \
-    layernorm_bwd_kernel<CHV><<<grid, kThreads, smem, st>>>(dyp, sp, ld, gamma, mean, rstd, M, d, dsp, dgamma, dbeta, dcolsum); \
-  } while (0)
+  const bool full = d == ld && ld == (int64_t)ch * 256;
+#define IBM_LN_BWD(CHV)                                                                                               \
+  return full ? launch_ln_bwd<CHV, true>(dyp, sp, ld, gamma, mean, rstd, M, d, dsp, dgamma, dbeta, dcolsum, st)       \
+              : launch_ln_bwd<CHV, false>(dyp, sp, ld, gamma, mean, rstd, M, d, dsp, dgamma, dbeta, dcolsum, st)
   switch (ch) {
-    case 1: IBM_LN_BWD(1); break;
-    case 2: IBM_LN_BWD(2); break;
-    case 3: IBM_LN_BWD(3); break;
-    default: IBM_LN_BWD(4); break;
+    case 1: IBM_LN_BWD(1);
+    case 2: IBM_LN_BWD(2);
+    case 3: IBM_LN_BWD(3);
+    default: IBM_LN_BWD(4);
   }
 #undef IBM_LN_BWD
-  IBM_LAUNCH_CHECK();
-  return IBM_OK;
 }

@@ -178,11 +178,11 @@ class EncoderLayerPlan:
                           g(n("norm2.weight")), g(n("norm2.bias")), g(n("feedforward.2.bias")))
         # FFN-2: dW2 += ds^T h ; dh = (ds · W2) ∘ relu'(h)
         ops.gemm(ds, a["h"], g(n("feedforward.2.weight"), (d, ff)), d, ff, M, a_mn=True, b_mn=True, accumulate=True)
+        #        db1 = colsum(dh) accumulated by the same epilogue
         ops.gemm(ds, A.shadow_of(n("feedforward.2.weight"), (d, ff)), dh, M, ff, d, b_mn=True, act="relu", aux=a["h"],
-                 aux_mode=2)
-        # FFN-1: dW1 += dh^T x1 ; db1 = colsum(dh) ; dx1 = dh · W1 + ds (residual)
+                 aux_mode=2, colsum=g(n("feedforward.0.bias")))
+        # FFN-1: dW1 += dh^T x1 ; dx1 = dh · W1 + ds (residual)
         ops.gemm(dh, a["x1"], g(n("feedforward.0.weight"), (ff, d)), ff, d, M, a_mn=True, b_mn=True, accumulate=True)
-        ops.colsum(dh, M, ff, g(n("feedforward.0.bias")))
         ops.gemm(dh, A.shadow_of(n("feedforward.0.weight"), (ff, d)), dx1, M, d, ff, b_mn=True, aux=ds, aux_mode=1)
         # LN1 backward (+ bias grad of out-proj)
         ops.layernorm_bwd(dx1, a["s1"], A.master_of(n("norm1.weight")), a["mean1"], a["rstd1"], M, d, ds,

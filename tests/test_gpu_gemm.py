@@ -86,6 +86,26 @@ def test_gemm_residual_and_dact(M, N, K):
         _check(out, ref, True, f"dact {act}")
 
 
+@pytest.mark.parametrize("M,N,K", [(515, 512, 256), (4000, 2048, 512), (77, 200, 128), (130, 72, 64)])
+def test_gemm_fused_colsum(M, N, K):
+    """colsum_out += column sums of the bf16 output rows < M (bias gradient of the producing layer), in the same launch."""
+    from inferbiomechanics_b200 import ops
+    A, B = _mk(M, K, K, 51), _mk(K, ops.round_up(N, 8), ops.round_up(N, 8), 52, 1.0 / math.sqrt(K))
+    h = torch.relu(_mk(M, N, ops.round_up(N, 8), 53).float()).to(torch.bfloat16)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(54))
+    out = torch.empty(M, ops.round_up(N, 8), dtype=torch.bfloat16, device="cuda")
+    cs = torch.full((N,), 2.0, device="cuda")
+    # dgrad through relu (aux epilogue) and a plain biased forward (non-aux epilogue)
+    ops.gemm(A.cuda(), B.cuda(), out, M, N, K, b_mn=True, act="relu", aux=h.cuda(), aux_mode=2, colsum=cs)
+    want = 2.0 + out[:, :N].double().sum(0).cpu()
+    torch.testing.assert_close(cs.double().cpu(), want, rtol=1e-4, atol=1e-3 * math.sqrt(M))
+    ref = (A.double() @ B[:, :N].double()) * (h[:, :N].double() > 0)
+    _check(out[:, :N], ref, True, "dact relu with colsum")
+    cs.fill_(0.0)
+    ops.gemm(A.cuda(), B.cuda(), out, M, N, K, b_mn=True, bias=bias.cuda(), colsum=cs)
+    torch.testing.assert_close(cs.double().cpu(), out[:, :N].double().sum(0).cpu(), rtol=1e-4, atol=1e-3 * math.sqrt(M))
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 128, 192), (1000, 1470, 512), (333, 512, 300), (640, 208, 512), (6, 32, 30), (70, 24, 40)])
 def test_gemm_dgrad_b_mn_major(M, N, K):
     """dX[M,N] = dY[M,K] · W[K,N]  with W stored row-major [K, N] (MN-major B operand)."""

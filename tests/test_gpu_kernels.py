@@ -215,7 +215,8 @@ def test_timestep_embedding_and_time_pos():
 
 
 # ---------------------------------------- LayerNorm ------------------------------------------------
-@pytest.mark.parametrize("M,d,ld", [(1000, 512, 512), (300, 108, 112), (77, 128, 128), (50, 1024, 1024), (129, 64, 64)])
+@pytest.mark.parametrize("M,d,ld", [(1000, 512, 512), (300, 108, 112), (77, 128, 128), (50, 1024, 1024), (129, 64, 64),
+                                    (5000, 256, 256), (3001, 768, 768), (70001, 512, 512), (9, 512, 512)])
 def test_layernorm_fwd_bwd(M, d, ld):
     from inferbiomechanics_b200 import ops
     g = torch.Generator().manual_seed(M + d)

@@ -20,6 +20,7 @@ CASES = {
     "outproj_fwd_res": (M, 512, 512, 0, 0, 1, "none", 1, 0, 0),
     "outproj_dgrad": (M, 512, 512, 0, 1, 0, "none", 0, 0, 0),
     "ffn2_dgrad": (M, 2048, 512, 0, 1, 0, "relu", 2, 0, 0),
+    "ffn2_dgrad_cs": (M, 2048, 512, 0, 1, 0, "relu", 2, 0, 0),       # + fused bias-gradient column sums
     "ffn1_dgrad_res": (M, 512, 2048, 0, 1, 0, "none", 1, 0, 0),
     "qkv_dgrad_res": (M, 512, 1536, 0, 1, 0, "none", 1, 0, 0),
     "ffn1_wgrad": (2048, 512, M, 1, 1, 0, "none", 0, 1, 1),
@@ -37,8 +38,9 @@ def run(name, iters=10):
     out = torch.zeros(m, n, dtype=torch.float32 if f32 else torch.bfloat16, device=dev)
     bv = torch.randn(n, device=dev) if bias else None
     aux = torch.randn(m, n, device=dev).to(torch.bfloat16) if aux_mode else None
+    cs = torch.zeros(n, device=dev) if name.endswith("_cs") else None
     f = lambda: ops.gemm(A, B, out, m, n, k, a_mn=bool(a_mn), b_mn=bool(b_mn), bias=bv, act=act, aux=aux, aux_mode=aux_mode,
-                         accumulate=bool(acc))
+                         accumulate=bool(acc), colsum=cs)
     for _ in range(3):
         f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
