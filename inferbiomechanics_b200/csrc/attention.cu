@@ -36,6 +36,18 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 
+// four 8x8 b16 matrices, row-major reads: lane l passes the address of row (l & 7) of matrix (l >> 3)
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // cooperative tile load: rows [r0, r0+nrows) x W columns (W % 8 == 0) into smem with row stride LDS;
 // rows >= r_valid are zero-filled.
 template <int W, int LDS>
@@ -177,9 +189,22 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int W, int LDS>
 __device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t ld, int T) {
   constexpr int CPR = W / 8;
-  for (int i = threadIdx.x; i < T * CPR; i += kThreads) {
-    const int r = i / CPR, c = (i - r * CPR) * 8;
-    cp_async16(dst + r * LDS + c, src + (int64_t)r * ld + c);
+  if constexpr ((CPR & (CPR - 1)) == 0) {
+    // a thread keeps its 16-byte column and walks down the rows: one pointer bump per copy
+    constexpr int RPP = kThreads / CPR;               // rows per pass
+    const int r0 = threadIdx.x / CPR, c = (threadIdx.x % CPR) * 8;
+    const __nv_bfloat16* sp = src + (int64_t)r0 * ld + c;
+    __nv_bfloat16* dp = dst + r0 * LDS + c;
+#pragma unroll
+    for (int p = 0; p < 64 / RPP; ++p) {
+      if (r0 + p * RPP < T) cp_async16(dp + p * RPP * LDS, sp);
+      sp += (int64_t)RPP * ld;
+    }
+  } else {
+    for (int i = threadIdx.x; i < T * CPR; i += kThreads) {
+      const int r = i / CPR, c = (i - r * CPR) * 8;
+      cp_async16(dst + r * LDS + c, src + (int64_t)r * ld + c);
+    }
   }
 }
 // a warp's 16 staged rows (row stride LDS) → global rows, 16 bytes per lane, whole 128-byte lines per 8 lanes
@@ -192,6 +217,98 @@ __device__ __forceinline__ void store_rows16(const __nv_bfloat16* stage, __nv_bf
     if (r_first + r < T)
       st_stream16(dst + (int64_t)(r_first + r) * ld + c, *reinterpret_cast<const uint4*>(stage + (r_first + r) * LDS + c));
   }
+}
+
+// two 8x8 matrices, row-major: lanes 0-15 pass the address of row (l & 7) of matrix (l >> 3)
+__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, const void* p) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+// acc[16 x 64] += A[16 x HD] · B[64 x HD]^T.  A: 16 rows starting at `Arows` (row stride LA); B: 64 rows (stride LB).
+// Key blocks j with j*8 >= T are skipped (their columns are masked afterwards).
+template <int HD, int LA, int LB>
+__device__ __forceinline__ void mma_abt(float (&acc)[8][4], const __nv_bfloat16* Arows, const __nv_bfloat16* Bs, int lane, int T) {
+  const __nv_bfloat16* ap = Arows + (lane & 15) * LA + (lane >> 4) * 8;
+  const __nv_bfloat16* bp = Bs + (lane & 7) * LB + (lane >> 3) * 8;
+#pragma unroll
+  for (int k2 = 0; k2 < HD / 32; ++k2) {
+    uint32_t a0[4], a1[4];
+    ldsm_x4(a0, ap + k2 * 32);
+    ldsm_x4(a1, ap + k2 * 32 + 16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j * 8 < T) {
+        uint32_t b[4];
+        ldsm_x4(b, bp + j * 8 * LB + k2 * 32);
+        mma16816(acc[j], a0, b[0], b[1]);
+        mma16816(acc[j], a1, b[2], b[3]);
+      }
+    }
+  }
+  if constexpr ((HD / 16) % 2 == 1) {
+    constexpr int kk = HD / 16 - 1;
+    uint32_t a0[4];
+    ldsm_x4(a0, ap + kk * 16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j * 8 < T) {
+        uint32_t b0, b1;
+        ldsm_x2(b0, b1, Bs + (j * 8 + (lane & 7)) * LB + kk * 16 + ((lane >> 3) & 1) * 8);
+        mma16816(acc[j], a0, b0, b1);
+      }
+    }
+  }
+}
+// acc[16 x HD] += A[16 x 16] · B[16 x HD] for one 16-row block of B starting at `Brows` (row-major, stride LB)
+template <int HD, int LB>
+__device__ __forceinline__ void mma_ab16(float (&acc)[HD / 8][4], const uint32_t (&a)[4], const __nv_bfloat16* Brows, int lane) {
+  const __nv_bfloat16* bp = Brows + (lane & 15) * LB + (lane >> 4) * 8;
+#pragma unroll
+  for (int j2 = 0; j2 < HD / 16; ++j2) {
+    uint32_t b[4];
+    ldsm_x4_trans(b, bp + j2 * 16);
+    mma16816(acc[2 * j2], a, b[0], b[1]);
+    mma16816(acc[2 * j2 + 1], a, b[2], b[3]);
+  }
+}
+// scale into the log2 domain, mask keys >= T, row max over the quad, exponentials and row sums.  Returns 1/rowsum.
+__device__ __forceinline__ void softmax_rows(float (&s)[8][4], int t, int T, float scale_log2, float& inv0, float& inv1) {
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j * 8 + 8 <= T) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    } else {
+      const int key = j * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = (key + (e & 1) < T) ? s[j][e] : -INFINITY;
+      if (j * 8 < T) {
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+      }
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  // scale > 0, so max(scale*s) = scale*max(s): one FFMA per element feeds ex2
+  const float o0 = mx0 * scale_log2, o1 = mx1 * scale_log2;
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j * 8 < T) {
+      s[j][0] = ex2(fmaf(s[j][0], scale_log2, -o0)); s[j][1] = ex2(fmaf(s[j][1], scale_log2, -o0));
+      s[j][2] = ex2(fmaf(s[j][2], scale_log2, -o1)); s[j][3] = ex2(fmaf(s[j][3], scale_log2, -o1));
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    } else {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  inv0 = 1.f / l0;
+  inv1 = 1.f / l1;
 }
 
 template <int HD>
@@ -232,55 +349,21 @@ attn_fwd_pipe_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __n
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < HD / 16; ++kk) {
-      uint32_t qa[4];
-      const __nv_bfloat16* qp = Qs + r0 * LD + kk * 16 + 2 * t;
-      qa[0] = *reinterpret_cast<const uint32_t*>(qp);          qa[1] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD);
-      qa[2] = *reinterpret_cast<const uint32_t*>(qp + 8);      qa[3] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD + 8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const __nv_bfloat16* kp = Ks + (j * 8 + g) * LD + kk * 16 + 2 * t;
-        mma16816(s[j], qa, *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
-      }
-    }
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int key = j * 8 + 2 * t;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s[j][e] = (key + (e & 1) < T) ? s[j][e] * scale_log2 : -INFINITY;
-      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j][0] = exp2f(s[j][0] - mx0); s[j][1] = exp2f(s[j][1] - mx0);
-      s[j][2] = exp2f(s[j][2] - mx1); s[j][3] = exp2f(s[j][3] - mx1);
-      l0 += s[j][0] + s[j][1];
-      l1 += s[j][2] + s[j][3];
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    mma_abt<HD, LD, LD>(s, Qs + warp * 16 * LD, Ks, lane, T);
+    float inv0, inv1;
+    softmax_rows(s, t, T, scale_log2, inv0, inv1);
     float oacc[HD / 8][4];
 #pragma unroll
     for (int j = 0; j < HD / 8; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-      pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-      pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-      for (int j = 0; j < HD / 8; ++j) {
-        uint32_t b0, b1;
-        ldsm_x2_trans(b0, b1, Vs + (kk * 16 + (lane & 15)) * LD + j * 8);
-        mma16816(oacc[j], pa, b0, b1);
+      if (kk * 16 < T) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        mma_ab16<HD, LD>(oacc, pa, Vs + kk * 16 * LD, lane);
       }
     }
     // O → this warp's own (now dead) Q rows → coalesced 16-byte stores.  Rows >= T stay zero.
@@ -352,52 +435,19 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_of
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
-#pragma unroll
-    for (int kk = 0; kk < HD / 16; ++kk) {
-      uint32_t qa[4], da[4];
-      const __nv_bfloat16* qp = Qs + r0 * LD + kk * 16 + 2 * t;
-      const __nv_bfloat16* dpp = dOs + r0 * LD + kk * 16 + 2 * t;
-      qa[0] = *reinterpret_cast<const uint32_t*>(qp);          qa[1] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD);
-      qa[2] = *reinterpret_cast<const uint32_t*>(qp + 8);      qa[3] = *reinterpret_cast<const uint32_t*>(qp + 8 * LD + 8);
-      da[0] = *reinterpret_cast<const uint32_t*>(dpp);         da[1] = *reinterpret_cast<const uint32_t*>(dpp + 8 * LD);
-      da[2] = *reinterpret_cast<const uint32_t*>(dpp + 8);     da[3] = *reinterpret_cast<const uint32_t*>(dpp + 8 * LD + 8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const __nv_bfloat16* kp = Ks + (j * 8 + g) * LX + kk * 16 + 2 * t;
-        const __nv_bfloat16* vp = Vs + (j * 8 + g) * LX + kk * 16 + 2 * t;
-        mma16816(s[j], qa, *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
-        mma16816(dp[j], da, *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
-      }
-    }
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int key = j * 8 + 2 * t;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s[j][e] = (key + (e & 1) < T) ? s[j][e] * scale_log2 : -INFINITY;
-      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j][0] = exp2f(s[j][0] - mx0); s[j][1] = exp2f(s[j][1] - mx0);
-      s[j][2] = exp2f(s[j][2] - mx1); s[j][3] = exp2f(s[j][3] - mx1);
-      l0 += s[j][0] + s[j][1];
-      l1 += s[j][2] + s[j][3];
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    mma_abt<HD, LD, LX>(s, Qs + warp * 16 * LD, Ks, lane, T);
+    mma_abt<HD, LD, LX>(dp, dOs + warp * 16 * LD, Vs, lane, T);
+    float inv0, inv1;
+    softmax_rows(s, t, T, scale_log2, inv0, inv1);
     // padded query rows (>= T) get P = 0 so that the K tile they later alias keeps zero pad rows
-    const float inv0 = r0 < T ? 1.f / l0 : 0.f, inv1 = r0 + 8 < T ? 1.f / l1 : 0.f;
+    if (r0 >= T) inv0 = 0.f;
+    if (r0 + 8 >= T) inv1 = 0.f;
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s[j][0] *= inv0; s[j][1] *= inv0; s[j][2] *= inv1; s[j][3] *= inv1;      // P
-      d0 += s[j][0] * dp[j][0] + s[j][1] * dp[j][1];
-      d1 += s[j][2] * dp[j][2] + s[j][3] * dp[j][3];
+      d0 = fmaf(s[j][0], dp[j][0], fmaf(s[j][1], dp[j][1], d0));
+      d1 = fmaf(s[j][2], dp[j][2], fmaf(s[j][3], dp[j][3], d1));
     }
     d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
@@ -405,8 +455,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_of
     uint32_t ppk[8][2];                                  // P (bf16 pairs), parked in registers until K/V are dead
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float e0 = scale * s[j][0] * (dp[j][0] - d0), e1 = scale * s[j][1] * (dp[j][1] - d0);
-      const float e2 = scale * s[j][2] * (dp[j][2] - d1), e3 = scale * s[j][3] * (dp[j][3] - d1);
+      const float e0 = s[j][0] * (dp[j][0] - d0) * scale, e1 = s[j][1] * (dp[j][1] - d0) * scale;
+      const float e2 = s[j][2] * (dp[j][2] - d1) * scale, e3 = s[j][3] * (dp[j][3] - d1) * scale;
       ppk[j][0] = pack_bf16x2(s[j][0], s[j][1]);
       ppk[j][1] = pack_bf16x2(s[j][2], s[j][3]);
       dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(e0, e1);
@@ -417,25 +467,17 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_of
 #pragma unroll
       for (int j = 0; j < HD / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-        for (int j = 0; j < HD / 8; ++j) {
-          uint32_t b0, b1;
-          ldsm_x2_trans(b0, b1, Ks + (kk * 16 + (lane & 15)) * LX + j * 8);
-          mma16816(dq[j], dsa[kk], b0, b1);
-        }
-      }
+      for (int kk = 0; kk < 4; ++kk)
+        if (kk * 16 < T) mma_ab16<HD, LX>(dq, dsa[kk], Ks + kk * 16 * LX, lane);
       __nv_bfloat16* g0 = dqkv + (row0 + r0) * ld + h * HD + 2 * t;
       __nv_bfloat16* g1 = g0 + 8 * ld;
 #pragma unroll
       for (int j = 0; j < HD / 8; ++j) {
-        const uint32_t lo = pack_bf16x2(dq[j][0], dq[j][1]), hi = pack_bf16x2(dq[j][2], dq[j][3]);
-        if (r0 < T) *reinterpret_cast<uint32_t*>(g0 + j * 8) = lo;
-        if (r0 + 8 < T) *reinterpret_cast<uint32_t*>(g1 + j * 8) = hi;
-        // bias gradient sums the ROUNDED values (what the in-projection weight-gradient GEMM reads); rows >= T are 0
-        const float2 a = unpack_bf16x2(lo), b = unpack_bf16x2(hi);
-        cq[j][0] += a.x + b.x;
-        cq[j][1] += a.y + b.y;
+        if (r0 < T) *reinterpret_cast<uint32_t*>(g0 + j * 8) = pack_bf16x2(dq[j][0], dq[j][1]);
+        if (r0 + 8 < T) *reinterpret_cast<uint32_t*>(g1 + j * 8) = pack_bf16x2(dq[j][2], dq[j][3]);
+        // bias gradient: fp32 column sums of the unrounded values; rows >= T are exactly 0
+        cq[j][0] += dq[j][0] + dq[j][2];
+        cq[j][1] += dq[j][1] + dq[j][3];
       }
     }
     __syncthreads();                                     // every warp is done reading K and V
@@ -459,36 +501,30 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, int64_t kv_of
       const int koff = ((lane >> 3) & 1) << 3;
 #pragma unroll
       for (int kq = 0; kq < 4; ++kq) {
-        uint32_t pa[4], sa[4];
-        ldsm_x4_trans(pa, Ps + (kq * 16 + qoff) * LP + kr + koff);
-        ldsm_x4_trans(sa, dSs + (kq * 16 + qoff) * LP + kr + koff);
-#pragma unroll
-        for (int j = 0; j < HD / 8; ++j) {
-          uint32_t b0, b1;
-          ldsm_x2_trans(b0, b1, dOs + (kq * 16 + (lane & 15)) * LD + j * 8);
-          mma16816(dv[j], pa, b0, b1);
-          ldsm_x2_trans(b0, b1, Qs + (kq * 16 + (lane & 15)) * LD + j * 8);
-          mma16816(dk[j], sa, b0, b1);
+        if (kq * 16 < T) {                               // P and dS rows of padded queries are zero
+          uint32_t pa[4], sa[4];
+          ldsm_x4_trans(pa, Ps + (kq * 16 + qoff) * LP + kr + koff);
+          ldsm_x4_trans(sa, dSs + (kq * 16 + qoff) * LP + kr + koff);
+          mma_ab16<HD, LD>(dv, pa, dOs + kq * 16 * LD, lane);
+          mma_ab16<HD, LD>(dk, sa, Qs + kq * 16 * LD, lane);
         }
       }
       __nv_bfloat16* gk0 = dqkv + (row0 + r0) * ld + kv_off + h * HD + 2 * t;
       __nv_bfloat16* gv0 = gk0 + kv_off;
+      __nv_bfloat16* gk1 = gk0 + 8 * ld;
+      __nv_bfloat16* gv1 = gv0 + 8 * ld;
 #pragma unroll
       for (int j = 0; j < HD / 8; ++j) {
-        const uint32_t klo = pack_bf16x2(dk[j][0], dk[j][1]), khi = pack_bf16x2(dk[j][2], dk[j][3]);
-        const uint32_t vlo = pack_bf16x2(dv[j][0], dv[j][1]), vhi = pack_bf16x2(dv[j][2], dv[j][3]);
         if (r0 < T) {
-          *reinterpret_cast<uint32_t*>(gk0 + j * 8) = klo;
-          *reinterpret_cast<uint32_t*>(gv0 + j * 8) = vlo;
+          *reinterpret_cast<uint32_t*>(gk0 + j * 8) = pack_bf16x2(dk[j][0], dk[j][1]);
+          *reinterpret_cast<uint32_t*>(gv0 + j * 8) = pack_bf16x2(dv[j][0], dv[j][1]);
         }
         if (r0 + 8 < T) {
-          *reinterpret_cast<uint32_t*>(gk0 + 8 * ld + j * 8) = khi;
-          *reinterpret_cast<uint32_t*>(gv0 + 8 * ld + j * 8) = vhi;
+          *reinterpret_cast<uint32_t*>(gk1 + j * 8) = pack_bf16x2(dk[j][2], dk[j][3]);
+          *reinterpret_cast<uint32_t*>(gv1 + j * 8) = pack_bf16x2(dv[j][2], dv[j][3]);
         }
-        float2 a = unpack_bf16x2(klo), b = unpack_bf16x2(khi);
-        ck[j][0] += a.x + b.x; ck[j][1] += a.y + b.y;
-        a = unpack_bf16x2(vlo); b = unpack_bf16x2(vhi);
-        cv[j][0] += a.x + b.x; cv[j][1] += a.y + b.y;
+        ck[j][0] += dk[j][0] + dk[j][2]; ck[j][1] += dk[j][1] + dk[j][3];
+        cv[j][0] += dv[j][0] + dv[j][2]; cv[j][1] += dv[j][1] + dv[j][3];
       }
     }
     __syncthreads();                                     // stage st (incl. the P / dS aliases) is free again

@@ -284,9 +284,13 @@ def test_attention_backward(n_win, T, H, hd):
     ops.attention_bwd(qkv.cuda(), d, do.cuda(), dqkv, n_win, T, H, hd, scale, dbias=dbias)
     err = (dqkv.double().cpu() - want).abs().max().item()
     assert err <= 3e-2 * want.abs().max().item() + 1e-3, err
-    # fused in_proj_bias gradient: 0.5 + column sums of the bf16 dqkv the kernel wrote (fp32 atomics: order differs)
-    cs = 0.5 + dqkv.double().sum(0).cpu()
-    torch.testing.assert_close(dbias.double().cpu(), cs, rtol=1e-4, atol=1e-4 * math.sqrt(n_win * T))
+    # fused in_proj_bias gradient: 0.5 + fp32 column sums of the kernel's unrounded dqkv (fp32 atomics: order differs);
+    # vs the fp64 reference the per-element error is the bf16-operand error above, accumulating like sqrt(rows)
+    torch.testing.assert_close(dbias.double().cpu() - 0.5, want.sum(0), rtol=2e-2,
+                               atol=2e-2 * want.abs().max().item() * math.sqrt(n_win * T))
+    # and it stays within bf16 rounding of the column sums of what was written
+    torch.testing.assert_close(dbias.double().cpu() - 0.5, dqkv.double().sum(0).cpu(), rtol=2e-2,
+                               atol=4e-3 * want.abs().max().item() * math.sqrt(n_win * T))
     # without the accumulator the kernel must still run (NULL pointer path)
     dqkv2 = torch.empty_like(dqkv)
     ops.attention_bwd(qkv.cuda(), d, do.cuda(), dqkv2, n_win, T, H, hd, scale)
