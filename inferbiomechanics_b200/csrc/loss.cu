@@ -386,17 +386,24 @@ loss_bwd_generic_kernel(const LossParams p, const GradParams gp, const float* __
 // =============================================================================================
 constexpr int kSO = 36;          // smem row stride of the output tile (floats)
 constexpr int kSL = 34;          // smem row stride of the label tile (floats)
+constexpr int kRowStages = 3;    // cp.async ring depth per warp: two 32-row chunks in flight behind the one in use
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 
 template <bool kBwd>
 __global__ void __launch_bounds__(kLossThreads)
 loss_rows_kernel(const float* __restrict__ out, const float* __restrict__ lab, __nv_bfloat16* __restrict__ grad,
                  const LossParams p, const float* __restrict__ upstream, float* __restrict__ result,
                  float* __restrict__ partials, unsigned int* __restrict__ counter) {
-  extern __shared__ __align__(16) float smem_rows[];    // per warp: out tile [32][36], lab tile [32][34]
+  extern __shared__ __align__(16) float smem_rows[];    // per warp and stage: out tile [32][36], lab tile [32][34]
   __shared__ float wsum[kLossThreads / 32][40];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  float* so = smem_rows + wid * (32 * (kSO + kSL));
-  float* sl = so + 32 * kSO;
+  float* ring = smem_rows + wid * (kRowStages * 32 * (kSO + kSL));
   const long long M = p.B * p.F;
   const unsigned F32 = (unsigned)p.F;
   const long long n_chunks = (M + 31) >> 5;
@@ -412,30 +419,42 @@ loss_rows_kernel(const float* __restrict__ out, const float* __restrict__ lab, _
     for (int c = 0; c < 30; ++c) wsc[c] = 2.f * p.w[c] * up;
   }
 
-  for (long long ck = (long long)blockIdx.x * (kLossThreads / 32) + wid; ck < n_chunks; ck += warps) {
+  // stage a 32-row chunk with cp.async: out rows are 8 x 16 B, label rows 15 x 8 B, both contiguous in HBM
+  auto stage_chunk = [&](long long ck, int st) {
+    if (ck < n_chunks) {
+      const long long m0 = ck << 5;
+      const int rows = (int)min((long long)32, M - m0);
+      float* so = ring + st * (32 * (kSO + kSL));
+      float* sl = so + 32 * kSO;
+      const float4* go = reinterpret_cast<const float4*>(out + m0 * 32);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = k * 32 + lane;                    // float4 index inside the 32-row block
+        if (i < rows * 8) cp_async_16(so + (i >> 3) * kSO + (i & 7) * 4, go + i);
+      }
+      const float2* gl = reinterpret_cast<const float2*>(lab + m0 * 30);
+#pragma unroll
+      for (int k = 0; k < 15; ++k) {
+        const int i = k * 32 + lane;                    // float2 index: row = i / 15
+        const int r = i / 15;
+        if (i < rows * 15) cp_async_8(sl + r * kSL + (i - r * 15) * 2, gl + i);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // one group per slot, empty past the end
+  };
+  const long long ck0 = (long long)blockIdx.x * (kLossThreads / 32) + wid;
+#pragma unroll
+  for (int i = 0; i < kRowStages - 1; ++i) stage_chunk(ck0 + i * warps, i);
+  int it = 0;
+  for (long long ck = ck0; ck < n_chunks; ck += warps, ++it) {
     const long long m0 = ck << 5;
     const int rows = (int)min((long long)32, M - m0);
-    // ---- stage: out rows are 8 float4 each, label rows 15 float2 each ----
-    const float4* go = reinterpret_cast<const float4*>(out + m0 * 32);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = k * 32 + lane;                      // float4 index inside the 32-row block
-      if (i < rows * 8) {
-        const float4 v = ld_stream_f4(reinterpret_cast<const float*>(go + i));
-        *reinterpret_cast<float4*>(so + (i >> 3) * kSO + (i & 7) * 4) = v;
-      }
-    }
-    const float2* gl = reinterpret_cast<const float2*>(lab + m0 * 30);
-#pragma unroll
-    for (int k = 0; k < 15; ++k) {
-      const int i = k * 32 + lane;                      // float2 index: row = i / 15
-      if (i < rows * 15) {
-        const float2 v = __ldg(gl + i);
-        const int r = i / 15;
-        *reinterpret_cast<float2*>(sl + r * kSL + (i - r * 15) * 2) = v;
-      }
-    }
+    // the slot freed by the previous iteration (every lane passed its trailing __syncwarp) takes the chunk 2 ahead
+    stage_chunk(ck + (kRowStages - 1) * warps, (it + kRowStages - 1) % kRowStages);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kRowStages - 1) : "memory");
     __syncwarp();
+    const float* so = ring + (it % kRowStages) * (32 * (kSO + kSL));
+    const float* sl = so + 32 * kSO;
     // ---- one row per lane ----
     if (lane < rows) {
       float o[32], l[30];
@@ -550,7 +569,7 @@ static bool pairable(const LossParams& p, const GradParams* gp, size_t gelem) {
   return true;
 }
 
-constexpr size_t kRowsSmem = (size_t)(kLossThreads / 32) * 32 * (kSO + kSL) * sizeof(float);   // 71 680 B
+constexpr size_t kRowsSmem = (size_t)(kLossThreads / 32) * kRowStages * 32 * (kSO + kSL) * sizeof(float);   // 215 040 B
 
 static int rows_grid(int64_t rows) {
   static bool attr_set = false;
@@ -560,7 +579,7 @@ static int rows_grid(int64_t rows) {
     attr_set = true;
   }
   int64_t need = ceil_div(rows, 32 * (kLossThreads / 32));
-  int64_t cap = (int64_t)sm_count() * 3;
+  int64_t cap = (int64_t)sm_count();            // one block (its ring is 210 KB) per SM
   int64_t maxp = (int64_t)(ibm_workspace_bytes() - 256) / (kResult * sizeof(float));
   if (cap > maxp) cap = maxp;
   return (int)(need < cap ? (need < 1 ? 1 : need) : cap);

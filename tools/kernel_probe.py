@@ -53,21 +53,40 @@ def case(name):
     if name == "colsum_ffn":
         x, out = bf(M, FF), torch.zeros(FF, device=dev)
         return (lambda: ops.colsum(x, M, FF, out)), 2 * M * FF
+    if name in ("loss_fwd", "loss_bwd"):
+        Bb = 16384                                   # 819 200 rows: out + labels = 203 MB > L2
+        rows = torch.randn(Bb * F, 32, device=dev)
+        lab = torch.randn(Bb, F, 30, device=dev) * 5
+        v = lambda x: [x[..., 0:6], x[..., 6:12], x[..., 12:18], x[..., 18:30]]
+        outs, labs = v(rows.view(Bb, F, 32)), v(lab)
+        w = [1.0] * 30
+        if name == "loss_fwd":
+            res = torch.zeros(40, device=dev)
+            return (lambda: ops.regression_loss_fwd(outs, labs, w, result=res)), Bb * F * 240
+        g16 = v(torch.zeros(Bb, F, 32, dtype=torch.bfloat16, device=dev))
+        return (lambda: ops.regression_loss_bwd(outs, labs, w, g16)), Bb * F * 300
     raise KeyError(name)
 
 
-CASES = ["attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "colsum_ffn"]
+CASES = ["attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "colsum_ffn", "loss_fwd", "loss_bwd"]
 
 
 def run(name, iters=10):
+    """`iters` launches captured in a CUDA graph and replayed: host-side ctypes marshalling (50-100 us per call, longer
+    than some of these kernels) stays out of the number."""
     f, byts = case(name)
     for _ in range(3):
         f()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            f()
+    g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(iters):
-        f()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
