@@ -57,7 +57,7 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.first = index, [], None, 0
 
     def start(self):
         try:
@@ -71,13 +71,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Start of the timed region: samples taken before this point (warm-up) are dropped."""
+        self.first = len(self.lines)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for l in self.lines[self.first:]:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -104,7 +108,7 @@ def run_reference_arm(args) -> None:
     from oracle import train as otrain
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b = 8
+    sample_b = 32
     sd = otrain.init_denoiser(C_IN, F, D_MODEL, FF, LAYERS, seed=0)
     tr = otrain.PortTrainer(sd, lr=1e-4, opt="rmsprop")
     sched = oddpm.make_schedule()
@@ -145,7 +149,7 @@ def cpu_baseline_leg() -> dict:
     from oracle import train as otrain
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b = 8
+    sample_b = 32
     tr = otrain.PortTrainer(otrain.init_denoiser(C_IN, F, D_MODEL, FF, LAYERS, seed=0), lr=1e-4)
     sched = oddpm.make_schedule()
     g = torch.Generator().manual_seed(1234)
@@ -207,12 +211,13 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------ value: HBM-resident inputs ---------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                      # nvidia-smi needs a moment to start: launch it before the warm-up
     for i in range(args.warmup):
         trainer.train_step(store, batches[i % n_batches])
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _lib.launch_count
     barrier()

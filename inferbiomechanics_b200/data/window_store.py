@@ -111,6 +111,58 @@ class WindowStore:
                         self.subject_mass[subj].contiguous(), self.F, self.stride, self.Fo == 1, out.view(B * self.Fo, -1))
         return out
 
+    # ---- pre-packed store file (SURVEY §8f-1; replaces the pickled windows of src/cli/pickle_data.py:30-81 and
+    #      src/data/PickledDataset.py:7-25 with the packer's own layout, so a training job maps the file and
+    #      uploads three arrays instead of running Dataset.__getitem__ per window) -------------------------
+    MAGIC = b"IBMSTORE1\0\0\0\0\0\0\0"          # 16 bytes
+
+    def save(self, path: str) -> None:
+        """[magic 16 B][header length u64][JSON header][64-byte-aligned sections: frames f32 [n, ld] | raw_labels f32
+        [n, 15*nb] | missing u8 [n]].  Window size / stride / output format are NOT stored: they are indexing
+        parameters chosen when the store is opened (Dataset.py:121-139)."""
+        import json
+        import struct
+        arrays = [("frames", self.frames.cpu().numpy()), ("raw_labels", self.raw_labels.cpu().contiguous().numpy()),
+                  ("missing", self.missing.cpu().numpy())]
+        header = {"frame_width": int(self.C), "num_contact_bodies": int(self.nb), "trial_len": self.trial_len.tolist(),
+                  "trial_subject": self.trial_subject.tolist(), "subject_mass": self.subject_mass.cpu().tolist(),
+                  "subject_contact_idx": self.subject_contact_idx.cpu().tolist(), "sections": {}}
+        off = 0
+        for name, a in arrays:
+            header["sections"][name] = {"offset": off, "shape": list(a.shape), "dtype": str(a.dtype)}
+            off += (a.nbytes + 63) // 64 * 64
+        blob = json.dumps(header).encode()
+        pre = 16 + 8 + len(blob)
+        pad = (-pre) % 64
+        with open(path, "wb") as f:
+            f.write(self.MAGIC)
+            f.write(struct.pack("<Q", len(blob) + pad))
+            f.write(blob + b" " * pad)
+            for _, a in arrays:
+                f.write(a.tobytes())
+                f.write(b"\0" * ((-a.nbytes) % 64))
+
+    @staticmethod
+    def load(path: str, window_size: int, stride: int = 1, output_data_format: str = "last_frame", device="cuda") -> "WindowStore":
+        import json
+        import struct
+        with open(path, "rb") as f:
+            if f.read(16) != WindowStore.MAGIC:
+                raise ValueError(f"{path} is not a window store file")
+            (hlen,) = struct.unpack("<Q", f.read(8))
+            header = json.loads(f.read(hlen).decode())
+            base = 16 + 8 + hlen
+        mm = np.memmap(path, dtype=np.uint8, mode="r")
+        def section(name):
+            sec = header["sections"][name]
+            dt = np.dtype(sec["dtype"])
+            n = int(np.prod(sec["shape"])) * dt.itemsize
+            a = mm[base + sec["offset"]: base + sec["offset"] + n].view(dt).reshape(sec["shape"])
+            return torch.from_numpy(np.array(a)).to(device)        # copy out of the read-only mapping, then upload
+        return WindowStore(section("frames"), section("raw_labels"), section("missing"), header["trial_len"],
+                           header["trial_subject"], header["subject_mass"], header["subject_contact_idx"], window_size, stride,
+                           output_data_format, header["num_contact_bodies"], header["frame_width"])
+
     # ---- builders -------------------------------------------------------------------------------------
     @staticmethod
     def from_subjects(subjects: Sequence[dict], window_size: int, stride: int, output_data_format: str, device="cuda",

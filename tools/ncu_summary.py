@@ -39,7 +39,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__cycles_active.avg", "lts__t_sector_hit_rate.pct"]
+        "smsp__cycles_active.avg", "lts__t_sector_hit_rate.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "sm__cycles_elapsed.avg.per_second", "launch__cluster_dim_x", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem"]
 
 
 def full(path):
