@@ -10,6 +10,8 @@
 // The projections around it are tcgen05 GEMMs (gemm_sm100.cu).  The score/PV products here are
 // <2 % of the layer FLOPs at these sizes and use warp-level mma.sync.m16n8k16 (bf16 in, fp32
 // accumulate) with an online softmax; one CTA = 4 warps = 64 query rows.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ibm {
@@ -657,6 +659,11 @@ extern "C" int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int6
   return IBM_E_UNSUPPORTED;
 }
 
+namespace ibm {
+int attention_bwd_tc(const void* qkv, int64_t ld, int64_t kv_off, const void* d_o, int64_t ldo, void* dqkv, int64_t n_win, int T, int H,
+                     int head_dim, float scale, float* dbias, cudaStream_t s);      // attention_tc.cu
+}
+
 extern "C" int ibm_attention_bwd(const void* qkv, int64_t ld_qkv, int64_t kv_off, const void* d_o, int64_t ld_o, void* dqkv,
                                  int64_t n_win, int32_t T, int32_t H, int32_t head_dim, float scale, float* dbias_qkv,
                                  void* stream) {
@@ -667,6 +674,18 @@ extern "C" int ibm_attention_bwd(const void* qkv, int64_t ld_qkv, int64_t kv_off
   IBM_CHECK_ARG(ld_qkv % 8 == 0 && ld_o % 8 == 0 && kv_off % 8 == 0 && aligned16(qkv) && aligned16(d_o) && aligned16(dqkv),
                 "attention_bwd: leading dimensions must be multiples of 8 and pointers 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    // tcgen05 kernel for the denoiser's heads (head_dim 64); IBM_ATTN_BWD=mma keeps the mma.sync kernel (A/B measurements)
+    static int use_tc = -1;
+    if (use_tc < 0) {
+      const char* e = getenv("IBM_ATTN_BWD");
+      use_tc = (e && e[0] == 'm') ? 0 : 1;
+    }
+    if (use_tc) {
+      const int rc = attention_bwd_tc(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, head_dim, scale, dbias_qkv, s);
+      if (rc != IBM_E_UNSUPPORTED) return rc;
+    }
+  }
   if (head_dim == 64) return attn::launch_bwd<64>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, dbias_qkv, s);
   if (head_dim == 48) return attn::launch_bwd<48>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, dbias_qkv, s);
   if (head_dim == 32) return attn::launch_bwd<32>(qkv, ld_qkv, kv_off, d_o, ld_o, dqkv, n_win, T, H, scale, dbias_qkv, s);

@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tma_host.cuh"
 
 namespace ibm {
 namespace gemm {
@@ -40,6 +41,11 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kStageA = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int kWarpStage = 32 * 128;                    // one epilogue warp's staging tile: 32 rows x 128 B = 4 KB
 constexpr int kSmemCap = 227 * 1024;                    // opt-in dynamic shared memory per CTA on sm_100
+// aux tiles (residual / saved activation): true = each epilogue thread loads its own 128-byte row piece straight from
+// global memory (L2-resident: the producer prefetches the tile a tile ahead) into registers; false = per-warp TMA ring in
+// shared memory.  Direct loads give the 64 KB of ring space back to the operand pipeline (4 -> 6 stages at 256 x 256).
+constexpr bool kAuxDirect = false;
+constexpr int kOutBufsPerWarp = 1;                      // output staging tiles per epilogue warp
 
 // CG = CTAs per MMA (cta_group): 1 = one 128 x BN tile per CTA; 2 = a CTA pair computes a 256 x BN tile, each CTA
 // holding its own 128 rows of A and HALF of the B tile (BN / 2 rows), which halves the B traffic through shared memory
@@ -50,8 +56,8 @@ struct Cfg {
   static constexpr int kStageB = (BN / CG) * BLOCK_K * 2;
   // per epilogue warp: output staging tiles (double-buffered; single when the aux ring also needs room) and a
   // 2-deep ring of aux tiles, each loaded one of the warp's chunks ahead
-  static constexpr int kOutBufs = AUX ? 1 : 2;
-  static constexpr int kAuxBufs = AUX ? 2 : 0;
+  static constexpr int kOutBufs = kOutBufsPerWarp;
+  static constexpr int kAuxBufs = (AUX && !kAuxDirect) ? 2 : 0;
   static constexpr int kEpiBytes = kEpiWarps * (kOutBufs + kAuxBufs) * kWarpStage;
   static constexpr int kFixed = 1024 /*align slack*/ + kEpiBytes + 512 /*mbarriers, tmem slot*/;
   static constexpr int kFit = (kSmemCap - kFixed) / (kStageA + kStageB);
@@ -114,10 +120,10 @@ __device__ __forceinline__ void epi_dispatch_plain(float (&v)[PT], int act) {
 // MODE 1: out = act(acc + bias) + aux;  MODE 2: out = (acc + bias) * act'(aux).  aux: bf16, 8 per 16-byte piece of
 // this thread's swizzled 128-byte row.
 template <int ACT, int MODE, int PT>
-__device__ __forceinline__ void epi_aux(float (&v)[PT], uint32_t xrow, int rsw) {
+__device__ __forceinline__ void epi_aux(float (&v)[PT], uint32_t xrow, int rsw, const uint4* ax) {
 #pragma unroll
   for (int jj = 0; jj < PT / 8; ++jj) {
-    const uint4 u = ld_shared_v4(xrow + ((jj ^ rsw) << 4));
+    const uint4 u = kAuxDirect ? ax[jj] : ld_shared_v4(xrow + ((jj ^ rsw) << 4));
     float y[8];
     float2 t;
     t = unpack_bf16x2(u.x); y[0] = t.x; y[1] = t.y;
@@ -132,21 +138,21 @@ __device__ __forceinline__ void epi_aux(float (&v)[PT], uint32_t xrow, int rsw) 
   }
 }
 template <int PT>
-__device__ __forceinline__ void epi_dispatch_aux(float (&v)[PT], uint32_t xrow, int rsw, int act, int mode) {
+__device__ __forceinline__ void epi_dispatch_aux(float (&v)[PT], uint32_t xrow, int rsw, int act, int mode, const uint4* ax) {
   if constexpr (PT % 8 == 0) {
     if (mode == 1) {
       switch (act) {
-        case IBM_ACT_NONE: epi_aux<IBM_ACT_NONE, 1, PT>(v, xrow, rsw); break;
-        case IBM_ACT_RELU: epi_aux<IBM_ACT_RELU, 1, PT>(v, xrow, rsw); break;
-        default: epi_aux<IBM_ACT_ELU, 1, PT>(v, xrow, rsw); break;
+        case IBM_ACT_NONE: epi_aux<IBM_ACT_NONE, 1, PT>(v, xrow, rsw, ax); break;
+        case IBM_ACT_RELU: epi_aux<IBM_ACT_RELU, 1, PT>(v, xrow, rsw, ax); break;
+        default: epi_aux<IBM_ACT_ELU, 1, PT>(v, xrow, rsw, ax); break;
       }
     } else {
       switch (act) {
-        case IBM_ACT_NONE: epi_aux<IBM_ACT_NONE, 2, PT>(v, xrow, rsw); break;
-        case IBM_ACT_RELU: epi_aux<IBM_ACT_RELU, 2, PT>(v, xrow, rsw); break;
-        case IBM_ACT_SIGMOID: epi_aux<IBM_ACT_SIGMOID, 2, PT>(v, xrow, rsw); break;
-        case IBM_ACT_TANH: epi_aux<IBM_ACT_TANH, 2, PT>(v, xrow, rsw); break;
-        default: epi_aux<IBM_ACT_ELU, 2, PT>(v, xrow, rsw); break;
+        case IBM_ACT_NONE: epi_aux<IBM_ACT_NONE, 2, PT>(v, xrow, rsw, ax); break;
+        case IBM_ACT_RELU: epi_aux<IBM_ACT_RELU, 2, PT>(v, xrow, rsw, ax); break;
+        case IBM_ACT_SIGMOID: epi_aux<IBM_ACT_SIGMOID, 2, PT>(v, xrow, rsw, ax); break;
+        case IBM_ACT_TANH: epi_aux<IBM_ACT_TANH, 2, PT>(v, xrow, rsw, ax); break;
+        default: epi_aux<IBM_ACT_ELU, 2, PT>(v, xrow, rsw, ax); break;
       }
     }
   }
@@ -329,7 +335,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   ((t2 / args.tiles_n) * CG + rank) * BLOCK_M + q * 32);
       pch += 2;
     };
-    if (kAux && lane == 0) {
+    if (kAux && !kAuxDirect && lane == 0) {
       issue_aux(0);
       issue_aux(1);
     }
@@ -359,7 +365,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int i = 0; i < PT / 32; ++i) tmem_ld_32x32(tmem_acc + ch * CW + i * 32, reinterpret_cast<uint32_t*>(v) + i * 32);
         const int c0 = n0 + ch * CW;               // global column of the chunk
         const int xb = xg & 1;
-        if (kAux) mbar_wait(&my_aux_bar[xb], (uint32_t)((xg >> 1) & 1));     // this chunk's aux tile has landed
+        uint4 ax[PT / 8];                          // this thread's aux row piece (kAuxDirect)
+        if (kAux && kAuxDirect) {
+          const int64_t row = (int64_t)m0 + lane;
+          const __nv_bfloat16* ap = args.aux + row * args.ldaux + c0;
+          if (row < args.M && c0 + PT <= args.N) {
+#pragma unroll
+            for (int j = 0; j < PT / 8; ++j) ax[j] = ld_stream16(ap + 8 * j);
+          } else {                                 // ragged edge: element-wise, zero beyond the matrix
+#pragma unroll
+            for (int j = 0; j < PT / 8; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int col = c0 + 8 * j + 2 * e;
+                const float lo = (row < args.M && col < args.N) ? __bfloat162float(ap[8 * j + 2 * e]) : 0.f;
+                const float hi = (row < args.M && col + 1 < args.N) ? __bfloat162float(ap[8 * j + 2 * e + 1]) : 0.f;
+                w[e] = pack_bf16x2(lo, hi);
+              }
+              ax[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+        if (kAux && !kAuxDirect) mbar_wait(&my_aux_bar[xb], (uint32_t)((xg >> 1) & 1));     // this chunk's aux tile has landed
         tmem_ld_wait();
         if (ch + 2 >= n_chunks) release_tmem();
 
@@ -378,7 +406,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if (kAux) {
-            epi_dispatch_aux<PT>(v, smem_u32(my_aux + xb * kWarpStage + lane * 128), rsw, args.act, args.aux_mode);
+            epi_dispatch_aux<PT>(v, smem_u32(my_aux + xb * kWarpStage + lane * 128), rsw, args.act, args.aux_mode, ax);
           } else {
             epi_dispatch_plain<PT>(v, args.act);
             if (args.aux_mode != 0) {
@@ -415,7 +443,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (kAccum) tma_reduce_add_2d(&tmD, my_out + ob * kWarpStage, c0, m0);
           else tma_store_2d(&tmD, my_out + ob * kWarpStage, c0, m0);
           tma_commit_group();
-          if (kAux) issue_aux(xb);                // every lane is past its reads of aux tile xb
+          if (kAux && !kAuxDirect) issue_aux(xb);   // every lane is past its reads of aux tile xb
         }
         if constexpr (!kOutF32) {
           if (args.colsum != nullptr) {
@@ -456,44 +484,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 // ------------------------------------------- host side -------------------------------------------
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// 2-D row-major tensor [outer, inner] with row pitch ld (elements); box = [box_outer, box_inner]
-static int make_map(CUtensorMap* map, const void* base, bool f32, int64_t inner, int64_t outer, int64_t ld,
-                    uint32_t box_inner, uint32_t box_outer) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return IBM_E_CUDA; }
-  const size_t es = f32 ? 4 : 2;
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
-                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld ld=%lld box=%ux%u", (int)r, (long long)inner,
-              (long long)outer, (long long)ld, box_inner, box_outer);
-    return IBM_E_CUDA;
-  }
-  return IBM_OK;
-}
 
 template <int BN, bool F32, bool ACC, bool AUX, int CG>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& x, const Args& args, int grid,
@@ -548,6 +538,29 @@ static int pick_bn(int64_t N) {
 
 }  // namespace gemm
 }  // namespace ibm
+
+// Diagnostic: how many clusters of `cluster_size` CTAs of the 256 x 256 bf16 kernel can be resident at once (the answer
+// bounds the persistent grid; GPCs whose SM count is not a multiple of the cluster size leave SMs idle).
+extern "C" int ibm_debug_gemm_max_clusters(int32_t cluster_size) {
+  using namespace ibm::gemm;
+  auto kern = gemm_kernel<256, false, false, false, 2>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256, false, 2>::kSmem);
+  if (cluster_size > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148 / cluster_size * cluster_size);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg<256, false, 2>::kSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
 
 extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
                              int64_t M, int64_t N, int64_t K, const float* bias, int32_t act, const void* aux, int64_t ldaux,
