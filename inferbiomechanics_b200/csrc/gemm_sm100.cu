@@ -51,13 +51,21 @@ constexpr int kOutBufsPerWarp = 1;                      // output staging tiles 
 // holding its own 128 rows of A and HALF of the B tile (BN / 2 rows), which halves the B traffic through shared memory
 // (at 128 x 256 with cta_group::1 the operand reads + TMA writes exceed the 128 B/clk shared-memory port: 64 % tensor
 // pipe, profiles/r01a; the pair brings it under the port limit).
-template <int BN, bool AUX, int CG>
+// NT = column tiles per work item (1 or 2).  With NT = 2 a work item is a 256 x 2*BN "supertile": one A tile feeds both
+// accumulators, so the operand bytes pulled through the L2 -> SM fabric per FLOP drop by a quarter.  All well-shaped
+// launches measured 9.6-9.9 TB/s of L2 -> SM reads at 68-69 % tensor pipe, whatever their K, stage count or epilogue
+// (profiles/r01b): that fabric, not the tensor pipe, paces a 256 x 256 tile.  The price: both TMEM accumulators belong to
+// one work item, so its epilogue no longer overlaps the next main loop — worth it when the main loop is long (K >= 1024).
+template <int BN, bool AUX, int CG, int NT = 1>
 struct Cfg {
-  static constexpr int kStageB = (BN / CG) * BLOCK_K * 2;
+  static constexpr int kStageB = NT * (BN / CG) * BLOCK_K * 2;
   // per epilogue warp: output staging tiles (double-buffered; single when the aux ring also needs room) and a
   // 2-deep ring of aux tiles, each loaded one of the warp's chunks ahead
   static constexpr int kOutBufs = kOutBufsPerWarp;
-  static constexpr int kAuxBufs = (AUX && !kAuxDirect) ? 2 : 0;
+  // supertiles keep ONE aux tile per warp: it is copied to registers as soon as it lands and the next load is issued
+  // into the same tile at once, so the load flies during the chunk's arithmetic and store (an operand stage is worth
+  // more than the second aux tile there)
+  static constexpr int kAuxBufs = (AUX && !kAuxDirect) ? (NT == 2 ? 1 : 2) : 0;
   static constexpr int kEpiBytes = kEpiWarps * (kOutBufs + kAuxBufs) * kWarpStage;
   static constexpr int kFixed = 1024 /*align slack*/ + kEpiBytes + 512 /*mbarriers, tmem slot*/;
   static constexpr int kFit = (kSmemCap - kFixed) / (kStageA + kStageB);
@@ -123,7 +131,7 @@ template <int ACT, int MODE, int PT>
 __device__ __forceinline__ void epi_aux(float (&v)[PT], uint32_t xrow, int rsw, const uint4* ax) {
 #pragma unroll
   for (int jj = 0; jj < PT / 8; ++jj) {
-    const uint4 u = kAuxDirect ? ax[jj] : ld_shared_v4(xrow + ((jj ^ rsw) << 4));
+    const uint4 u = ax != nullptr ? ax[jj] : ld_shared_v4(xrow + ((jj ^ rsw) << 4));
     float y[8];
     float2 t;
     t = unpack_bf16x2(u.x); y[0] = t.x; y[1] = t.y;
@@ -158,11 +166,13 @@ __device__ __forceinline__ void epi_dispatch_aux(float (&v)[PT], uint32_t xrow, 
   }
 }
 
-template <int BN, bool kOutF32, bool kAccum, bool kAux, int CG>
+template <int BN, bool kOutF32, bool kAccum, bool kAux, int CG, int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const Args args) {
-  using C = Cfg<BN, kAux, CG>;
+  using C = Cfg<BN, kAux, CG, NT>;
+  static_assert(NT == 1 || (NT == 2 && CG == 2 && BN == 256), "supertiles: CTA pairs, 256-wide tiles");
+  constexpr bool kAuxRegs = kAuxDirect || NT == 2;   // aux values reach the arithmetic through registers
   static_assert(CG == 1 || BN >= 128, "a CTA pair splits B into two halves of at least one 64-wide swizzle atom");
   static_assert(!kAux || (!kOutF32 && !kAccum), "TMA-staged aux tiles exist for bf16 outputs only");
   extern __shared__ uint8_t smem_raw[];
@@ -225,14 +235,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int split = w / n_tiles;
         const int tile = w - split * n_tiles;
         const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
-        const int m0 = (tm * CG + rank) * BLOCK_M, n0 = tn * BN;
-        const int nb0 = n0 + rank * BN_LOAD;                      // first B row this CTA loads
+        const int m0 = (tm * CG + rank) * BLOCK_M, n0 = tn * NT * BN;
+        const int nb0 = n0 + rank * BN_LOAD;                      // first B row this CTA loads (per column tile: + t*BN)
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
         if (prefetch_aux) {
           // the epilogue of this tile runs ~1.5 tile-times from now: pull its aux tile into L2 so the
           // epilogue's one-chunk-ahead TMA loads see L2 latency, not DRAM latency
-          for (int c = 0; c < BN && n0 + c < args.N; c += 64)
+          for (int c = 0; c < NT * BN && n0 + c < args.N; c += 64)
             for (int r = 0; r < BLOCK_M; r += 32) tma_prefetch_l2_2d(&tmX, n0 + c, m0 + r);
         }
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -253,11 +263,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i) load(sa + i * (BLOCK_K * 128), &tmA, m0 + 64 * i, k0a);
           }
-          if (!args.b_mn) {
-            load(sb, &tmB, k0b, nb0);
-          } else {
 #pragma unroll
-            for (int i = 0; i < BN_LOAD / 64; ++i) load(sb + i * (BLOCK_K * 128), &tmB, nb0 + 64 * i, k0b);
+          for (int t = 0; t < NT; ++t) {
+            uint8_t* sbt = sb + t * (C::kStageB / NT);
+            if (!args.b_mn) {
+              load(sbt, &tmB, k0b, nb0 + t * BN);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN_LOAD / 64; ++i) load(sbt + i * (BLOCK_K * 128), &tmB, nb0 + t * BN + 64 * i, k0b);
+            }
           }
           advance(stage, phase, C::kStages);
         }
@@ -278,7 +292,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int split = w / n_tiles;
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
+        // NT == 1: accumulator `as` (the other one is being drained).  NT == 2: both accumulators, one per column tile.
         mbar_wait(&tempty_bar[as], aphase ^ 1u);
+        if constexpr (NT == 2) mbar_wait(&tempty_bar[1], aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -289,19 +305,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-            if constexpr (CG == 2) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+              const uint64_t bdesc = make_smem_desc_sw128(sb + t * (C::kStageB / NT) + k * b_kstep, b_lbo, 1024);
+              if constexpr (CG == 2) umma_bf16_pair(tmem_d + t * BN, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(tmem_d + t * BN, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]);
           else umma_commit(&empty_bar[stage]);
           advance(stage, phase, C::kStages);
         }
-        // accumulator complete → epilogue (of both CTAs)
+        // accumulator(s) complete → epilogue (of both CTAs)
         if constexpr (CG == 2) umma_commit_pair(&tfull_bar[as]);
         else umma_commit(&tfull_bar[as]);
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        if constexpr (NT == 2) {
+          umma_commit_pair(&tfull_bar[1]);
+          aphase ^= 1u;                             // `as` stays 0: every work item uses both accumulators
+        } else {
+          if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -321,23 +345,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int as = 0, ob = 0;
     uint32_t aphase = 0;
     int xg = 0;                                     // chunks consumed so far by this warp (aux ring position)
-    int pw = worker, pch = half;                    // prefetch cursor: (work item, chunk) of this warp's next aux load
-    auto chunks_of = [&](int w) {
-      const int n0w = ((w % n_tiles) % args.tiles_n) * BN;
-      return ((int)min((int64_t)BN, args.N - n0w) + CW - 1) / CW;
+    int pw = worker, pts = 0, pch = half;           // prefetch cursor: (work item, column tile, chunk) of this warp's next aux load
+    auto chunks_of = [&](int w, int ts) {
+      const int n0w = (((w % n_tiles) % args.tiles_n) * NT + ts) * BN;
+      return ((int)max((int64_t)0, min((int64_t)BN, args.N - n0w)) + CW - 1) / CW;
     };
     auto issue_aux = [&](int buf) {                 // lane 0 only
-      while (pw < total_work && pch >= chunks_of(pw)) { pw += n_workers; pch = half; }
+      while (pw < total_work && pch >= chunks_of(pw, pts)) {
+        pch = half;
+        if (++pts == NT) { pts = 0; pw += n_workers; }
+      }
       if (pw >= total_work) return;
       const int t2 = pw % n_tiles;
       mbar_arrive_expect_tx(&my_aux_bar[buf], kWarpStage);
-      tma_load_2d(my_aux + buf * kWarpStage, &tmX, &my_aux_bar[buf], (t2 % args.tiles_n) * BN + pch * CW,
+      tma_load_2d(my_aux + buf * kWarpStage, &tmX, &my_aux_bar[buf], ((t2 % args.tiles_n) * NT + pts) * BN + pch * CW,
                   ((t2 / args.tiles_n) * CG + rank) * BLOCK_M + q * 32);
       pch += 2;
     };
     if (kAux && !kAuxDirect && lane == 0) {
       issue_aux(0);
-      issue_aux(1);
+      if (C::kAuxBufs == 2) issue_aux(1);
     }
     auto release_tmem = [&]() {                     // this warp has read everything it needs from accumulator `as`
       tc_fence_before();
@@ -347,11 +374,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         else mbar_arrive(&tempty_bar[as]);
       }
     };
-    for (int w = worker; w < total_work; w += n_workers) {
+    for (int w = worker; w < total_work; w += n_workers)
+    for (int tsub = 0; tsub < NT; ++tsub) {           // column tile inside the supertile: accumulator `as` == tsub when NT == 2
       const int tile = w % n_tiles;
       const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
-      const int m0 = (tm * CG + rank) * BLOCK_M + q * 32, n0 = tn * BN;       // this warp's first row
-      const int n_valid = (int)min((int64_t)BN, args.N - n0);
+      const int m0 = (tm * CG + rank) * BLOCK_M + q * 32, n0 = (tn * NT + tsub) * BN;       // this warp's first row
+      const int n_valid = (int)max((int64_t)0, min((int64_t)BN, args.N - n0));              // 0: the tile lies beyond N
       const int n_chunks = (n_valid + CW - 1) / CW;
 
       mbar_wait(&tfull_bar[as], aphase);
@@ -364,8 +392,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int i = 0; i < PT / 32; ++i) tmem_ld_32x32(tmem_acc + ch * CW + i * 32, reinterpret_cast<uint32_t*>(v) + i * 32);
         const int c0 = n0 + ch * CW;               // global column of the chunk
-        const int xb = xg & 1;
-        uint4 ax[PT / 8];                          // this thread's aux row piece (kAuxDirect)
+        const int xb = C::kAuxBufs == 2 ? (xg & 1) : 0;
+        const uint32_t xph = C::kAuxBufs == 2 ? (uint32_t)((xg >> 1) & 1) : (uint32_t)(xg & 1);
+        uint4 ax[PT / 8];                          // this thread's aux row piece when it travels through registers
         if (kAux && kAuxDirect) {
           const int64_t row = (int64_t)m0 + lane;
           const __nv_bfloat16* ap = args.aux + row * args.ldaux + c0;
@@ -387,7 +416,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
-        if (kAux && !kAuxDirect) mbar_wait(&my_aux_bar[xb], (uint32_t)((xg >> 1) & 1));     // this chunk's aux tile has landed
+        if (kAux && !kAuxDirect) {
+          mbar_wait(&my_aux_bar[xb], xph);         // this chunk's aux tile has landed
+          if constexpr (NT == 2) {
+            // single aux tile: move it to registers and put the next load in flight right away
+            const uint32_t xr = smem_u32(my_aux + lane * 128);
+#pragma unroll
+            for (int j = 0; j < PT / 8; ++j) ax[j] = ld_shared_v4(xr + ((j ^ rsw) << 4));
+            __syncwarp();
+            if (lane == 0) issue_aux(0);
+          }
+        }
         tmem_ld_wait();
         if (ch + 2 >= n_chunks) release_tmem();
 
@@ -406,7 +445,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if (kAux) {
-            epi_dispatch_aux<PT>(v, smem_u32(my_aux + xb * kWarpStage + lane * 128), rsw, args.act, args.aux_mode, ax);
+            epi_dispatch_aux<PT>(v, smem_u32(my_aux + xb * kWarpStage + lane * 128), rsw, args.act, args.aux_mode, kAuxRegs ? ax : nullptr);
           } else {
             epi_dispatch_plain<PT>(v, args.act);
             if (args.aux_mode != 0) {
@@ -443,7 +482,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (kAccum) tma_reduce_add_2d(&tmD, my_out + ob * kWarpStage, c0, m0);
           else tma_store_2d(&tmD, my_out + ob * kWarpStage, c0, m0);
           tma_commit_group();
-          if (kAux && !kAuxDirect) issue_aux(xb);   // every lane is past its reads of aux tile xb
+          if (kAux && !kAuxDirect && NT == 1) issue_aux(xb);   // every lane is past its reads of aux tile xb
         }
         if constexpr (!kOutF32) {
           if (args.colsum != nullptr) {
@@ -485,23 +524,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // ------------------------------------------- host side -------------------------------------------
 
-template <int BN, bool F32, bool ACC, bool AUX, int CG>
+template <int BN, bool F32, bool ACC, bool AUX, int CG, int NT = 1>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& x, const Args& args, int grid,
                   cudaStream_t s) {
   static bool attr_set = false;     // per instantiation
-  auto kern = gemm_kernel<BN, F32, ACC, AUX, CG>;
+  auto kern = gemm_kernel<BN, F32, ACC, AUX, CG, NT>;
   if (!attr_set) {
-    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, AUX, CG>::kSmem));
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, AUX, CG, NT>::kSmem));
     attr_set = true;
   }
   if constexpr (CG == 1) {
-    kern<<<grid, kThreads, Cfg<BN, AUX, CG>::kSmem, s>>>(a, b, d, x, args);
+    kern<<<grid, kThreads, Cfg<BN, AUX, CG, NT>::kSmem, s>>>(a, b, d, x, args);
   } else {
     // CTA pairs: clusters of 2 along x so both CTAs of a pair sit on the two SMs of one TPC
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg<BN, AUX, CG>::kSmem;
+    cfg.dynamicSmemBytes = Cfg<BN, AUX, CG, NT>::kSmem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -517,6 +556,15 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
 }
 
 // IBM_GEMM_CG=1 forces single-CTA MMAs everywhere (A/B measurements, tools/gemm_probe.py)
+// IBM_GEMM_NT=1 disables the two-tile supertiles
+static int forced_nt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IBM_GEMM_NT");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
 static int forced_cg() {
   static int v = -1;
   if (v < 0) {
@@ -543,7 +591,7 @@ static int pick_bn(int64_t N) {
 // bounds the persistent grid; GPCs whose SM count is not a multiple of the cluster size leave SMs idle).
 extern "C" int ibm_debug_gemm_max_clusters(int32_t cluster_size) {
   using namespace ibm::gemm;
-  auto kern = gemm_kernel<256, false, false, false, 2>;
+  auto kern = gemm_kernel<256, false, false, false, 2, 1>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256, false, 2>::kSmem);
   if (cluster_size > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg = {};
@@ -597,7 +645,13 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   int cg = (ceil_div(M, BLOCK_M) >= 2 && bn >= 128) ? 2 : 1;
   if (forced_cg() == 1) cg = 1;
   args.tiles_m = (int32_t)ceil_div(M, (int64_t)cg * BLOCK_M);
-  args.tiles_n = (int32_t)ceil_div(N, bn);
+  // two column tiles per work item when the main loop is long enough to pay for the un-overlapped epilogue, the plain
+  // (non-aux) epilogue is in use and the tile count is even
+  int nt = 1;
+  if (cg == 2 && bn == 256 && K >= 1024 && ceil_div(N, bn) % 2 == 0 && forced_nt() != 1 &&
+      (aux_mode == 0 || (out_dtype == IBM_BF16 && !accumulate)))
+    nt = 2;
+  args.tiles_n = (int32_t)ceil_div(N, (int64_t)nt * bn);
   const int sms = sm_count();
   int splits = 1;
   if (accumulate) {
@@ -659,6 +713,12 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
     if (aux_mode != 0) return launch<BNV, false, false, true, CGV>(ta, tb, td, tx, args, grid, s); \
     return launch<BNV, false, false, false, CGV>(ta, tb, td, tx, args, grid, s);                 \
   } while (0)
+  if (nt == 2) {
+    if (accumulate) return launch<256, true, true, false, 2, 2>(ta, tb, td, tx, args, grid, s);
+    if (f32) return launch<256, true, false, false, 2, 2>(ta, tb, td, tx, args, grid, s);
+    if (aux_mode != 0) return launch<256, false, false, true, 2, 2>(ta, tb, td, tx, args, grid, s);
+    return launch<256, false, false, false, 2, 2>(ta, tb, td, tx, args, grid, s);
+  }
   if (cg == 2) {
     if (bn == 256) IBM_GEMM_DISPATCH(256, 2);
     IBM_GEMM_DISPATCH(128, 2);

@@ -49,6 +49,9 @@ def _check(out, ref, bf16_out, what):
     (6, 24, 40, "tanh", False),
     (200, 8, 64, "none", False),
     (200, 12, 64, "none", True),
+    (5000, 512, 1472, "sigmoid", False),     # supertile (two column tiles per work item), bf16 and fp32 outputs
+    (777, 1000, 2048, "none", True),
+    (70000, 512, 1024, "relu", False),
 ])
 def test_gemm_forward(M, N, K, act, out_f32):
     from inferbiomechanics_b200 import ops
@@ -68,7 +71,8 @@ def test_gemm_forward(M, N, K, act, out_f32):
         assert torch.all(out[:, n_touched:].float() == 7.0)
 
 
-@pytest.mark.parametrize("M,N,K", [(515, 512, 256), (300, 200, 128), (40000, 512, 512), (1000, 2048, 512)])
+@pytest.mark.parametrize("M,N,K", [(515, 512, 256), (300, 200, 128), (40000, 512, 512), (1000, 2048, 512),
+                                   (3000, 512, 2048), (20000, 1024, 1536), (300, 504, 1024)])     # K >= 1024: two-tile supertiles
 def test_gemm_residual_and_dact(M, N, K):
     from inferbiomechanics_b200 import ops
     A, B = _mk(M, K, K, 4), _mk(N, K, K, 5, 1.0 / math.sqrt(K))
@@ -86,7 +90,7 @@ def test_gemm_residual_and_dact(M, N, K):
         _check(out, ref, True, f"dact {act}")
 
 
-@pytest.mark.parametrize("M,N,K", [(515, 512, 256), (4000, 2048, 512), (77, 200, 128), (130, 72, 64)])
+@pytest.mark.parametrize("M,N,K", [(515, 512, 256), (4000, 2048, 512), (77, 200, 128), (130, 72, 64), (1000, 512, 1024)])
 def test_gemm_fused_colsum(M, N, K):
     """colsum_out += column sums of the bf16 output rows < M (bias gradient of the producing layer), in the same launch."""
     from inferbiomechanics_b200 import ops
