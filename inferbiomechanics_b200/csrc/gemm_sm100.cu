@@ -648,7 +648,12 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   // two column tiles per work item when the main loop is long enough to pay for the un-overlapped epilogue, the plain
   // (non-aux) epilogue is in use and the tile count is even
   int nt = 1;
-  if (cg == 2 && bn == 256 && K >= 1024 && ceil_div(N, bn) % 2 == 0 && forced_nt() != 1 &&
+  static int64_t min_k = -1;
+  if (min_k < 0) {
+    const char* e = getenv("IBM_GEMM_NT_MINK");
+    min_k = e ? atoll(e) : 1024;
+  }
+  if (cg == 2 && bn == 256 && K >= min_k && ceil_div(N, bn) % 2 == 0 && forced_nt() != 1 &&
       (aux_mode == 0 || (out_dtype == IBM_BF16 && !accumulate)))
     nt = 2;
   args.tiles_n = (int32_t)ceil_div(N, (int64_t)nt * bn);

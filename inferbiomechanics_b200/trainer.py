@@ -206,6 +206,83 @@ def _train_step_host(self, inputs, labels) -> float:
     return float(result[0].item())
 
 
+def _train_steps_host(self, batches):
+    """Generator over host batches ``(inputs, labels)`` (dicts of pinned CPU tensors, as a DataLoader with
+    ``pin_memory=True`` yields them): one optimisation step per batch, yielding that step's loss as a python float.
+
+    Same work per step as ``train_step_host`` — H2D copy of the step's 14 tensors, packing kernels, the native step, a D2H
+    read of the loss — but pipelined the way a prefetching loader feeds a training loop: the copies of batch i+1 run on a
+    copy stream into the other half of a double-buffered staging area while step i computes, and the loss of step i is
+    read back only after step i+1 has been enqueued, so the GPU never waits for Python to launch the next step."""
+    from .keys import MODEL_INPUT_ORDER
+    dev = self.arena.device
+    copy_stream = getattr(self, "_copy_stream", None)
+    if copy_stream is None:
+        copy_stream = self._copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    it = iter(batches)
+
+    def upload(batch, slot):
+        inputs, labels = batch
+        B = inputs[MODEL_INPUT_ORDER[0]].shape[0]
+        key = ("hostpipe", B, slot)
+        if key not in self._lab:
+            self._lab[key] = ({k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in {**inputs, **labels}.items()},
+                              torch.cuda.Event(), torch.cuda.Event())
+        stage, ready, consumed = self._lab[key]
+        copy_stream.wait_event(consumed)                  # the step that last read this slot has packed it
+        with torch.cuda.stream(copy_stream):
+            for k, v in {**inputs, **labels}.items():
+                stage[k].copy_(v, non_blocking=True)
+            ready.record(copy_stream)
+        return B, stage, ready, consumed
+
+    def launch(up):
+        B, stage, ready, consumed = up
+        main.wait_event(ready)
+        F = stage[MODEL_INPUT_ORDER[0]].shape[1]
+        Fo = stage[LOSS_QUANTITIES[0]].shape[1]
+        if ("lab", B) not in self._lab:
+            self._lab[("lab", B)] = torch.empty(B, Fo, 30, dtype=torch.float32, device=dev)
+        lab = self._lab[("lab", B)]
+        ops.pack_inputs([stage[k].view(B * Fo, -1) for k in LOSS_QUANTITIES], B * Fo, Fo, out_f32=lab.view(B * Fo, 30))
+        srcs = [stage[k].view(B * F, -1) for k in MODEL_INPUT_ORDER]
+        self.arena.zero_grad()
+        self.bucketer.begin_step()
+        eng = self.eng
+        if self.is_denoiser:
+            ops.pack_inputs(srcs, B * F, F, out_bf16=eng.xc(B, True), frame_stride=eng.ld_in, win_extra=0, col0=30)
+            consumed.record(main)                         # staging slot is free once both packers have run
+            return self._finish_denoiser_step(B, lab)
+        ops.pack_inputs(srcs, B * F, F, out_bf16=eng.input_buffer(B), frame_stride=self.model.frame_width,
+                        win_extra=eng.in_ld - self.model.input_size, col0=0)
+        consumed.record(main)
+        return self._finish_ff_step(B, lab)
+
+    try:
+        nxt = upload(next(it), 0)
+    except StopIteration:
+        return
+    slot, pending = 0, None                               # pending: (result tensor, event) of the step enqueued last
+    while nxt is not None:
+        cur = nxt
+        result = launch(cur)
+        done = torch.cuda.Event()
+        done.record(main)
+        slot ^= 1
+        try:
+            nxt = upload(next(it), slot)                  # copies of the next batch overlap this step's kernels
+        except StopIteration:
+            nxt = None
+        if pending is not None:
+            pending[1].synchronize()
+            yield float(pending[0][0].item())
+        # the result ring holds 8 steps: cloning is not needed for a one-step delay
+        pending = (result, done)
+    pending[1].synchronize()
+    yield float(pending[0][0].item())
+
+
 def _finish_denoiser_step(self, B: int, lab: torch.Tensor) -> torch.Tensor:
     eng = self.eng
     xc = eng.xc(B, True)
@@ -371,6 +448,7 @@ def _aux_measurements(self, store, idx, pk, world):
 
 Trainer.make_host_batch = _make_host_batch
 Trainer.train_step_host = _train_step_host
+Trainer.train_steps_host = _train_steps_host
 Trainer._finish_denoiser_step = _finish_denoiser_step
 Trainer._finish_ff_step = _finish_ff_step
 Trainer.profile_gemms = _profile_gemms

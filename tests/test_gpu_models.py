@@ -308,3 +308,27 @@ def test_sampling_graph_equals_eager():
     assert torch.isfinite(a).all()
     torch.testing.assert_close(a, b, rtol=0, atol=0)
     torch.testing.assert_close(a, c, rtol=0, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-fed loops: the pipelined generator (prefetching copies, loss read one step late) == step-by-step calls
+# ---------------------------------------------------------------------------------------------------
+def test_train_steps_host_pipeline_matches_stepwise():
+    from inferbiomechanics_b200.models.FeedForwardRegressionBaseline import FeedForwardBaseline
+    from inferbiomechanics_b200.trainer import Trainer
+    T, s, D, B = 50, 5, 23, 48
+
+    def fresh():
+        m = FeedForwardBaseline(D, 2, T, "all_frames", "sigmoid", s, 10, hidden_dims=[64, 48])
+        m.load_state_dict(seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 5))
+        return Trainer(m.cuda(), opt_type="sgd", lr=1e-4)
+
+    a, b = fresh(), fresh()
+    batches = [a.make_host_batch(B, seed=100 + i) for i in range(5)]
+    batches = [(x["inputs"], x["labels"]) for x in batches]
+    stepwise = [a.train_step_host(i, l) for i, l in batches]
+    piped = list(b.train_steps_host(batches))
+    assert len(piped) == len(stepwise) == 5 and all(isinstance(v, float) for v in piped)
+    np.testing.assert_allclose(piped, stepwise, rtol=1e-5)          # same kernels, same order; only atomic order may differ
+    assert stepwise[-1] < stepwise[0] * 1.5                          # finite, sane
+    assert list(b.train_steps_host([])) == []
