@@ -56,7 +56,11 @@ constexpr int kOutBufsPerWarp = 1;                      // output staging tiles 
 // launches measured 9.6-9.9 TB/s of L2 -> SM reads at 68-69 % tensor pipe, whatever their K, stage count or epilogue
 // (profiles/r01b): that fabric, not the tensor pipe, paces a 256 x 256 tile.  The price: both TMEM accumulators belong to
 // one work item, so its epilogue no longer overlaps the next main loop — worth it when the main loop is long (K >= 1024).
-template <int BN, bool AUX, int CG, int NT = 1>
+// AS = A-stationary (short K): the whole 128 x K operand block of a row block (K <= 512: eight 16 KB slots) stays in shared
+// memory while the CTA pair walks ALL column tiles of that row block, so only B streams through the ring — half the
+// L2 -> SM bytes of a 256 x 256 tile, with the epilogue still overlapped (both TMEM accumulators alternate as usual).
+constexpr int kASlots = 8;
+template <int BN, bool AUX, int CG, int NT = 1, bool AS = false>
 struct Cfg {
   static constexpr int kStageB = NT * (BN / CG) * BLOCK_K * 2;
   // per epilogue warp: output staging tiles (double-buffered; single when the aux ring also needs room) and a
@@ -67,12 +71,13 @@ struct Cfg {
   // more than the second aux tile there)
   static constexpr int kAuxBufs = (AUX && !kAuxDirect) ? (NT == 2 ? 1 : 2) : 0;
   static constexpr int kEpiBytes = kEpiWarps * (kOutBufs + kAuxBufs) * kWarpStage;
-  static constexpr int kFixed = 1024 /*align slack*/ + kEpiBytes + 512 /*mbarriers, tmem slot*/;
-  static constexpr int kFit = (kSmemCap - kFixed) / (kStageA + kStageB);
+  static constexpr int kFixed = 1024 /*align slack*/ + kEpiBytes + 512 /*mbarriers, tmem slot*/ + (AS ? kASlots * kStageA : 0);
+  static constexpr int kFit = (kSmemCap - kFixed) / ((AS ? 0 : kStageA) + kStageB);
   static constexpr int kStages = kFit > 8 ? 8 : kFit;                  // operand ring: whatever is left, at most 8
   static_assert(kStages >= 2, "operand ring needs at least two stages");
   static constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmem = kFixed + kStages * (kStageA + kStageB);
+  static constexpr int kSmem = kFixed + kStages * ((AS ? 0 : kStageA) + kStageB);
+  static constexpr int kSlotsA = AS ? kASlots : kStages;               // A tiles resident in shared memory
 };
 
 struct Args {
@@ -166,19 +171,20 @@ __device__ __forceinline__ void epi_dispatch_aux(float (&v)[PT], uint32_t xrow, 
   }
 }
 
-template <int BN, bool kOutF32, bool kAccum, bool kAux, int CG, int NT>
+template <int BN, bool kOutF32, bool kAccum, bool kAux, int CG, int NT, bool kAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const Args args) {
-  using C = Cfg<BN, kAux, CG, NT>;
+  using C = Cfg<BN, kAux, CG, NT, kAS>;
   static_assert(NT == 1 || (NT == 2 && CG == 2 && BN == 256), "supertiles: CTA pairs, 256-wide tiles");
+  static_assert(!kAS || (CG == 2 && NT == 1 && !kAux && !kAccum), "A-stationary: CTA pairs, plain epilogue, no split-K");
   constexpr bool kAuxRegs = kAuxDirect || NT == 2;   // aux values reach the arithmetic through registers
   static_assert(CG == 1 || BN >= 128, "a CTA pair splits B into two halves of at least one 64-wide swizzle atom");
   static_assert(!kAux || (!kOutF32 && !kAccum), "TMA-staged aux tiles exist for bf16 outputs only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + C::kStages * kStageA;
+  uint8_t* smem_b = smem_a + C::kSlotsA * kStageA;
   uint8_t* smem_out = smem_b + C::kStages * C::kStageB;              // [8 warps][kOutBufs] x 4 KB, 1024-aligned
   uint8_t* smem_aux = smem_out + kEpiWarps * C::kOutBufs * kWarpStage;   // [8 warps][kAuxBufs] x 4 KB
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_aux + kEpiWarps * C::kAuxBufs * kWarpStage);
@@ -186,7 +192,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull_bar = empty_bar + C::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* aux_bar = tempty_bar + 2;                                // [8 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps * 2);
+  uint64_t* afull_bar = aux_bar + kEpiWarps * 2;                     // [kASlots] A-stationary: slot filled / slot free
+  uint64_t* aempty_bar = afull_bar + kASlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + kASlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -201,6 +209,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // the leader's MMA thread waits for the epilogue warps of BOTH CTAs of a pair before reusing an accumulator
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CG * kEpiWarps); }
     for (int i = 0; i < kEpiWarps * 2; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < kASlots; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -231,6 +240,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       const uint32_t tx_bytes = CG * (kStageA + C::kStageB);     // the pair's loads all complete on the leader's barrier
       const bool prefetch_aux = kAux;
+      if constexpr (kAS) {
+        // row block by row block: refill the A slots (each as soon as the previous block's last column tile has consumed
+        // it), then stream B for every column tile
+        uint32_t gen = 0;
+        for (int rb = worker; rb < args.tiles_m; rb += n_workers, ++gen) {
+          const int m0 = (rb * CG + rank) * BLOCK_M;
+          for (int kb = 0; kb < args.kb_total; ++kb) {
+            mbar_wait(&aempty_bar[kb], (gen & 1u) ^ 1u);
+            if (rank == 0) mbar_arrive_expect_tx(&afull_bar[kb], CG * kStageA);
+            uint8_t* sa = smem_a + kb * kStageA;
+            if (!args.a_mn) {
+              tma_load_2d_pair(sa, &tmA, &afull_bar[kb], kb * BLOCK_K, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d_pair(sa + i * (BLOCK_K * 128), &tmA, &afull_bar[kb], m0 + 64 * i, kb * BLOCK_K);
+            }
+          }
+          for (int ti = 0; ti < args.tiles_n; ++ti) {
+            // pairs start at different column tiles: all of them streaming the same B tile in lockstep would hammer
+            // the same L2 lines
+            const int tn = (ti + worker) % args.tiles_n;
+            const int nb0 = tn * BN + rank * BN_LOAD;
+            for (int kb = 0; kb < args.kb_total; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * C::kStageB);
+              uint8_t* sb = smem_b + stage * C::kStageB;
+              if (!args.b_mn) {
+                tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BLOCK_K, nb0);
+              } else {
+#pragma unroll
+                for (int i = 0; i < BN_LOAD / 64; ++i) tma_load_2d_pair(sb + i * (BLOCK_K * 128), &tmB, &full_bar[stage], nb0 + 64 * i, kb * BLOCK_K);
+              }
+              advance(stage, phase, C::kStages);
+            }
+          }
+        }
+      } else
       for (int w = worker; w < total_work; w += n_workers) {
         const int split = w / n_tiles;
         const int tile = w - split * n_tiles;
@@ -288,6 +334,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t b_kstep = args.b_mn ? UMMA_K * 128 : UMMA_K * 2;
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
+      if constexpr (kAS) {
+        uint32_t gen = 0;
+        for (int rb = worker; rb < args.tiles_m; rb += n_workers, ++gen) {
+          for (int tn = 0; tn < args.tiles_n; ++tn) {
+            mbar_wait(&tempty_bar[as], aphase ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+            for (int kb = 0; kb < args.kb_total; ++kb) {
+              if (tn == 0) mbar_wait(&afull_bar[kb], gen & 1u);
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem_a + kb * kStageA);
+              const uint32_t sb = smem_u32(smem_b + stage * C::kStageB);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_bf16_pair(tmem_d, make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024),
+                               make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_commit_pair(&empty_bar[stage]);
+              if (tn == args.tiles_n - 1) umma_commit_pair(&aempty_bar[kb]);   // last use of this A slot for the row block
+              advance(stage, phase, C::kStages);
+            }
+            umma_commit_pair(&tfull_bar[as]);
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+          }
+        }
+      } else
       for (int w = worker; w < total_work; w += n_workers) {
         const int split = w / n_tiles;
         const int kb0 = split * args.kb_per_split;
@@ -374,8 +446,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         else mbar_arrive(&tempty_bar[as]);
       }
     };
-    for (int w = worker; w < total_work; w += n_workers)
+    // the tile sequence of this worker: round-robin work items (and their NT column tiles), or — A-stationary — every
+    // column tile of its round-robin row blocks (w1 steps through one row block's tiles, w0 from row block to row block)
+    const int w_step0 = kAS ? n_workers * args.tiles_n : n_workers;
+    const int w_inner = kAS ? args.tiles_n : 1;
+    for (int w0 = kAS ? worker * args.tiles_n : worker; w0 < total_work; w0 += w_step0)
+    for (int wi = w0; wi < w0 + w_inner; ++wi)
     for (int tsub = 0; tsub < NT; ++tsub) {           // column tile inside the supertile: accumulator `as` == tsub when NT == 2
+      const int w = kAS ? w0 + (wi - w0 + worker) % args.tiles_n : wi;      // A-stationary: rotated column order (see producer)
       const int tile = w % n_tiles;
       const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
       const int m0 = (tm * CG + rank) * BLOCK_M + q * 32, n0 = (tn * NT + tsub) * BN;       // this warp's first row
@@ -524,23 +602,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // ------------------------------------------- host side -------------------------------------------
 
-template <int BN, bool F32, bool ACC, bool AUX, int CG, int NT = 1>
+template <int BN, bool F32, bool ACC, bool AUX, int CG, int NT = 1, bool AS = false>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& x, const Args& args, int grid,
                   cudaStream_t s) {
   static bool attr_set = false;     // per instantiation
-  auto kern = gemm_kernel<BN, F32, ACC, AUX, CG, NT>;
+  auto kern = gemm_kernel<BN, F32, ACC, AUX, CG, NT, AS>;
   if (!attr_set) {
-    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, AUX, CG, NT>::kSmem));
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, AUX, CG, NT, AS>::kSmem));
     attr_set = true;
   }
   if constexpr (CG == 1) {
-    kern<<<grid, kThreads, Cfg<BN, AUX, CG, NT>::kSmem, s>>>(a, b, d, x, args);
+    kern<<<grid, kThreads, Cfg<BN, AUX, CG, NT, AS>::kSmem, s>>>(a, b, d, x, args);
   } else {
     // CTA pairs: clusters of 2 along x so both CTAs of a pair sit on the two SMs of one TPC
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg<BN, AUX, CG, NT>::kSmem;
+    cfg.dynamicSmemBytes = Cfg<BN, AUX, CG, NT, AS>::kSmem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -591,7 +669,7 @@ static int pick_bn(int64_t N) {
 // bounds the persistent grid; GPCs whose SM count is not a multiple of the cluster size leave SMs idle).
 extern "C" int ibm_debug_gemm_max_clusters(int32_t cluster_size) {
   using namespace ibm::gemm;
-  auto kern = gemm_kernel<256, false, false, false, 2, 1>;
+  auto kern = gemm_kernel<256, false, false, false, 2, 1, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256, false, 2>::kSmem);
   if (cluster_size > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg = {};
@@ -709,8 +787,23 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
 
   const int64_t work = (int64_t)args.tiles_m * args.tiles_n * args.splits;
   const int workers = sms / cg;
-  const int grid = (int)(work < workers ? work : workers) * cg;
+  int grid = (int)(work < workers ? work : workers) * cg;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // A-stationary: short K (the row block's A fits eight 16 KB slots), several column tiles to amortise it over, enough
+  // row blocks to balance the pairs.  OFF by default: it cuts the L2 -> SM reads of the K = 512 layers by 44 % (ncu, r01c)
+  // but measured 4-7 % slower than the plain 256 x 256 tiles (290 vs 272 us QKV, 379 vs 361 us FFN-1; 60 % vs 68 % tensor
+  // pipe) — the short main loops are not fabric-bound.  IBM_GEMM_AS=1 enables it for experiments; parity-tested either way.
+  static int as_on = -1;
+  if (as_on < 0) {
+    const char* e = getenv("IBM_GEMM_AS");
+    as_on = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (as_on && cg == 2 && bn == 256 && nt == 1 && aux_mode == 0 && !accumulate && taps == 1 && args.kb_total <= kASlots &&
+      args.tiles_n >= 2 && args.tiles_m >= 2 * workers) {
+    grid = workers * cg;
+    if (f32) return launch<256, true, false, false, 2, 1, true>(ta, tb, td, tx, args, grid, s);
+    return launch<256, false, false, false, 2, 1, true>(ta, tb, td, tx, args, grid, s);
+  }
 #define IBM_GEMM_DISPATCH(BNV, CGV)                                                        \
   do {                                                                                     \
     if (accumulate) return launch<BNV, true, true, false, CGV>(ta, tb, td, tx, args, grid, s);   \

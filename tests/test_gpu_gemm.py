@@ -52,6 +52,10 @@ def _check(out, ref, bf16_out, what):
     (5000, 512, 1472, "sigmoid", False),     # supertile (two column tiles per work item), bf16 and fp32 outputs
     (777, 1000, 2048, "none", True),
     (70000, 512, 1024, "relu", False),
+    (40000, 1536, 512, "none", False),       # >= 148 row blocks, K <= 512 (also the A-stationary schedule when IBM_GEMM_AS=1)
+    (50000, 600, 256, "relu", False),        # ... ragged N, K = 4 k-blocks
+    (38011, 512, 328, "silu", False),        # ... ragged M and K
+    (40000, 1000, 512, "tanh", True),        # ... fp32 output
 ])
 def test_gemm_forward(M, N, K, act, out_f32):
     from inferbiomechanics_b200 import ops
@@ -110,7 +114,8 @@ def test_gemm_fused_colsum(M, N, K):
     torch.testing.assert_close(cs.double().cpu(), out[:, :N].double().sum(0).cpu(), rtol=1e-4, atol=1e-3 * math.sqrt(M))
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 128, 192), (1000, 1470, 512), (333, 512, 300), (640, 208, 512), (6, 32, 30), (70, 24, 40)])
+@pytest.mark.parametrize("M,N,K", [(256, 128, 192), (1000, 1470, 512), (333, 512, 300), (640, 208, 512), (6, 32, 30), (70, 24, 40),
+                                   (45000, 512, 512)])       # out-proj dgrad shape, >= 148 row blocks
 def test_gemm_dgrad_b_mn_major(M, N, K):
     """dX[M,N] = dY[M,K] · W[K,N]  with W stored row-major [K, N] (MN-major B operand)."""
     from inferbiomechanics_b200 import ops
@@ -134,6 +139,31 @@ def test_gemm_wgrad_mn_mn_accumulate(Mtok, Nout, Kin, split):
     ops.gemm(dY.cuda(), X.cuda(), dW, Nout, Kin, Mtok, a_mn=True, b_mn=True, accumulate=True, split_k=split)
     ref = init.double() + dY[:, :Nout].double().t() @ X[:, :Kin].double()
     _check(dW, ref, False, f"wgrad {Mtok} {Nout}x{Kin}")
+
+
+def test_gemm_a_stationary_mode_parity():
+    """The experimental A-stationary schedule (IBM_GEMM_AS=1, read once per process) gives the same results: run the QKV
+    shape in a subprocess with the switch on and compare with this process (switch off)."""
+    import subprocess
+    import sys
+    code = (
+        "import torch, math, sys; sys.path.insert(0, '.');"
+        "from inferbiomechanics_b200 import ops;"
+        "g = torch.Generator().manual_seed(3);"
+        "A = torch.randn(40000, 512, generator=g).to(torch.bfloat16).cuda();"
+        "B = (torch.randn(1536, 512, generator=g) / math.sqrt(512)).to(torch.bfloat16).cuda();"
+        "out = torch.empty(40000, 1536, dtype=torch.bfloat16, device='cuda');"
+        "ops.gemm(A, B, out, 40000, 1536, 512, act='relu');"
+        "torch.cuda.synchronize(); print(out.float().sum().item(), out.float().abs().max().item(), out[12345, 777].item())")
+    import os
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, IBM_GEMM_AS=flag)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+        assert r.returncode == 0, r.stderr[-800:]
+        outs.append([float(x) for x in r.stdout.split()])
+    assert outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2]          # same tile arithmetic: identical elements
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * abs(outs[0][0]) + 1e-3
 
 
 def test_gemm_taps_implicit_conv():
