@@ -29,13 +29,30 @@ namespace attn_tc {
 
 using namespace ptx;
 
-constexpr int kThreads = 512;             // 16 warps: TMEM lane quadrant (warp & 3) x column quarter (warp >> 2)
+constexpr int kComputeThreads = 512;      // 16 warps: TMEM lane quadrant (warp & 3) x column quarter (warp >> 2)
+// + five control warps, one issuing thread each.  A tcgen05.mma costs its issuing thread ~65 clocks and a TMA operation
+// ~130 (clock64 trace of one iteration: 24 MMAs 1 620 clocks, 6 loads 780), far more than these small MMAs keep the tensor
+// pipe busy (32-64 clocks), so one control thread paced the whole kernel at ~7 000 clocks per pair; the issue work is
+// spread over: loader | dV + S | dK + dP | dQ + storer (20 warps in all: a 21st would drop the register budget of the
+// compute warps from 96 to 80).
+constexpr int kControlWarps = 4;
+constexpr int kThreads = kComputeThreads + 32 * kControlWarps;
 constexpr int HD = 64;
 constexpr int kTile = 128 * 128;          // one [128 rows][128 B] tile = 16 KB
-// shared memory: 2 stages x {Q, K, V, dO} (also the staging of dQ, dK, dV) + P, dS (two 64-key chunks each) + row exchange
-constexpr int kSmem = 1024 + 2 * 4 * kTile + 2 * 2 * kTile + 3 * 128 * 4 * 4 + 256;
+// P and dS are block-diagonal [128 queries][2 x 64 keys]: chunk 0 = [P_a ; 0], chunk 1 = [0 ; P_b].  The two chunks are
+// laid 8 KB apart instead of 16, so the zero half of chunk 0 (rows 64-127) IS the zero half of chunk 1 (rows 0-63):
+// [P_a 8 KB | zeros 8 KB | P_b 8 KB] = 24 KB per matrix, and the descriptors simply use an 8 KB atom / chunk stride.
+constexpr int kPD = 3 * 8192;
+constexpr int kChunk = 8192;
+// shared memory: 2 stages x {Q, K, dO} + one V tile + P, dS + result staging dQ | dK | dV + row exchange
+constexpr int kOnes = 4096;                // a [16][128] tile of bf16 ones: B operand of the bias-gradient products
+constexpr int kSmem = 1024 + 2 * 3 * kTile + kTile + 2 * kPD + 3 * kTile + kOnes + 3 * 128 * 4 * 4 + 256;
 // TMEM columns: S 0..127, dP 128..255, dQ 256..319, dV 320..383, dK 384..447
 constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256, kColDV = 320, kColDK = 384;
+// bias gradient: column sums of the staged dQ | dK (lanes 0-63 | 64-127) at 448 and of dK | dV at 464, accumulated over
+// every pair of the CTA by M = 128, N = 16 products  [dQ | dK]^T · ones,  [dK | dV]^T · ones  (two adjacent staging tiles
+// form one MN-major operand) — no work for the compute warps, no registers
+constexpr uint32_t kColBqk = 448, kColBkv = 464;
 
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* r) { tmem_ld_32x16(taddr, reinterpret_cast<uint32_t*>(r)); }
 __device__ __forceinline__ float ex2(float x) {
@@ -67,37 +84,61 @@ __device__ __forceinline__ void add_bf16x8(float (&a)[8], uint4 u) {
   a[6] += __uint_as_float(u.w << 16); a[7] += __uint_as_float(u.w & 0xffff0000u);
 }
 
+// Software pipeline over the window pairs of one head (one CTA per SM: the TMEM map below needs 448 of its 512 columns).
+// The tensor pipe and the 16 compute warps work on different pairs at the same time:
+//     tensor pipe :  ... | products(i-1) = dV,dK,dQ | scores(i) = S,dP | products(i) | scores(i+1) | ...
+//     compute     :  ... | softmax(i) in registers  | fetch results(i-1), write P/dS(i) | stage + store results(i-1) | ...
+// which works because the two groups of MMAs use disjoint TMEM columns, P/dS of pair i stay in registers until the
+// products of pair i-1 have released the shared-memory P/dS tiles, and results are copied TMEM -> registers before the next
+// products overwrite them.  Five control warps (one thread each) issue the TMA loads, the MMAs and the TMA stores.
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmDQKV, int T, int H, int64_t n_win, int64_t kv_off, float scale,
                    float* __restrict__ dbias) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // stage st: Q | K | V | dO at smem + st * 4 * kTile
-  uint8_t* Ps = smem + 8 * kTile;                     // [2 key chunks][128 rows][128 B]
-  uint8_t* dSs = Ps + 2 * kTile;
-  float* xch = reinterpret_cast<float*>(dSs + 2 * kTile);               // [3][128 rows][4 quarters]: row max, sum, sum(e*dP)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(xch + 3 * 128 * 4);  // [2]
-  uint64_t* s_bar = full_bar + 2;                     // S, dP complete
+  // stage st: Q | K | dO at smem + st * 3 * kTile
+  uint8_t* Vs = smem + 6 * kTile;                     // single: V is dead as soon as the scores of its pair are complete
+  uint8_t* Ps = Vs + kTile;                           // [P_a | shared zero block | P_b], see kPD
+  uint8_t* dSs = Ps + kPD;
+  uint8_t* Gq = dSs + kPD;                            // result staging tiles
+  uint8_t* Gk = Gq + kTile;
+  uint8_t* Gv = Gk + kTile;
+  uint8_t* Ones = Gv + kTile;                         // kOnes bytes of bf16 1.0
+  float* xch = reinterpret_cast<float*>(Ones + kOnes);                  // [3][128 rows][4 quarters]: row max, sum, sum(e*dP)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(xch + 3 * 128 * 4);  // [2] Q, K, dO of a stage landed
+  uint64_t* v_bar = full_bar + 2;                     // V landed
+  uint64_t* s_bar = v_bar + 1;                        // S, dP complete
   uint64_t* o_bar = s_bar + 1;                        // dQ, dK, dV complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 1);
+  uint64_t* pd_bar = o_bar + 1;                       // P/dS of the pair are in shared memory, its predecessor's results in registers
+  uint64_t* stg_bar = pd_bar + 1;                     // results staged
+  uint64_t* sf_bar = stg_bar + 1;                     // staging tiles free again (TMA stores and bias products have read them)
+  uint64_t* c_bar = sf_bar + 1;                       // all bias-gradient products complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x % H;
   const int64_t cta = blockIdx.x / H, ctas = gridDim.x / H;
   const int64_t n_pairs = (n_win + 1) >> 1;
+  const int n_it = cta < n_pairs ? (int)((n_pairs - cta + ctas - 1) / ctas) : 0;      // pairs of this CTA
 
-  // zero everything once: pad rows (>= T of each 64-row half) of the operand stages stay zero for the whole kernel, and
+  // zero everything once: pad rows (>= T of each 64-row half) of the operand tiles stay zero for the whole kernel, and
   // so do the cross-window blocks of P and dS (only the diagonal blocks are ever written)
-  for (int i = tid; i < 12 * kTile / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (10 * kTile + 2 * kPD) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < kOnes / 16; i += kThreads) reinterpret_cast<uint4*>(Ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   if (tid == 0) {
     prefetch_tmap(&tmQKV);
     prefetch_tmap(&tmDO);
     prefetch_tmap(&tmDQKV);
     mbar_init(&full_bar[0], 1);
     mbar_init(&full_bar[1], 1);
-    mbar_init(s_bar, 1);
-    mbar_init(o_bar, 1);
+    mbar_init(v_bar, 1);
+    mbar_init(s_bar, 2);                              // S and dP are committed by two different warps
+    mbar_init(o_bar, 3);                              // dV, dK, dQ by three
+    mbar_init(pd_bar, kComputeThreads / 32);
+    mbar_init(stg_bar, kComputeThreads / 32);
+    mbar_init(sf_bar, dbias != nullptr ? 3 : 1);      // storer + the two warps that issue the bias products
+    mbar_init(c_bar, 2);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -107,238 +148,305 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int q = warp & 3, cq4 = warp >> 2;            // TMEM lane quadrant, column quarter (16 keys / 16 head columns)
-  const int r = q * 32 + lane;                        // this thread's row == TMEM lane (shared by 4 threads)
-  const int ri = r & 63;                              // row inside its window
-  const int own = r >> 6;                             // which window of the pair / which 64-key chunk is "ours"
-  const int rsw = r & 7;
-  const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-  const float scale_log2 = scale * 1.4426950408889634f;
-  const uint32_t tx_bytes = 8u * (uint32_t)T * 128u;
-  const uint32_t xrow = smem_u32(xch) + r * 16;       // this row's 4 exchange slots (16 B), three planes 2 KB apart
-  // bias-gradient partial sums: 16-byte piece (tid & 7) of rows (tid >> 3) and 64 + (tid >> 3) of the staged results
-  float cq[8], ck[8], cv[8];
+  if (warp >= kComputeThreads / 32) {
+    // ===================================== control warps =====================================
+    const int role = warp - kComputeThreads / 32;     // 0 loader, 1 dV + S, 2 dK + dP, 3 dQ + storer
+    if (lane == 0 && n_it > 0) {
+      const uint32_t tx_qkd = 6u * (uint32_t)T * 128u, tx_v = 2u * (uint32_t)T * 128u;
+      auto window_row = [&](int i, int it) {
+        int64_t w = 2 * (cta + (int64_t)i * ctas) + it;
+        if (w >= n_win) w = n_win - 1;                // odd tail: a valid window again, its results are not stored
+        return (int32_t)(w * T);
+      };
+      // descriptors are built once; a k step only advances the 14-bit start-address field
+      const uint64_t dK_Q0 = make_smem_desc_sw128(smem_u32(smem), 0, 1024);          // stage 0 Q as K-major operand
+      const uint64_t dM_Q0 = make_smem_desc_sw128(smem_u32(smem), kTile, 1024);      // stage 0 Q as MN-major operand
+      constexpr uint64_t kTileStep = kTile >> 4, kStageStep = (3 * kTile) >> 4, kChunkStep = kChunk >> 4;
+      const uint64_t dK_V = make_smem_desc_sw128(smem_u32(Vs), 0, 1024);
+      const uint64_t dM_P = make_smem_desc_sw128(smem_u32(Ps), kChunk, 1024);        // the two 64-key atoms are 8 KB apart
+      const uint64_t dM_dS = make_smem_desc_sw128(smem_u32(dSs), kChunk, 1024);
+      const uint64_t dK_dS = make_smem_desc_sw128(smem_u32(dSs), 0, 1024);
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1), idesc_q = make_idesc_bf16(128, 64, 0, 1);
+      // bias gradient of pair i: D[col][*] += sum_rows G[row][col], A = two staged tiles as one MN-major operand (M = 2 x 64
+      // columns, K = 128 rows), B = ones (K-major, N = 16); accumulates over all pairs; signals "staging free" when done
+      const uint64_t dM_G = make_smem_desc_sw128(smem_u32(Gq), kTile, 1024);
+      const uint64_t dK_1 = make_smem_desc_sw128(smem_u32(Ones), 0, 1024);
+      const uint32_t idesc_b = make_idesc_bf16(128, 16, 1, 0);
+      auto bias_products = [&](int i, uint32_t col, uint64_t a_desc) {
+        mbar_wait(stg_bar, (uint32_t)(i & 1));
+        tc_fence_after();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) cq[j] = ck[j] = cv[j] = 0.f;
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + col, a_desc + 128 * k, dK_1 + (k >> 2) * 128 + (k & 3) * 2, idesc_b, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(sf_bar);
+      };
+      auto wait_inputs = [&](int i) {                 // Q, K, dO and V of pair i have landed
+        mbar_wait(&full_bar[i & 1], (uint32_t)((i >> 1) & 1));
+        mbar_wait(v_bar, (uint32_t)(i & 1));
+        tc_fence_after();
+      };
 
-  auto issue_loads = [&](int64_t pair, int st) {      // thread 0
-    uint8_t* base = smem + st * 4 * kTile;
-    mbar_arrive_expect_tx(&full_bar[st], tx_bytes);
+      if (role == 0) {
+        // ---- loader ----
+        auto load_qkd = [&](int i) {                  // Q, K, dO of pair i into stage i & 1
+          uint8_t* base = smem + (i & 1) * 3 * kTile;
+          mbar_arrive_expect_tx(&full_bar[i & 1], tx_qkd);
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      int64_t w = 2 * pair + it;
-      if (w >= n_win) w = n_win - 1;                  // odd tail: a valid window again, its results are not stored
-      const int32_t row0 = (int32_t)(w * T);
-      uint8_t* dst = base + it * 64 * 128;
-      tma_load_2d(dst, &tmQKV, &full_bar[st], h * HD, row0);
-      tma_load_2d(dst + kTile, &tmQKV, &full_bar[st], (int32_t)kv_off + h * HD, row0);
-      tma_load_2d(dst + 2 * kTile, &tmQKV, &full_bar[st], (int32_t)(2 * kv_off) + h * HD, row0);
-      tma_load_2d(dst + 3 * kTile, &tmDO, &full_bar[st], h * HD, row0);
-    }
-  };
-  // Shared-memory descriptors are built once: a k step only advances the 14-bit start-address field (by 32 B >> 4 = 2
-  // for K-major operands, 2048 B >> 4 = 128 for MN-major ones), so the single issuing thread spends one add per operand
-  // per MMA instead of rebuilding descriptors — with 32-clock MMAs the issue rate is what paces the tensor pipe.
-  const uint64_t dK_Q0 = make_smem_desc_sw128(smem_u32(smem), 0, 1024);                  // stage 0 Q as K-major operand
-  const uint64_t dM_Q0 = make_smem_desc_sw128(smem_u32(smem), kTile, 1024);              // stage 0 Q as MN-major operand
-  constexpr uint64_t kTileStep = kTile >> 4, kStageStep = (4 * kTile) >> 4;
-  const uint64_t dM_P = make_smem_desc_sw128(smem_u32(Ps), kTile, 1024);
-  const uint64_t dM_dS = make_smem_desc_sw128(smem_u32(dSs), kTile, 1024);
-  const uint64_t dK_dS = make_smem_desc_sw128(smem_u32(dSs), 0, 1024);
-  const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-  // S = Q K^T, dP = dO V^T of the pair in stage st: K-major operands, K = 64 = 4 steps of 16        (thread 0)
-  auto issue_scores = [&](int st, int use) {
-    mbar_wait(&full_bar[st], (uint32_t)(use & 1));
-    tc_fence_after();
-    const uint64_t q = dK_Q0 + st * kStageStep;
+          for (int it = 0; it < 2; ++it) {
+            const int32_t row0 = window_row(i, it);
+            uint8_t* dst = base + it * 64 * 128;
+            tma_load_2d(dst, &tmQKV, &full_bar[i & 1], h * HD, row0);
+            tma_load_2d(dst + kTile, &tmQKV, &full_bar[i & 1], (int32_t)kv_off + h * HD, row0);
+            tma_load_2d(dst + 2 * kTile, &tmDO, &full_bar[i & 1], h * HD, row0);
+          }
+        };
+        auto load_v = [&](int i) {
+          mbar_arrive_expect_tx(v_bar, tx_v);
 #pragma unroll
-    for (int k = 0; k < HD / 16; ++k)
-      umma_bf16(tmem_base + kColS, q + 2 * k, q + kTileStep + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          for (int it = 0; it < 2; ++it)
+            tma_load_2d(Vs + it * 64 * 128, &tmQKV, v_bar, (int32_t)(2 * kv_off) + h * HD, window_row(i, it));
+        };
+        // Shared memory holds the operands of ~1.5 pairs (51 KB each): with HBM latency near 2 us that is only ~25 GB/s per
+        // SM in flight, and every schedule of this kernel measured the same ~3.2 TB/s.  Pairs further ahead are therefore
+        // pulled into L2 (no shared memory needed), so the shared-memory loads see L2 latency.
+        constexpr int kAhead = 4;
+        auto prefetch_pair = [&](int i) {
 #pragma unroll
-    for (int k = 0; k < HD / 16; ++k)
-      umma_bf16(tmem_base + kColDP, q + 3 * kTileStep + 2 * k, q + 2 * kTileStep + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-    umma_commit(s_bar);
-  };
-
-  if (tid == 0 && cta < n_pairs) {
-    issue_loads(cta, 0);
-    issue_scores(0, 0);
-  }
-  uint32_t ph_s = 0, ph_o = 0;
-  int it_n = 0;
-  for (int64_t pair = cta; pair < n_pairs; pair += ctas, ++it_n) {
-    const int st = it_n & 1;
-    uint8_t* Qs = smem + st * 4 * kTile;
-    uint8_t* Ks = Qs + kTile;
-    uint8_t* Vs = Ks + kTile;
-    uint8_t* dOs = Vs + kTile;
-    const bool second_valid = 2 * pair + 1 < n_win;
-    const bool has_next = pair + ctas < n_pairs;
-
-    if (tid == 0 && has_next) {
-      // the other stage was the staging area of the previous iteration's result stores: they must have read it
-      tma_wait_group_read<0>();
-      issue_loads(pair + ctas, st ^ 1);
-    }
-
-    // ---- softmax / dS: four threads per row, 16 keys each ----
-    mbar_wait(s_bar, ph_s);
-    ph_s ^= 1u;
-    tc_fence_after();
-    float s[16], dp[16];
-    tmem_ld_x16(lane_base + kColS + own * 64 + cq4 * 16, s);
-    tmem_ld_x16(lane_base + kColDP + own * 64 + cq4 * 16, dp);
-    tmem_ld_wait();
-    tc_fence_before();
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (cq4 * 16 + j >= T) s[j] = -INFINITY;
-      mx = fmaxf(mx, s[j]);
-    }
-    sts_f(xrow + cq4 * 4, mx);
-    named_bar_sync(1 + q, 128);                        // the four warps of this lane quadrant
-    {
-      const float4 m4 = lds_f4(xrow);                  // keys 0..15 always hold a valid key: the maximum is finite
-      mx = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
-    }
-    const float off = mx * scale_log2;
-    float l = 0.f, ed = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      s[j] = ex2(fmaf(s[j], scale_log2, -off));        // masked keys: ex2(-inf) = 0
-      l += s[j];
-      ed = fmaf(s[j], dp[j], ed);
-    }
-    sts_f(xrow + 2048 + cq4 * 4, l);
-    sts_f(xrow + 4096 + cq4 * 4, ed);
-    named_bar_sync(1 + q, 128);
-    {
-      const float4 l4 = lds_f4(xrow + 2048), e4 = lds_f4(xrow + 4096);
-      l = (l4.x + l4.y) + (l4.z + l4.w);
-      ed = (e4.x + e4.y) + (e4.z + e4.w);
-    }
-    const float inv = ri < T ? 1.f / l : 0.f;          // padded query rows contribute nothing
-    const float dsc = ed * inv;                        // D = sum_j P_j dP_j
-    {
-      const uint32_t prow = smem_u32(Ps) + own * kTile + r * 128, srow = smem_u32(dSs) + own * kTile + r * 128;
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        uint32_t pw[4], sw[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = 8 * jj + 2 * e;
-          const float p0 = s[j] * inv, p1 = s[j + 1] * inv;
-          pw[e] = pack_bf16x2(p0, p1);
-          sw[e] = pack_bf16x2(p0 * (dp[j] - dsc) * scale, p1 * (dp[j + 1] - dsc) * scale);
+          for (int it = 0; it < 2; ++it) {
+            const int32_t row0 = window_row(i, it);
+            tma_prefetch_l2_2d(&tmQKV, h * HD, row0);
+            tma_prefetch_l2_2d(&tmQKV, (int32_t)kv_off + h * HD, row0);
+            tma_prefetch_l2_2d(&tmQKV, (int32_t)(2 * kv_off) + h * HD, row0);
+            tma_prefetch_l2_2d(&tmDO, h * HD, row0);
+          }
+        };
+        load_qkd(0);
+        load_v(0);
+        if (n_it > 1) load_qkd(1);
+        for (int i = 1; i < kAhead && i < n_it; ++i) prefetch_pair(i);
+        for (int i = 0; i < n_it; ++i) {
+          if (i + kAhead < n_it) prefetch_pair(i + kAhead);
+          if (i + 1 < n_it) {                         // V(i) is dead once the scores of pair i are complete
+            mbar_wait(s_bar, (uint32_t)(i & 1));
+            load_v(i + 1);
+          }
+          if (i + 2 < n_it) {                         // Q, K, dO of pair i die with its products
+            mbar_wait(o_bar, (uint32_t)(i & 1));
+            load_qkd(i + 2);
+          }
         }
-        const uint32_t po = (uint32_t)(((cq4 * 2 + jj) ^ rsw) << 4);
-        sts16(prow + po, make_uint4(pw[0], pw[1], pw[2], pw[3]));
-        sts16(srow + po, make_uint4(sw[0], sw[1], sw[2], sw[3]));
+      } else if (role == 1) {
+        // ---- dV(i) = P^T dO (A, B MN-major, K = 128 queries), then S(i+1) = Q K^T (K-major, K = 64) ----
+        wait_inputs(0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + kColS, dK_Q0 + 2 * k, dK_Q0 + kTileStep + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_bar);
+        for (int i = 0; i < n_it; ++i) {
+          mbar_wait(pd_bar, (uint32_t)(i & 1));       // P/dS(i) written; results(i-1) and scores(i) are in registers
+          tc_fence_after();
+          const uint64_t qm = dM_Q0 + (i & 1) * kStageStep;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) umma_bf16(tmem_base + kColDV, dM_P + 128 * k, qm + 2 * kTileStep + 128 * k, idesc_t, k > 0 ? 1u : 0u);
+          umma_commit(o_bar);
+          if (i + 1 < n_it) {
+            wait_inputs(i + 1);
+            const uint64_t q = dK_Q0 + ((i + 1) & 1) * kStageStep;
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + kColS, q + 2 * k, q + kTileStep + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(s_bar);
+          }
+          if (dbias != nullptr && i > 0) bias_products(i - 1, kColBqk, dM_G);
+        }
+        if (dbias != nullptr) {
+          bias_products(n_it - 1, kColBqk, dM_G);
+          umma_commit(c_bar);
+        }
+      } else if (role == 2) {
+        // ---- dK(i) = dS^T Q, then dP(i+1) = dO V^T ----
+        wait_inputs(0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + kColDP, dK_Q0 + 2 * kTileStep + 2 * k, dK_V + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_bar);
+        for (int i = 0; i < n_it; ++i) {
+          mbar_wait(pd_bar, (uint32_t)(i & 1));
+          tc_fence_after();
+          const uint64_t qm = dM_Q0 + (i & 1) * kStageStep;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) umma_bf16(tmem_base + kColDK, dM_dS + 128 * k, qm + 128 * k, idesc_t, k > 0 ? 1u : 0u);
+          umma_commit(o_bar);
+          if (i + 1 < n_it) {
+            wait_inputs(i + 1);
+            const uint64_t q = dK_Q0 + ((i + 1) & 1) * kStageStep;
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + kColDP, q + 2 * kTileStep + 2 * k, dK_V + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(s_bar);
+          }
+          if (dbias != nullptr && i > 0) bias_products(i - 1, kColBkv, dM_G + kTileStep);
+        }
+        if (dbias != nullptr) {
+          bias_products(n_it - 1, kColBkv, dM_G + kTileStep);
+          umma_commit(c_bar);
+        }
+      } else {
+        // ---- dQ(i) = dS K (A K-major, K = 128 keys = two chunks; B MN-major), then the stores of pair i-1's staged results ----
+        auto store_results = [&](int i) {
+          mbar_wait(stg_bar, (uint32_t)(i & 1));
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int64_t w = 2 * (cta + (int64_t)i * ctas) + it;
+            if (w >= n_win) break;
+            const int32_t row0 = (int32_t)(w * T);
+            tma_store_2d(&tmDQKV, Gq + it * 64 * 128, h * HD, row0);
+            tma_store_2d(&tmDQKV, Gk + it * 64 * 128, (int32_t)kv_off + h * HD, row0);
+            tma_store_2d(&tmDQKV, Gv + it * 64 * 128, (int32_t)(2 * kv_off) + h * HD, row0);
+          }
+          tma_commit_group();
+          tma_wait_group_read<0>();
+          mbar_arrive(sf_bar);                        // staging tiles may be rewritten
+        };
+        for (int i = 0; i < n_it; ++i) {
+          mbar_wait(pd_bar, (uint32_t)(i & 1));
+          tc_fence_after();
+          const uint64_t qm = dM_Q0 + (i & 1) * kStageStep;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem_base + kColDQ, dK_dS + (k >> 2) * kChunkStep + (k & 3) * 2, qm + kTileStep + 128 * k, idesc_q, k > 0 ? 1u : 0u);
+          umma_commit(o_bar);
+          if (i > 0) store_results(i - 1);
+        }
+        store_results(n_it - 1);
+        tma_wait_group<0>();
       }
     }
-    fence_proxy_async_smem();
-    __syncthreads();
+  } else {
+    // ===================================== compute warps =====================================
+    const int q = warp & 3, cq4 = warp >> 2;          // TMEM lane quadrant, column quarter (16 keys / 16 head columns)
+    const int r = q * 32 + lane;                      // this thread's row == TMEM lane (shared by 4 threads)
+    const int ri = r & 63;                            // row inside its window
+    const int own = r >> 6;                           // which window of the pair / which 64-key chunk is "ours"
+    const int rsw = r & 7;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float scale_log2 = scale * 1.4426950408889634f;
+    const uint32_t xrow = smem_u32(xch) + r * 16;     // this row's 4 exchange slots (16 B), three planes 2 KB apart
+    const uint32_t prow = smem_u32(Ps) + own * kChunk + r * 128, srow = smem_u32(dSs) + own * kChunk + r * 128;
+    const uint32_t po0 = (uint32_t)(((cq4 * 2) ^ rsw) << 4), po1 = (uint32_t)(((cq4 * 2 + 1) ^ rsw) << 4);
 
-    if (tid == 0) {
-      tc_fence_after();
-      // ---- dV = P^T dO, dK = dS^T Q : A MN-major (M = keys: two 64-wide atoms 16 KB apart), B MN-major, K = 128 queries ----
-      const uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);
-      const uint64_t qm = dM_Q0 + st * kStageStep;                     // this stage's Q | K | V | dO as MN-major operands
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16(tmem_base + kColDV, dM_P + 128 * k, qm + 3 * kTileStep + 128 * k, idesc_t, k > 0 ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16(tmem_base + kColDK, dM_dS + 128 * k, qm + 128 * k, idesc_t, k > 0 ? 1u : 0u);
-      // ---- dQ = dS K : A K-major (K = 128 keys = two chunks), B MN-major ----
-      const uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16(tmem_base + kColDQ, dK_dS + (k >> 2) * kTileStep + (k & 3) * 2, qm + kTileStep + 128 * k, idesc_q, k > 0 ? 1u : 0u);
-      umma_commit(o_bar);
-      // S / dP are free (every thread passed the barrier above): start the next pair's scores behind these products,
-      // so they are ready when this pair's results have been drained
-      if (has_next) issue_scores(st ^ 1, (it_n + 1) >> 1);
-    }
-
-    // ---- results: TMEM -> bf16 -> the (now dead) Q / K / V tiles -> TMA stores (one wait for all three products: waiting
-    //      per product so that the drain overlaps the remaining MMAs measured slower, 470 vs 439 us) ----
-    uint8_t* Gq = Qs;
-    uint8_t* Gk = Ks;
-    uint8_t* Gv = Vs;
-    mbar_wait(o_bar, ph_o);
-    ph_o ^= 1u;
-    tc_fence_after();
-    {
-      float vq[16], vk[16], vv[16];
-      tmem_ld_x16(lane_base + kColDQ + cq4 * 16, vq);
-      tmem_ld_x16(lane_base + kColDK + cq4 * 16, vk);
-      tmem_ld_x16(lane_base + kColDV + cq4 * 16, vv);
-      tmem_ld_wait();
+    // fetch pair i's results into registers is interleaved below; this finishes the job: pack, stage, hand to the control warp
+    auto stage_results = [&](int i, const float (&vq)[16], const float (&vk)[16], const float (&vv)[16]) {
+      if (i > 0) mbar_wait(sf_bar, (uint32_t)((i - 1) & 1));           // the previous pair's stores have read the staging tiles
+      // odd tail: the second window of the last pair is a duplicate — its rows are staged as zeros (they are not stored,
+      // and must not enter the bias gradient)
+      const bool dup = own == 1 && 2 * (cta + (int64_t)i * ctas) + 1 >= n_win;
       if (ri < T) {
         const uint32_t ro = r * 128;
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
-          const uint32_t po = ro + (uint32_t)(((cq4 * 2 + jj) ^ rsw) << 4);
-          sts16(smem_u32(Gq) + po, make_uint4(pack_bf16x2(vq[8 * jj], vq[8 * jj + 1]), pack_bf16x2(vq[8 * jj + 2], vq[8 * jj + 3]),
-                                              pack_bf16x2(vq[8 * jj + 4], vq[8 * jj + 5]), pack_bf16x2(vq[8 * jj + 6], vq[8 * jj + 7])));
-          sts16(smem_u32(Gk) + po, make_uint4(pack_bf16x2(vk[8 * jj], vk[8 * jj + 1]), pack_bf16x2(vk[8 * jj + 2], vk[8 * jj + 3]),
-                                              pack_bf16x2(vk[8 * jj + 4], vk[8 * jj + 5]), pack_bf16x2(vk[8 * jj + 6], vk[8 * jj + 7])));
-          sts16(smem_u32(Gv) + po, make_uint4(pack_bf16x2(vv[8 * jj], vv[8 * jj + 1]), pack_bf16x2(vv[8 * jj + 2], vv[8 * jj + 3]),
-                                              pack_bf16x2(vv[8 * jj + 4], vv[8 * jj + 5]), pack_bf16x2(vv[8 * jj + 6], vv[8 * jj + 7])));
+          const uint32_t po = ro + (jj == 0 ? po0 : po1);
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          sts16(smem_u32(Gq) + po, dup ? z : make_uint4(pack_bf16x2(vq[8 * jj], vq[8 * jj + 1]), pack_bf16x2(vq[8 * jj + 2], vq[8 * jj + 3]),
+                                                        pack_bf16x2(vq[8 * jj + 4], vq[8 * jj + 5]), pack_bf16x2(vq[8 * jj + 6], vq[8 * jj + 7])));
+          sts16(smem_u32(Gk) + po, dup ? z : make_uint4(pack_bf16x2(vk[8 * jj], vk[8 * jj + 1]), pack_bf16x2(vk[8 * jj + 2], vk[8 * jj + 3]),
+                                                        pack_bf16x2(vk[8 * jj + 4], vk[8 * jj + 5]), pack_bf16x2(vk[8 * jj + 6], vk[8 * jj + 7])));
+          sts16(smem_u32(Gv) + po, dup ? z : make_uint4(pack_bf16x2(vv[8 * jj], vv[8 * jj + 1]), pack_bf16x2(vv[8 * jj + 2], vv[8 * jj + 3]),
+                                                        pack_bf16x2(vv[8 * jj + 4], vv[8 * jj + 5]), pack_bf16x2(vv[8 * jj + 6], vv[8 * jj + 7])));
         }
       }
-    }
-    tc_fence_before();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stg_bar);            // control: TMA stores and the bias-gradient products
+    };
+
+    for (int i = 0; i < n_it; ++i) {
+      // ---- softmax / dS of pair i in registers: four threads per row, 16 keys each ----
+      mbar_wait(s_bar, (uint32_t)(i & 1));
+      tc_fence_after();
+      float s[16], dp[16];
+      tmem_ld_x16(lane_base + kColS + own * 64 + cq4 * 16, s);
+      tmem_ld_x16(lane_base + kColDP + own * 64 + cq4 * 16, dp);
+      tmem_ld_wait();
+      float mx = -INFINITY;
 #pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        if (it == 1 && !second_valid) break;
-        const int32_t row0 = (int32_t)((2 * pair + it) * T);
-        tma_store_2d(&tmDQKV, Gq + it * 64 * 128, h * HD, row0);
-        tma_store_2d(&tmDQKV, Gk + it * 64 * 128, (int32_t)kv_off + h * HD, row0);
-        tma_store_2d(&tmDQKV, Gv + it * 64 * 128, (int32_t)(2 * kv_off) + h * HD, row0);
+      for (int j = 0; j < 16; ++j) {
+        if (cq4 * 16 + j >= T) s[j] = -INFINITY;
+        mx = fmaxf(mx, s[j]);
       }
-      tma_commit_group();
-    }
-    if (dbias != nullptr) {
-      // in_proj bias gradient from the staged (rounded) rows: this thread owns 16-byte piece (tid & 7) of rows g and 64 + g
-      const int j = tid & 7, g = tid >> 3;
-      if (g < T) {
-        const uint32_t o0 = (uint32_t)(g * 128 + ((j ^ (g & 7)) << 4));
-        add_bf16x8(cq, lds16(smem_u32(Gq) + o0));
-        add_bf16x8(ck, lds16(smem_u32(Gk) + o0));
-        add_bf16x8(cv, lds16(smem_u32(Gv) + o0));
-        if (second_valid) {
-          add_bf16x8(cq, lds16(smem_u32(Gq) + o0 + 64 * 128));
-          add_bf16x8(ck, lds16(smem_u32(Gk) + o0 + 64 * 128));
-          add_bf16x8(cv, lds16(smem_u32(Gv) + o0 + 64 * 128));
-        }
+      sts_f(xrow + cq4 * 4, mx);
+      named_bar_sync(1 + q, 128);                      // the four warps of this lane quadrant
+      {
+        const float4 m4 = lds_f4(xrow);                // keys 0..15 always hold a valid key: the maximum is finite
+        mx = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
       }
-    }
-    __syncthreads();                                  // staging reads done before this stage is loaded again
-  }
-  if (tid == 0) tma_wait_group<0>();
-  if (dbias != nullptr) {
-    // lanes that share (tid & 7) hold partial sums of the same 8 columns: fold the warp's 4 row groups, then one atomic
-    // per column per warp
+      const float off = mx * scale_log2;
+      float l = 0.f, ed = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 8);  cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 16);
-      ck[j] += __shfl_xor_sync(0xffffffffu, ck[j], 8);  ck[j] += __shfl_xor_sync(0xffffffffu, ck[j], 16);
-      cv[j] += __shfl_xor_sync(0xffffffffu, cv[j], 8);  cv[j] += __shfl_xor_sync(0xffffffffu, cv[j], 16);
-    }
-    if (lane < 8) {
-      const int c = h * HD + lane * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(dbias + c + j, cq[j]);
-        atomicAdd(dbias + kv_off + c + j, ck[j]);
-        atomicAdd(dbias + 2 * kv_off + c + j, cv[j]);
+      for (int j = 0; j < 16; ++j) {
+        s[j] = ex2(fmaf(s[j], scale_log2, -off));      // masked keys: ex2(-inf) = 0
+        l += s[j];
+        ed = fmaf(s[j], dp[j], ed);
       }
+      sts_f(xrow + 2048 + cq4 * 4, l);
+      sts_f(xrow + 4096 + cq4 * 4, ed);
+      named_bar_sync(1 + q, 128);
+      {
+        const float4 l4 = lds_f4(xrow + 2048), e4 = lds_f4(xrow + 4096);
+        l = (l4.x + l4.y) + (l4.z + l4.w);
+        ed = (e4.x + e4.y) + (e4.z + e4.w);
+      }
+      const float inv = ri < T ? 1.f / l : 0.f;        // padded query rows contribute nothing
+      const float dsc = ed * inv;                      // D = sum_j P_j dP_j
+      uint32_t pw[8], sw[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float p0 = s[2 * e] * inv, p1 = s[2 * e + 1] * inv;
+        pw[e] = pack_bf16x2(p0, p1);
+        sw[e] = pack_bf16x2(p0 * (dp[2 * e] - dsc) * scale, p1 * (dp[2 * e + 1] - dsc) * scale);
+      }
+      // ---- the products of pair i-1 are complete: take its results out of TMEM, which also frees the P/dS tiles ----
+      float vq[16], vk[16], vv[16];
+      if (i > 0) {
+        mbar_wait(o_bar, (uint32_t)((i - 1) & 1));
+        tc_fence_after();
+        tmem_ld_x16(lane_base + kColDQ + cq4 * 16, vq);
+        tmem_ld_x16(lane_base + kColDK + cq4 * 16, vk);
+        tmem_ld_x16(lane_base + kColDV + cq4 * 16, vv);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      sts16(prow + po0, make_uint4(pw[0], pw[1], pw[2], pw[3]));
+      sts16(prow + po1, make_uint4(pw[4], pw[5], pw[6], pw[7]));
+      sts16(srow + po0, make_uint4(sw[0], sw[1], sw[2], sw[3]));
+      sts16(srow + po1, make_uint4(sw[4], sw[5], sw[6], sw[7]));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pd_bar);              // control: products(i), then scores(i+1)
+      // ---- while they run: stage and store the results of pair i-1 ----
+      if (i > 0) stage_results(i - 1, vq, vk, vv);
+    }
+    if (n_it > 0) {
+      float vq[16], vk[16], vv[16];
+      mbar_wait(o_bar, (uint32_t)((n_it - 1) & 1));
+      tc_fence_after();
+      tmem_ld_x16(lane_base + kColDQ + cq4 * 16, vq);
+      tmem_ld_x16(lane_base + kColDK + cq4 * 16, vk);
+      tmem_ld_x16(lane_base + kColDV + cq4 * 16, vv);
+      tmem_ld_wait();
+      tc_fence_before();
+      stage_results(n_it - 1, vq, vk, vv);
+    }
+    if (dbias != nullptr && n_it > 0 && cq4 == 0) {
+      // one thread per TMEM lane: lane m of column kColBqk holds the sum of dQ column m (m < 64) or dK column m - 64,
+      // lane m of column kColBkv that of dK column m (m < 64) or dV column m - 64 — over every window this CTA processed
+      mbar_wait(c_bar, 0);
+      tc_fence_after();
+      float bqk[16], bkv[16];
+      tmem_ld_x16(lane_base + kColBqk, bqk);
+      tmem_ld_x16(lane_base + kColBkv, bkv);
+      tmem_ld_wait();
+      tc_fence_before();
+      const int c = h * HD + ri;
+      atomicAdd(dbias + (own == 0 ? 0 : kv_off) + c, bqk[0]);           // dQ | dK
+      if (own == 1) atomicAdd(dbias + 2 * kv_off + c, bkv[0]);          // dV
     }
   }
   tc_fence_before();
