@@ -114,7 +114,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint64_t* stg_bar = pd_bar + 1;                     // results staged
   uint64_t* sf_bar = stg_bar + 1;                     // staging tiles free again (TMA stores and bias products have read them)
   uint64_t* c_bar = sf_bar + 1;                       // all bias-gradient products complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_bar + 1);
+  uint64_t* sc_bar = c_bar + 1;                       // S / dP of the pair have been copied to registers: the columns are free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sc_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x % H;
@@ -139,6 +140,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     mbar_init(stg_bar, kComputeThreads / 32);
     mbar_init(sf_bar, dbias != nullptr ? 3 : 1);      // storer + the two warps that issue the bias products
     mbar_init(c_bar, 2);
+    mbar_init(sc_bar, kComputeThreads / 32);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -243,19 +245,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + kColS, dK_Q0 + 2 * k, dK_Q0 + kTileStep + 2 * k, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(s_bar);
         for (int i = 0; i < n_it; ++i) {
-          mbar_wait(pd_bar, (uint32_t)(i & 1));       // P/dS(i) written; results(i-1) and scores(i) are in registers
-          tc_fence_after();
-          const uint64_t qm = dM_Q0 + (i & 1) * kStageStep;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) umma_bf16(tmem_base + kColDV, dM_P + 128 * k, qm + 2 * kTileStep + 128 * k, idesc_t, k > 0 ? 1u : 0u);
-          umma_commit(o_bar);
+          // the next pair's scores start as soon as this pair's S / dP have been read out of TMEM (early in the softmax):
+          // they are what the compute warps wait for next
           if (i + 1 < n_it) {
             wait_inputs(i + 1);
+            mbar_wait(sc_bar, (uint32_t)(i & 1));
+            tc_fence_after();
             const uint64_t q = dK_Q0 + ((i + 1) & 1) * kStageStep;
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + kColS, q + 2 * k, q + kTileStep + 2 * k, idesc_s, k > 0 ? 1u : 0u);
             umma_commit(s_bar);
           }
+          mbar_wait(pd_bar, (uint32_t)(i & 1));       // P/dS(i) written; results(i-1) are in registers
+          tc_fence_after();
+          const uint64_t qm = dM_Q0 + (i & 1) * kStageStep;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) umma_bf16(tmem_base + kColDV, dM_P + 128 * k, qm + 2 * kTileStep + 128 * k, idesc_t, k > 0 ? 1u : 0u);
+          umma_commit(o_bar);
           if (dbias != nullptr && i > 0) bias_products(i - 1, kColBqk, dM_G);
         }
         if (dbias != nullptr) {
@@ -269,19 +275,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + kColDP, dK_Q0 + 2 * kTileStep + 2 * k, dK_V + 2 * k, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(s_bar);
         for (int i = 0; i < n_it; ++i) {
+          if (i + 1 < n_it) {
+            wait_inputs(i + 1);
+            mbar_wait(sc_bar, (uint32_t)(i & 1));
+            tc_fence_after();
+            const uint64_t q = dK_Q0 + ((i + 1) & 1) * kStageStep;
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + kColDP, q + 2 * kTileStep + 2 * k, dK_V + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(s_bar);
+          }
           mbar_wait(pd_bar, (uint32_t)(i & 1));
           tc_fence_after();
           const uint64_t qm = dM_Q0 + (i & 1) * kStageStep;
 #pragma unroll
           for (int k = 0; k < 8; ++k) umma_bf16(tmem_base + kColDK, dM_dS + 128 * k, qm + 128 * k, idesc_t, k > 0 ? 1u : 0u);
           umma_commit(o_bar);
-          if (i + 1 < n_it) {
-            wait_inputs(i + 1);
-            const uint64_t q = dK_Q0 + ((i + 1) & 1) * kStageStep;
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + kColDP, q + 2 * kTileStep + 2 * k, dK_V + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-            umma_commit(s_bar);
-          }
           if (dbias != nullptr && i > 0) bias_products(i - 1, kColBkv, dM_G + kTileStep);
         }
         if (dbias != nullptr) {
@@ -365,19 +373,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tmem_ld_x16(lane_base + kColS + own * 64 + cq4 * 16, s);
       tmem_ld_x16(lane_base + kColDP + own * 64 + cq4 * 16, dp);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sc_bar);              // control: the next pair's scores may overwrite S / dP
+      // One exchange round: every quarter publishes its local maximum m_q, sum l_q = sum exp(s - m_q) and
+      // e_q = sum exp(s - m_q) dP, then rescales by exp(m_q - M) like an online softmax merge.
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         if (cq4 * 16 + j >= T) s[j] = -INFINITY;
         mx = fmaxf(mx, s[j]);
       }
-      sts_f(xrow + cq4 * 4, mx);
-      named_bar_sync(1 + q, 128);                      // the four warps of this lane quadrant
-      {
-        const float4 m4 = lds_f4(xrow);                // keys 0..15 always hold a valid key: the maximum is finite
-        mx = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
-      }
-      const float off = mx * scale_log2;
+      // a quarter that holds no valid key (T <= 16 * cq4) publishes m = -inf, l = e = 0 and scales by 0 below
+      const float off = mx == -INFINITY ? 0.f : mx * scale_log2;
       float l = 0.f, ed = 0.f;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -385,20 +393,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         l += s[j];
         ed = fmaf(s[j], dp[j], ed);
       }
+      sts_f(xrow + cq4 * 4, mx);
       sts_f(xrow + 2048 + cq4 * 4, l);
       sts_f(xrow + 4096 + cq4 * 4, ed);
-      named_bar_sync(1 + q, 128);
+      named_bar_sync(1 + q, 128);                      // the four warps of this lane quadrant
+      float own_scale;
       {
-        const float4 l4 = lds_f4(xrow + 2048), e4 = lds_f4(xrow + 4096);
-        l = (l4.x + l4.y) + (l4.z + l4.w);
-        ed = (e4.x + e4.y) + (e4.z + e4.w);
+        const float4 m4 = lds_f4(xrow), l4 = lds_f4(xrow + 2048), e4 = lds_f4(xrow + 4096);
+        const float M = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));      // quarter 0 always holds a valid key: finite
+        const float Ml = M * scale_log2;
+        const float f0 = ex2(fmaf(m4.x, scale_log2, -Ml)), f1 = ex2(fmaf(m4.y, scale_log2, -Ml));
+        const float f2 = ex2(fmaf(m4.z, scale_log2, -Ml)), f3 = ex2(fmaf(m4.w, scale_log2, -Ml));
+        l = fmaf(l4.x, f0, fmaf(l4.y, f1, fmaf(l4.z, f2, l4.w * f3)));
+        ed = fmaf(e4.x, f0, fmaf(e4.y, f1, fmaf(e4.z, f2, e4.w * f3)));
+        own_scale = cq4 == 0 ? f0 : (cq4 == 1 ? f1 : (cq4 == 2 ? f2 : f3));
       }
       const float inv = ri < T ? 1.f / l : 0.f;        // padded query rows contribute nothing
       const float dsc = ed * inv;                      // D = sum_j P_j dP_j
+      const float pscale = inv * own_scale;            // exp(s - m_q) -> P
       uint32_t pw[8], sw[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float p0 = s[2 * e] * inv, p1 = s[2 * e + 1] * inv;
+        const float p0 = s[2 * e] * pscale, p1 = s[2 * e + 1] * pscale;
         pw[e] = pack_bf16x2(p0, p1);
         sw[e] = pack_bf16x2(p0 * (dp[2 * e] - dsc) * scale, p1 * (dp[2 * e + 1] - dsc) * scale);
       }
