@@ -171,11 +171,16 @@ int ibm_add_time_pos_bwd(const void* dh_bf16, int64_t ld, void* dtemb_bf16, int6
  *   m + (kb / kb_per_tap) (implicit-GEMM temporal convolution, Groundlink.py:41).
  *   colsum_out: NULL, or fp32[N] that the column sums of the bf16 output (rows < M, as rounded) are
  *   ADDED to by the epilogue: when D is the gradient w.r.t. a layer's pre-activation this is that
- *   layer's bias gradient (nn.Linear bias, TransformerBaseline.py:15) without another pass over D. */
+ *   layer's bias gradient (nn.Linear bias, TransformerBaseline.py:15) without another pass over D.
+ *   mask / ldmask / mask_mode: sign bitmask [M][ldmask bytes] (bit c&7 of byte c>>3 <-> column c; bf16 output,
+ *   N %% 64 == 0, no aux).  mask_mode 1 (forward of Linear+ReLU, TransformerBaseline.py:15-16): bit = (D > 0) is
+ *   written next to D.  mask_mode 2 (its dgrad): D = (acc + bias) where the bit is set, 0 elsewhere — the ReLU
+ *   derivative from 1 bit per element instead of re-reading the saved activation (aux_mode 2).  0: unused. */
 int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb,
                   int32_t b_mn_major, int64_t M, int64_t N, int64_t K, const float* bias, int32_t act,
                   const void* aux, int64_t ldaux, int32_t aux_mode, void* D, int64_t ldd,
-                  int32_t out_dtype, int32_t accumulate, int32_t split_k, int32_t taps, float* colsum_out, void* stream);
+                  int32_t out_dtype, int32_t accumulate, int32_t split_k, int32_t taps, float* colsum_out, void* mask,
+                  int64_t ldmask, int32_t mask_mode, void* stream);
 
 /* out[n] (+)= sum_m X[m,n]   (bias gradients; X bf16 [M,N] ld; out fp32; accumulate via atomics) */
 int ibm_colsum_bf16(const void* X, int64_t ld, int64_t M, int64_t N, float* out, void* stream);

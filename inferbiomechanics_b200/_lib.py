@@ -33,7 +33,7 @@ SIGNATURES = {
     "ibm_add_time_pos": [P, _i64, P, _i64, P, _i64, _i32, _i32, P],
     "ibm_add_time_pos_bwd": [P, _i64, P, _i64, P, _i64, _i32, _i32, P],
     "ibm_gemm_bf16": [P, _i64, _i32, P, _i64, _i32, _i64, _i64, _i64, P, _i32, P, _i64, _i32, P, _i64, _i32, _i32,
-                      _i32, _i32, P, P],
+                      _i32, _i32, P, P, _i64, _i32, P],
     "ibm_colsum_bf16": [P, _i64, _i64, _i64, P, P],
     "ibm_act_fwd": [P, P, _i64, _i32, P],
     "ibm_act_bwd": [P, P, P, _i64, _i32, P],

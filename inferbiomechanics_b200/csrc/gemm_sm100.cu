@@ -93,6 +93,9 @@ struct Args {
   const __nv_bfloat16* aux;
   int64_t ldaux;
   float* colsum;           // optional fp32[N]: += column sums of the (bf16-rounded) output — a bias gradient
+  uint8_t* mask;           // optional sign bitmask [M][ldmask bytes], bit (c & 7) of byte c >> 3 <-> column c
+  int64_t ldmask;
+  int32_t mask_mode;       // 1: write (output > 0) after the activation; 2: zero the outputs whose bit is clear
 };
 
 __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int nstages) {
@@ -460,6 +463,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n_valid = (int)max((int64_t)0, min((int64_t)BN, args.N - n0));              // 0: the tile lies beyond N
       const int n_chunks = (n_valid + CW - 1) / CW;
 
+      // ReLU-derivative bitmask of this thread's row (mask_mode 2): 8 bytes per chunk, fetched before the accumulator wait
+      // so that the (uncoalesced, tiny) loads fly under the main loop
+      uint2 mbits[(BN / CW + 1) / 2];
+      if constexpr (!kOutF32 && !kAux) {
+        if (args.mask_mode == 2) {
+          const int64_t row = (int64_t)m0 + lane;
+#pragma unroll
+          for (int i = 0; i < (BN / CW + 1) / 2; ++i) {
+            const int ch = half + 2 * i;
+            mbits[i] = make_uint2(0u, 0u);
+            if (ch < n_chunks && row < args.M) mbits[i] = __ldg(reinterpret_cast<const uint2*>(args.mask + row * args.ldmask + ((n0 + ch * CW) >> 3)));
+          }
+        }
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
@@ -526,6 +543,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             epi_dispatch_aux<PT>(v, smem_u32(my_aux + xb * kWarpStage + lane * 128), rsw, args.act, args.aux_mode, kAuxRegs ? ax : nullptr);
           } else {
             epi_dispatch_plain<PT>(v, args.act);
+            if constexpr (!kOutF32) {
+              if (args.mask_mode == 1) {
+                // the sign pattern of the (post-activation) outputs: what the dgrad of this layer needs instead of the
+                // whole activation matrix (1 bit instead of 16 per element)
+                // outputs are >= 0 here (ReLU): x > 0  <=>  the sign bit of -bits(x) is set; a funnel shift pushes that
+                // bit into the word, two instructions per element
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int j = 31; j >= 0; --j) {
+                  lo = __funnelshift_l((uint32_t)(-(int32_t)__float_as_uint(fmaxf(v[j], 0.f))), lo, 1);
+                  hi = __funnelshift_l((uint32_t)(-(int32_t)__float_as_uint(fmaxf(v[32 + j], 0.f))), hi, 1);
+                }
+                const int64_t row = (int64_t)m0 + lane;
+                if (row < args.M && c0 + PT <= args.N) *reinterpret_cast<uint2*>(args.mask + row * args.ldmask + (c0 >> 3)) = make_uint2(lo, hi);
+              } else if (args.mask_mode == 2) {
+                const uint2 mb = mbits[(ch - half) >> 1];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (!((mb.x >> j) & 1u)) v[j] = 0.f;
+                  if (!((mb.y >> j) & 1u)) v[32 + j] = 0.f;
+                }
+              }
+            }
             if (args.aux_mode != 0) {
               // fp32-output fallback: aux read straight from global memory (not on the training path)
               const int64_t row = (int64_t)m0 + lane;
@@ -691,7 +731,7 @@ extern "C" int ibm_debug_gemm_max_clusters(int32_t cluster_size) {
 extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
                              int64_t M, int64_t N, int64_t K, const float* bias, int32_t act, const void* aux, int64_t ldaux,
                              int32_t aux_mode, void* D, int64_t ldd, int32_t out_dtype, int32_t accumulate, int32_t split_k,
-                             int32_t taps, float* colsum_out, void* stream) {
+                             int32_t taps, float* colsum_out, void* mask, int64_t ldmask, int32_t mask_mode, void* stream) {
   using namespace ibm;
   using namespace ibm::gemm;
   IBM_CHECK_ARCH();
@@ -708,6 +748,10 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   IBM_CHECK_ARG(!accumulate || (out_dtype == IBM_F32 && act == IBM_ACT_NONE && aux_mode == 0 && bias == nullptr),
                 "gemm: accumulate mode needs fp32 output and a plain epilogue");
   IBM_CHECK_ARG(colsum_out == nullptr || (out_dtype == IBM_BF16 && !accumulate), "gemm: colsum_out needs a bf16 output");
+  IBM_CHECK_ARG(mask_mode >= 0 && mask_mode <= 2, "gemm: bad mask mode");
+  IBM_CHECK_ARG(mask_mode == 0 || (mask != nullptr && out_dtype == IBM_BF16 && !accumulate && aux_mode == 0 && N % 64 == 0 &&
+                                   ldmask % 8 == 0 && ldmask * 8 >= N && (reinterpret_cast<uintptr_t>(mask) & 7) == 0),
+                "gemm: sign bitmask needs a bf16 output without aux, N %% 64 == 0 and an 8-byte aligned mask with ldmask %% 8 == 0");
   if (taps < 1) taps = 1;
   IBM_CHECK_ARG(taps == 1 || (!a_mn_major && K % taps == 0 && (K / taps) % 8 == 0), "gemm: taps needs K-major A and K/taps %% 8 == 0");
 
@@ -765,6 +809,9 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   args.aux = static_cast<const __nv_bfloat16*>(aux);
   args.ldaux = ldaux;
   args.colsum = colsum_out;
+  args.mask = static_cast<uint8_t*>(mask);
+  args.ldmask = ldmask;
+  args.mask_mode = mask_mode;
   // With taps the B operand is [N, taps * kb_per_tap * 64] (each tap's K padded to whole k blocks).
   const int64_t Kb = taps == 1 ? K : (int64_t)args.kb_total * BLOCK_K;
 

@@ -10,6 +10,7 @@ only the memory the kernels read and write.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -146,6 +147,9 @@ class EncoderLayerPlan:
         d, ff = self.d, self.ff
         names = [("qkv", 3 * d), ("o", d), ("s1", d), ("x1", d), ("h", ff), ("s2", d), ("x2", d)]
         out = {k: buf.tensor(st, f"{tag}.{k}", (M, w), BF16) for k, w in names}
+        # sign bits of h (1 bit per element): all the FFN-2 dgrad needs of the saved activation
+        use_mask = train and ff % 64 == 0 and os.environ.get("IBM_NO_HMASK", "0") != "1"     # env switch: A/B measurements
+        out["hmask"] = buf.tensor(st, f"{tag}.hmask", (M, ff // 8), torch.uint8) if use_mask else None
         for k in ("mean1", "rstd1", "mean2", "rstd2"):
             out[k] = buf.tensor(st, f"{tag}.{k}", (M,), F32)
         return out
@@ -160,7 +164,7 @@ class EncoderLayerPlan:
         ops.layernorm_fwd(a["s1"], a["x1"], A.master_of(n("norm1.weight")), A.master_of(n("norm1.bias")), M, d,
                           mean=a["mean1"], rstd=a["rstd1"])
         ops.gemm(a["x1"], A.shadow_of(n("feedforward.0.weight"), (ff, d)), a["h"], M, ff, d,
-                 bias=A.master_of(n("feedforward.0.bias")), act="relu")
+                 bias=A.master_of(n("feedforward.0.bias")), act="relu", mask=a.get("hmask"), mask_mode=1)
         ops.gemm(a["h"], A.shadow_of(n("feedforward.2.weight"), (d, ff)), a["s2"], M, d, ff,
                  bias=A.master_of(n("feedforward.2.bias")), aux=a["x1"], aux_mode=1)
         ops.layernorm_fwd(a["s2"], a["x2"], A.master_of(n("norm2.weight")), A.master_of(n("norm2.bias")), M, d,
@@ -179,8 +183,12 @@ class EncoderLayerPlan:
         # FFN-2: dW2 += ds^T h ; dh = (ds · W2) ∘ relu'(h)
         ops.gemm(ds, a["h"], g(n("feedforward.2.weight"), (d, ff)), d, ff, M, a_mn=True, b_mn=True, accumulate=True)
         #        db1 = colsum(dh) accumulated by the same epilogue
-        ops.gemm(ds, A.shadow_of(n("feedforward.2.weight"), (d, ff)), dh, M, ff, d, b_mn=True, act="relu", aux=a["h"],
-                 aux_mode=2, colsum=g(n("feedforward.0.bias")))
+        if a.get("hmask") is not None:
+            ops.gemm(ds, A.shadow_of(n("feedforward.2.weight"), (d, ff)), dh, M, ff, d, b_mn=True, mask=a["hmask"], mask_mode=2,
+                     colsum=g(n("feedforward.0.bias")))
+        else:
+            ops.gemm(ds, A.shadow_of(n("feedforward.2.weight"), (d, ff)), dh, M, ff, d, b_mn=True, act="relu", aux=a["h"],
+                     aux_mode=2, colsum=g(n("feedforward.0.bias")))
         # FFN-1: dW1 += dh^T x1 ; dx1 = dh · W1 + ds (residual)
         ops.gemm(dh, a["x1"], g(n("feedforward.0.weight"), (ff, d)), ff, d, M, a_mn=True, b_mn=True, accumulate=True)
         ops.gemm(dh, A.shadow_of(n("feedforward.0.weight"), (ff, d)), dx1, M, d, ff, b_mn=True, aux=ds, aux_mode=1)
@@ -286,6 +294,7 @@ class DenoiserEngine:
         for l in range(self.L - 1, -1, -1):
             layer = self.layers[l]
             a = {k: st[f"L{l}.{k}"] for k in ("qkv", "o", "s1", "x1", "h", "s2", "x2", "mean1", "rstd1", "mean2", "rstd2")}
+            a["hmask"] = st.get(f"L{l}.hmask")
             x_in = st["h0"] if l == 0 else st[f"L{l - 1}.x2"]
             layer.backward(x_in, a, dx, sc, M, B, F, other)
             dx, other = other, dx

@@ -47,9 +47,11 @@ def round_up(x: int, m: int) -> int:
 def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, M: int, N: int, K: int, *, lda=None, ldb=None, ldd=None,
          a_mn=False, b_mn=False, bias: Optional[torch.Tensor] = None, act="none", aux: Optional[torch.Tensor] = None,
          ldaux: int = 0, aux_mode: int = 0, accumulate=False, split_k: int = 0, taps: int = 1,
-         colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+         colsum: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, mask_mode: int = 0) -> torch.Tensor:
     """out[M,N] (+)= epilogue(A[M,K] · B[N,K]^T); see ibm_gemm_bf16.  Leading dims default to the
-    tensors' row strides.  colsum (fp32 [N]): += column sums of the bf16 output (a bias gradient)."""
+    tensors' row strides.  colsum (fp32 [N]): += column sums of the bf16 output (a bias gradient).
+    mask (uint8 [M, N/8]) with mask_mode 1: sign bits of the output are written; mask_mode 2: outputs whose bit is clear
+    are zeroed (ReLU derivative without re-reading the activation)."""
     _require_cuda(A, B, out)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     lda = A.stride(0) if lda is None else lda
@@ -59,7 +61,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
         ldaux = aux.stride(0)
     od = F32 if out.dtype == torch.float32 else BF16
     call("ibm_gemm_bf16", _p(A), lda, int(a_mn), _p(B), ldb, int(b_mn), M, N, K, _p(bias), ACT[act], _p(aux), ldaux,
-         aux_mode, _p(out), ldd, od, int(accumulate), split_k, taps, _p(colsum), stream_ptr())
+         aux_mode, _p(out), ldd, od, int(accumulate), split_k, taps, _p(colsum), _p(mask),
+         0 if mask is None else mask.stride(0), mask_mode if mask is not None else 0, stream_ptr())
     return out
 
 

@@ -6,6 +6,7 @@ outputs (one bf16 rounding = 2^-8 relative) and 1e-4 relative-to-scale for fp32 
 """
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -139,6 +140,32 @@ def test_gemm_wgrad_mn_mn_accumulate(Mtok, Nout, Kin, split):
     ops.gemm(dY.cuda(), X.cuda(), dW, Nout, Kin, Mtok, a_mn=True, b_mn=True, accumulate=True, split_k=split)
     ref = init.double() + dY[:, :Nout].double().t() @ X[:, :Kin].double()
     _check(dW, ref, False, f"wgrad {Mtok} {Nout}x{Kin}")
+
+
+@pytest.mark.parametrize("M,N,K", [(515, 512, 256), (4000, 2048, 512), (300, 128, 64), (40000, 2048, 512)])
+def test_gemm_relu_sign_bitmask(M, N, K):
+    """mask_mode 1 writes (relu output > 0) bits next to the forward output; mask_mode 2 applies them in the dgrad:
+    identical to the aux_mode-2 path that re-reads the activation."""
+    from inferbiomechanics_b200 import ops
+    X, W = _mk(M, K, K, 61), _mk(N, K, K, 62, 1.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(63))
+    h = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    mask = torch.full((M, N // 8), 0xAA, dtype=torch.uint8, device="cuda")
+    ops.gemm(X.cuda(), W.cuda(), h, M, N, K, bias=bias.cuda(), act="relu", mask=mask, mask_mode=1)
+    bits = torch.from_numpy(np.unpackbits(mask.cpu().numpy(), axis=1, bitorder="little")).bool()
+    assert torch.equal(bits, h.cpu() > 0)                          # bit-exact: the sign of what was stored
+    # dgrad: dY [M, Kd] · Wd [Kd, N]  gated by the bits  ==  the aux_mode-2 result, element for element
+    Kd = 256
+    dY, Wd = _mk(M, Kd, Kd, 64), _mk(Kd, N, N, 65, 1.0 / math.sqrt(Kd))
+    a = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    b = torch.empty_like(a)
+    ca, cb = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+    ops.gemm(dY.cuda(), Wd.cuda(), a, M, N, Kd, b_mn=True, mask=mask, mask_mode=2, colsum=ca)
+    ops.gemm(dY.cuda(), Wd.cuda(), b, M, N, Kd, b_mn=True, act="relu", aux=h, aux_mode=2, colsum=cb)
+    assert torch.equal(a, b)
+    torch.testing.assert_close(ca, cb, rtol=1e-4, atol=1e-3 * math.sqrt(M))
+    with pytest.raises(ValueError):
+        ops.gemm(X.cuda(), W.cuda(), h, M, N, K, mask=mask[:, :-1].contiguous(), mask_mode=1)      # ldmask*8 < N
 
 
 def test_gemm_a_stationary_mode_parity():

@@ -21,6 +21,8 @@ CASES = {
     "outproj_dgrad": (M, 512, 512, 0, 1, 0, "none", 0, 0, 0),
     "ffn2_dgrad": (M, 2048, 512, 0, 1, 0, "relu", 2, 0, 0),
     "ffn2_dgrad_cs": (M, 2048, 512, 0, 1, 0, "relu", 2, 0, 0),       # + fused bias-gradient column sums
+    "ffn2_dgrad_mask_cs": (M, 2048, 512, 0, 1, 0, "none", 0, 0, 0),  # ReLU derivative from the sign bitmask + column sums
+    "ffn1_fwd_mask": (M, 2048, 512, 0, 0, 1, "relu", 0, 0, 0),       # forward that also writes the sign bitmask
     "ffn1_dgrad_res": (M, 512, 2048, 0, 1, 0, "none", 1, 0, 0),
     "qkv_dgrad_res": (M, 512, 1536, 0, 1, 0, "none", 1, 0, 0),
     "ffn1_wgrad": (2048, 512, M, 1, 1, 0, "none", 0, 1, 1),
@@ -39,8 +41,10 @@ def run(name, iters=10):
     bv = torch.randn(n, device=dev) if bias else None
     aux = torch.randn(m, n, device=dev).to(torch.bfloat16) if aux_mode else None
     cs = torch.zeros(n, device=dev) if name.endswith("_cs") else None
+    mask = torch.zeros(m, n // 8, dtype=torch.uint8, device=dev) if "_mask" in name else None
+    mm = 0 if mask is None else (1 if act == "relu" else 2)
     f = lambda: ops.gemm(A, B, out, m, n, k, a_mn=bool(a_mn), b_mn=bool(b_mn), bias=bv, act=act, aux=aux, aux_mode=aux_mode,
-                         accumulate=bool(acc), colsum=cs)
+                         accumulate=bool(acc), colsum=cs, mask=mask, mask_mode=mm)
     for _ in range(3):
         f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
