@@ -1,0 +1,62 @@
+"""CLI surface (no GPU): the train / analyze sub-commands accept the reference's command lines and defaults
+(/root/reference/src/cli/train.py:24-69, analyze.py:23-47), the model factory and checkpoint loader keep the reference's
+signatures (abstract_command.py:44-120), and the pre-packed store header round-trips."""
+import argparse
+import inspect
+import os
+
+import pytest
+import torch
+
+
+def _parser():
+    from inferbiomechanics_b200.cli.analyze import AnalyzeCommand
+    from inferbiomechanics_b200.cli.train import TrainCommand
+    p = argparse.ArgumentParser()
+    sub = p.add_subparsers(dest="command")
+    for c in (TrainCommand(), AnalyzeCommand()):
+        c.register_subcommand(sub)
+    return p
+
+
+def test_train_flags_and_defaults_match_reference():
+    a = _parser().parse_args(["train"])
+    # defaults of the reference (train.py:26-69)
+    assert (a.dataset_home, a.model_type, a.output_data_format, a.checkpoint_dir) == ("../data", "feedforward", "all_frames", "../checkpoints")
+    assert (a.history_len, a.stride, a.learning_rate, a.dropout, a.dropout_prob) == (50, 5, 1e-4, False, 0.5)
+    assert (a.hidden_dims, a.batchnorm, a.activation, a.epochs, a.opt_type, a.batch_size) == ([512, 512], False, "sigmoid", 10, "rmsprop", 64)
+    assert a.predict_grf_components == list(range(6)) and a.predict_wrench_components == list(range(12))
+    assert a.no_wandb is False and a.short is False and a.compute_report is False and a.data_loading_workers == 1
+    # a reference-style command line parses unchanged
+    b = _parser().parse_args("train --model-type groundlink --no-wandb --history-len 100 --stride 2 --opt-type adam --batch-size 128 "
+                             "--hidden-dims 256 256 128 --activation relu --predict-grf-components 1 4 --trial-filter walk run".split())
+    assert b.model_type == "groundlink" and b.hidden_dims == [256, 256, 128] and b.predict_grf_components == [1, 4]
+
+
+def test_analyze_flags_and_defaults_match_reference():
+    a = _parser().parse_args(["analyze"])
+    assert (a.model_type, a.history_len, a.stride, a.hidden_dims, a.activation) == ("feedforward", 50, 5, [512, 512], "sigmoid")
+    assert a.predict_grf_components == [1] and a.predict_cop_components == [] and a.predict_wrench_components == []
+
+
+def test_factory_and_checkpoint_loader_signatures(tmp_path, capsys):
+    from inferbiomechanics_b200.cli.abstract_command import AbstractCommand
+    sig = inspect.signature(AbstractCommand.get_model)
+    assert list(sig.parameters)[1:] == ["num_dofs", "num_contact_bodies", "model_type", "history_len", "stride", "hidden_dims",
+                                        "activation", "batchnorm", "dropout", "dropout_prob", "root_history_len",
+                                        "output_data_format", "device"]
+    cmd = AbstractCommand()
+    with pytest.raises(ValueError):
+        cmd.get_model(23, 2, "analytical")
+    # latest-checkpoint rule (epoch, batch) and the DDP `module.` prefix (train.py:276) on a plain torch module
+    model = torch.nn.Linear(3, 2)
+    d = tmp_path / "ck"
+    assert cmd.load_latest_checkpoint(model, checkpoint_dir=str(d)) == (-1, 0)
+    os.makedirs(d)
+    assert cmd.load_latest_checkpoint(model, checkpoint_dir=str(d)) == (-1, 0)
+    for e, b, val in ((0, 999, 1.0), (2, 5, 3.0), (1, 2000, 2.0)):
+        sd = {"module." + k: torch.full_like(v, val) for k, v in model.state_dict().items()}
+        torch.save({"epoch": e, "model_state_dict": sd, "optimizer_state_dict": {}}, d / f"epoch_{e}_batch_{b}.pt")
+    assert cmd.load_latest_checkpoint(model, checkpoint_dir=str(d)) == (2, 5)
+    assert float(model.weight.detach()[0, 0]) == 3.0
+    assert "Loaded checkpoint from epoch 2, batch 5" in capsys.readouterr().out
