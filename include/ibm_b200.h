@@ -258,6 +258,13 @@ int ibm_optimizer_step(int32_t kind, float* param, const float* grad, float* sta
                        void* param_bf16, int64_t n, float lr, float grad_scale, int64_t step,
                        void* stream);
 
+/* ---- diagnostics ---------------------------------------------------------------------------- */
+
+/* How many thread-block clusters of `cluster_size` CTAs of the 256 x 256 GEMM kernel can be resident at once
+ * (cudaOccupancyMaxActiveClusters).  On B200: 74 pairs, 33 quads, 15 octets — why the GEMM uses CTA pairs and
+ * two-tile work items rather than larger multicast clusters.  Returns -1 on error. */
+int ibm_debug_gemm_max_clusters(int32_t cluster_size);
+
 #ifdef __cplusplus
 }
 #endif

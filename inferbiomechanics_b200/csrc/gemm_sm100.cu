@@ -775,8 +775,11 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
     const char* e = getenv("IBM_GEMM_NT_MINK");
     min_k = e ? atoll(e) : 1024;
   }
+  // (small problems keep single tiles: fewer, fatter work items would leave pairs idle in the last round —
+  //  split-K launches are exempt, their split count restores the balance)
   if (cg == 2 && bn == 256 && K >= min_k && ceil_div(N, bn) % 2 == 0 && forced_nt() != 1 &&
-      (aux_mode == 0 || (out_dtype == IBM_BF16 && !accumulate)))
+      (aux_mode == 0 || (out_dtype == IBM_BF16 && !accumulate)) &&
+      (accumulate || (int64_t)args.tiles_m * (ceil_div(N, bn) / 2) >= 2 * (sm_count() / cg)))
     nt = 2;
   args.tiles_n = (int32_t)ceil_div(N, (int64_t)nt * bn);
   const int sms = sm_count();
