@@ -635,6 +635,13 @@ static int launch_bwd(const void* qkv, int64_t ld, int64_t kv_off, const void* d
 }  // namespace attn
 }  // namespace ibm
 
+namespace ibm {
+int attention_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                     int64_t n_win, int T, int H, int head_dim, float scale, cudaStream_t s);        // attention_tc.cu
+int attention_bwd_tc(const void* qkv, int64_t ld, int64_t kv_off, const void* d_o, int64_t ldo, void* dqkv, int64_t n_win, int T, int H,
+                     int head_dim, float scale, float* dbias, cudaStream_t s);      // attention_tc.cu
+}
+
 extern "C" int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                                  int64_t ldo, int64_t n_win, int32_t T, int32_t H, int32_t hd_qk, int32_t hd_v, float scale,
                                  void* stream) {
@@ -645,7 +652,19 @@ extern "C" int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int6
   IBM_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0 && aligned16(q) && aligned16(k) && aligned16(v),
                 "attention_fwd: leading dimensions must be multiples of 8 and pointers 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // short windows (the denoiser's T = 50): persistent, double-buffered kernel
+  // short windows, 64-wide heads (the denoiser): tcgen05 kernel; IBM_ATTN_FWD=mma keeps the mma.sync kernel (A/B measurements)
+  if (T <= 64 && hd_qk == 64 && hd_v == 64 && ldo % 8 == 0 && aligned16(o)) {
+    static int use_tc = -1;
+    if (use_tc < 0) {
+      const char* e = getenv("IBM_ATTN_FWD");
+      use_tc = (e && e[0] == 'm') ? 0 : 1;
+    }
+    if (use_tc) {
+      const int rc = attention_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, hd_qk, scale, s);
+      if (rc != IBM_E_UNSUPPORTED) return rc;
+    }
+  }
+  // short windows (T <= 64), other head sizes: persistent, double-buffered mma.sync kernel
   if (T <= 64 && hd_qk == hd_v && ldo % 8 == 0 && aligned16(o)) {
     if (hd_qk == 64) return attn::launch_fwd_pipe<64>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
     if (hd_qk == 48) return attn::launch_fwd_pipe<48>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
@@ -657,11 +676,6 @@ extern "C" int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int6
   if (hd_qk == 112 && hd_v == 8) return attn::launch_fwd<112, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
   set_error("attention_fwd: unsupported head dims (%d, %d); supported (64,64) (48,48) (32,32) (112,8)", hd_qk, hd_v);
   return IBM_E_UNSUPPORTED;
-}
-
-namespace ibm {
-int attention_bwd_tc(const void* qkv, int64_t ld, int64_t kv_off, const void* d_o, int64_t ldo, void* dqkv, int64_t n_win, int T, int H,
-                     int head_dim, float scale, float* dbias, cudaStream_t s);      // attention_tc.cu
 }
 
 extern "C" int ibm_attention_bwd(const void* qkv, int64_t ld_qkv, int64_t kv_off, const void* d_o, int64_t ld_o, void* dqkv,

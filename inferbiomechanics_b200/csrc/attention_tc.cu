@@ -473,7 +473,281 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   }
 }
 
+// ------------------------------------------------ forward -----------------------------------------------------------
+// Same construction as the backward: two windows of one head = one 128-row problem, S = Q K^T (128 x 128 x 64) and
+// O = P V (128 x 64 x 128) on tcgen05 with P written block-diagonal (shared zero half), softmax by four threads per row,
+// 16 compute warps + 4 issuing warps (loader | S | O | storer), software-pipelined over the (pair, head) items of a CTA.
+constexpr int kFwdControlWarps = 4;
+constexpr int kFwdThreads = kComputeThreads + 32 * kFwdControlWarps;
+// 2 stages x {Q, K, V} + P + O staging + exchange (max, sum) + barriers
+constexpr int kFwdSmem = 1024 + 2 * 3 * kTile + kPD + kTile + 2 * 128 * 4 * 4 + 256;
+constexpr uint32_t kColFS = 0, kColFO = 128;
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int T, int H, int64_t n_win,
+                   float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // stage st: Q | K | V at smem + st * 3 * kTile
+  uint8_t* Ps = smem + 6 * kTile;                     // [P_a | shared zero block | P_b]
+  uint8_t* Go = Ps + kPD;                             // O staging tile
+  float* xch = reinterpret_cast<float*>(Go + kTile);  // [2][128 rows][4 quarters]: row max, row sum
+  uint64_t* qk_bar = reinterpret_cast<uint64_t*>(xch + 2 * 128 * 4);   // [2] Q, K of a stage landed
+  uint64_t* v_bar = qk_bar + 2;                       // [2] V of a stage landed
+  uint64_t* s_bar = v_bar + 2;                        // S complete
+  uint64_t* sc_bar = s_bar + 1;                       // S copied to registers
+  uint64_t* pd_bar = sc_bar + 1;                      // P in shared memory, previous O in registers
+  uint64_t* o_bar = pd_bar + 1;                       // O complete
+  uint64_t* stg_bar = o_bar + 1;                      // O staged
+  uint64_t* sf_bar = stg_bar + 1;                     // staging tile free again
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sf_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_pairs = (n_win + 1) >> 1;
+  const int64_t n_items = n_pairs * H;                // item = pair * H + head
+  const int n_it = blockIdx.x < n_items ? (int)((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+  for (int i = tid; i < (6 * kTile + kPD + kTile) / 16; i += kFwdThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmO);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qk_bar[i], 1); mbar_init(&v_bar[i], 1); }
+    mbar_init(s_bar, 1);
+    mbar_init(sc_bar, kComputeThreads / 32);
+    mbar_init(pd_bar, kComputeThreads / 32);
+    mbar_init(o_bar, 1);
+    mbar_init(stg_bar, kComputeThreads / 32);
+    mbar_init(sf_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto item_pair = [&](int i) { return ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) / H; };
+  auto item_head = [&](int i) { return (int)(((int64_t)blockIdx.x + (int64_t)i * gridDim.x) % H); };
+
+  if (warp >= kComputeThreads / 32) {
+    const int role = warp - kComputeThreads / 32;     // 0 loader, 1 S, 2 O, 3 storer
+    if (lane == 0 && n_it > 0) {
+      auto window_row = [&](int i, int it) {
+        int64_t w = 2 * item_pair(i) + it;
+        if (w >= n_win) w = n_win - 1;
+        return (int32_t)(w * T);
+      };
+      constexpr uint64_t kTileStep = kTile >> 4, kStageStep = (3 * kTile) >> 4, kChunkStep = kChunk >> 4;
+      if (role == 0) {
+        const uint32_t tx_qk = 4u * (uint32_t)T * 128u, tx_v = 2u * (uint32_t)T * 128u;
+        auto load_qk = [&](int i) {
+          uint8_t* base = smem + (i & 1) * 3 * kTile;
+          const int h = item_head(i);
+          mbar_arrive_expect_tx(&qk_bar[i & 1], tx_qk);
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int32_t row0 = window_row(i, it);
+            tma_load_2d(base + it * 64 * 128, &tmQ, &qk_bar[i & 1], h * HD, row0);
+            tma_load_2d(base + kTile + it * 64 * 128, &tmK, &qk_bar[i & 1], h * HD, row0);
+          }
+        };
+        auto load_v = [&](int i) {
+          uint8_t* base = smem + (i & 1) * 3 * kTile + 2 * kTile;
+          const int h = item_head(i);
+          mbar_arrive_expect_tx(&v_bar[i & 1], tx_v);
+#pragma unroll
+          for (int it = 0; it < 2; ++it) tma_load_2d(base + it * 64 * 128, &tmV, &v_bar[i & 1], h * HD, window_row(i, it));
+        };
+        auto prefetch_item = [&](int i) {
+          const int h = item_head(i);
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int32_t row0 = window_row(i, it);
+            tma_prefetch_l2_2d(&tmQ, h * HD, row0);
+            tma_prefetch_l2_2d(&tmK, h * HD, row0);
+            tma_prefetch_l2_2d(&tmV, h * HD, row0);
+          }
+        };
+        constexpr int kAhead = 4;
+        load_qk(0); load_v(0);
+        if (n_it > 1) { load_qk(1); load_v(1); }
+        for (int i = 2; i < kAhead && i < n_it; ++i) prefetch_item(i);
+        for (int i = 0; i < n_it; ++i) {
+          if (i + kAhead < n_it) prefetch_item(i + kAhead);
+          if (i + 2 < n_it) {
+            // the stage of item i is free once O(i) is complete (its scores finished long before).  Only o_bar is waited
+            // on: the loader sits on it before it can complete, whereas S may run two items ahead of a late waiter and
+            // a parity wait would then miss its phase
+            mbar_wait(o_bar, (uint32_t)(i & 1));
+            load_qk(i + 2);
+            load_v(i + 2);
+          }
+        }
+      } else if (role == 1) {
+        // ---- S(i) = Q K^T: issued as soon as S(i-1) has been copied out of TMEM ----
+        const uint64_t dK_Q0 = make_smem_desc_sw128(smem_u32(smem), 0, 1024);
+        const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+        for (int i = 0; i < n_it; ++i) {
+          mbar_wait(&qk_bar[i & 1], (uint32_t)((i >> 1) & 1));
+          if (i > 0) mbar_wait(sc_bar, (uint32_t)((i - 1) & 1));
+          tc_fence_after();
+          const uint64_t q = dK_Q0 + (i & 1) * kStageStep;
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + kColFS, q + 2 * k, q + kTileStep + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(s_bar);
+        }
+      } else if (role == 2) {
+        // ---- O(i) = P V: A = P K-major (K = 128 keys = two chunks 8 KB apart), B = V MN-major ----
+        const uint64_t dK_P = make_smem_desc_sw128(smem_u32(Ps), 0, 1024);
+        const uint64_t dM_V0 = make_smem_desc_sw128(smem_u32(smem + 2 * kTile), kTile, 1024);
+        const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+        for (int i = 0; i < n_it; ++i) {
+          mbar_wait(&v_bar[i & 1], (uint32_t)((i >> 1) & 1));
+          mbar_wait(pd_bar, (uint32_t)(i & 1));       // P(i) written, O(i-1) in registers
+          tc_fence_after();
+          const uint64_t vm = dM_V0 + (i & 1) * kStageStep;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem_base + kColFO, dK_P + (k >> 2) * kChunkStep + (k & 3) * 2, vm + 128 * k, idesc_o, k > 0 ? 1u : 0u);
+          umma_commit(o_bar);
+        }
+      } else {
+        // ---- storer ----
+        for (int i = 0; i < n_it; ++i) {
+          mbar_wait(stg_bar, (uint32_t)(i & 1));
+          const int h = item_head(i);
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int64_t w = 2 * item_pair(i) + it;
+            if (w >= n_win) break;
+            tma_store_2d(&tmO, Go + it * 64 * 128, h * HD, (int32_t)(w * T));
+          }
+          tma_commit_group();
+          tma_wait_group_read<0>();
+          mbar_arrive(sf_bar);
+        }
+        tma_wait_group<0>();
+      }
+    }
+  } else {
+    const int q = warp & 3, cq4 = warp >> 2;
+    const int r = q * 32 + lane, ri = r & 63, own = r >> 6, rsw = r & 7;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float scale_log2 = scale * 1.4426950408889634f;
+    const uint32_t xrow = smem_u32(xch) + r * 16;
+    const uint32_t prow = smem_u32(Ps) + own * kChunk + r * 128;
+    const uint32_t po0 = (uint32_t)(((cq4 * 2) ^ rsw) << 4), po1 = (uint32_t)(((cq4 * 2 + 1) ^ rsw) << 4);
+    auto stage_o = [&](int i, const float (&vo)[16]) {
+      if (i > 0) mbar_wait(sf_bar, (uint32_t)((i - 1) & 1));
+      if (ri < T) {
+        const uint32_t ro = smem_u32(Go) + r * 128;
+        sts16(ro + po0, make_uint4(pack_bf16x2(vo[0], vo[1]), pack_bf16x2(vo[2], vo[3]), pack_bf16x2(vo[4], vo[5]), pack_bf16x2(vo[6], vo[7])));
+        sts16(ro + po1, make_uint4(pack_bf16x2(vo[8], vo[9]), pack_bf16x2(vo[10], vo[11]), pack_bf16x2(vo[12], vo[13]), pack_bf16x2(vo[14], vo[15])));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stg_bar);
+    };
+    for (int i = 0; i < n_it; ++i) {
+      mbar_wait(s_bar, (uint32_t)(i & 1));
+      tc_fence_after();
+      float s[16];
+      tmem_ld_x16(lane_base + kColFS + own * 64 + cq4 * 16, s);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sc_bar);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (cq4 * 16 + j >= T) s[j] = -INFINITY;
+        mx = fmaxf(mx, s[j]);
+      }
+      const float off = mx == -INFINITY ? 0.f : mx * scale_log2;
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        s[j] = ex2(fmaf(s[j], scale_log2, -off));
+        l += s[j];
+      }
+      sts_f(xrow + cq4 * 4, mx);
+      sts_f(xrow + 2048 + cq4 * 4, l);
+      named_bar_sync(1 + q, 128);
+      float pscale;
+      {
+        const float4 m4 = lds_f4(xrow), l4 = lds_f4(xrow + 2048);
+        const float Ml = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w)) * scale_log2;
+        const float f0 = ex2(fmaf(m4.x, scale_log2, -Ml)), f1 = ex2(fmaf(m4.y, scale_log2, -Ml));
+        const float f2 = ex2(fmaf(m4.z, scale_log2, -Ml)), f3 = ex2(fmaf(m4.w, scale_log2, -Ml));
+        l = fmaf(l4.x, f0, fmaf(l4.y, f1, fmaf(l4.z, f2, l4.w * f3)));
+        pscale = (ri < T ? 1.f / l : 0.f) * (cq4 == 0 ? f0 : (cq4 == 1 ? f1 : (cq4 == 2 ? f2 : f3)));
+      }
+      uint32_t pw[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pw[e] = pack_bf16x2(s[2 * e] * pscale, s[2 * e + 1] * pscale);
+      float vo[16];
+      if (i > 0) {
+        mbar_wait(o_bar, (uint32_t)((i - 1) & 1));    // O(i-1) complete: fetch it; P tile is free
+        tc_fence_after();
+        tmem_ld_x16(lane_base + kColFO + cq4 * 16, vo);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      sts16(prow + po0, make_uint4(pw[0], pw[1], pw[2], pw[3]));
+      sts16(prow + po1, make_uint4(pw[4], pw[5], pw[6], pw[7]));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pd_bar);
+      if (i > 0) stage_o(i - 1, vo);
+      // the exchange slots are rewritten in the next iteration only after every partner has passed this iteration's
+      // named barrier and (through sc_bar -> s_bar) read them
+    }
+    if (n_it > 0) {
+      float vo[16];
+      mbar_wait(o_bar, (uint32_t)((n_it - 1) & 1));
+      tc_fence_after();
+      tmem_ld_x16(lane_base + kColFO + cq4 * 16, vo);
+      tmem_ld_wait();
+      tc_fence_before();
+      stage_o(n_it - 1, vo);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 }  // namespace attn_tc
+
+int attention_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                     int64_t n_win, int T, int H, int head_dim, float scale, cudaStream_t s) {
+  using namespace attn_tc;
+  if (head_dim != HD || T > 64 || T < 1 || scale <= 0.f || n_win * T >= (1ll << 31)) return IBM_E_UNSUPPORTED;
+  const int64_t rows = n_win * T, cols = (int64_t)H * HD;
+  CUtensorMap mq, mk, mv, mo;
+  int rc = make_map(&mq, q, false, cols, rows, ldq, 64, (uint32_t)T);
+  if (rc) return rc;
+  rc = make_map(&mk, k, false, cols, rows, ldk, 64, (uint32_t)T);
+  if (rc) return rc;
+  rc = make_map(&mv, v, false, cols, rows, ldv, 64, (uint32_t)T);
+  if (rc) return rc;
+  rc = make_map(&mo, o, false, cols, rows, ldo, 64, (uint32_t)T);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+    attr_set = true;
+  }
+  const int64_t n_items = (n_win + 1) / 2 * H;
+  const int64_t grid = n_items < sm_count() ? n_items : sm_count();
+  attn_fwd_tc_kernel<<<(unsigned)grid, kFwdThreads, kFwdSmem, s>>>(mq, mk, mv, mo, T, H, n_win, scale);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
 
 // returns IBM_E_UNSUPPORTED when the shape is outside this kernel's domain (the caller falls back to mma.sync)
 int attention_bwd_tc(const void* qkv, int64_t ld, int64_t kv_off, const void* d_o, int64_t ldo, void* dqkv, int64_t n_win, int T, int H,
