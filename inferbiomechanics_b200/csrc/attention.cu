@@ -652,12 +652,14 @@ extern "C" int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int6
   IBM_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0 && aligned16(q) && aligned16(k) && aligned16(v),
                 "attention_fwd: leading dimensions must be multiples of 8 and pointers 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // short windows, 64-wide heads (the denoiser): tcgen05 kernel; IBM_ATTN_FWD=mma keeps the mma.sync kernel (A/B measurements)
+  // short windows, 64-wide heads (the denoiser): a tcgen05 forward kernel exists (attention_tc.cu, same construction as the
+  // backward) and is parity-tested, but with half the work per window pair its per-pair latency chain leaves it at
+  // 182 us vs 171 us for the mma.sync pipeline below, so it is opt-in: IBM_ATTN_FWD=tc
   if (T <= 64 && hd_qk == 64 && hd_v == 64 && ldo % 8 == 0 && aligned16(o)) {
     static int use_tc = -1;
     if (use_tc < 0) {
       const char* e = getenv("IBM_ATTN_FWD");
-      use_tc = (e && e[0] == 'm') ? 0 : 1;
+      use_tc = (e && e[0] == 't') ? 1 : 0;
     }
     if (use_tc) {
       const int rc = attention_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, hd_qk, scale, s);

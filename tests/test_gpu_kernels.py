@@ -266,6 +266,29 @@ def test_attention_forward(n_win, T, H, hd):
     assert (o.double().cpu() - ref).abs().max().item() <= 2.5e-2
 
 
+def test_attention_forward_tcgen05_variant():
+    """The opt-in tcgen05 forward (IBM_ATTN_FWD=tc, read once per process) against the same fp64 reference, in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, math, sys; sys.path.insert(0, '.');"
+        "from inferbiomechanics_b200 import ops;"
+        "n_win, T, H, hd = 701, 50, 8, 64; d = H * hd;"
+        "g = torch.Generator().manual_seed(5);"
+        "qkv = torch.randn(n_win * T, 3 * d, generator=g).to(torch.bfloat16);"
+        "o = torch.zeros(n_win * T, d, dtype=torch.bfloat16, device='cuda');"
+        "ops.attention_fwd_fused(qkv.cuda(), d, o, n_win, T, H, hd, 1.0 / math.sqrt(hd));"
+        "x = qkv.double().view(n_win, T, 3, H, hd).permute(2, 0, 3, 1, 4);"
+        "s = (x[0] @ x[1].transpose(-2, -1)) / math.sqrt(hd);"
+        "ref = (torch.softmax(s, -1) @ x[2]).permute(0, 2, 1, 3).reshape(n_win * T, d);"
+        "print((o.double().cpu() - ref).abs().max().item())")
+    env = dict(os.environ, IBM_ATTN_FWD="tc")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert r.returncode == 0, r.stderr[-800:]
+    assert float(r.stdout.split()[-1]) <= 2.5e-2
+
+
 @pytest.mark.parametrize("n_win,T,H,hd", [(3, 50, 8, 64), (2, 64, 2, 64), (5, 10, 4, 32), (2, 33, 3, 48), (700, 50, 8, 64),
                                           (1500, 17, 4, 32)])
 def test_attention_backward(n_win, T, H, hd):
