@@ -182,6 +182,10 @@ def main():
         run_reference_arm(args)
         return
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's "NCCL version ..." banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -279,7 +283,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg()
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
