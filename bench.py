@@ -262,8 +262,20 @@ def main():
     gemm_ms, gemm_flops, n_gemm = trainer.profile_gemms(store, batches[0])
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    # DRAM traffic of the dominant kernel: ncu --set full captures of its four big shapes (48 of the 106 launches, ~75 % of
+    # the GEMM time), committed under profiles/; per launch, like `achieved`
+    traffic, traffic_detail = None, None
+    tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        per = {k: v["dram_read"] + v["dram_write"] for k, v in tj["shapes"].items()}
+        traffic = sum(per.values()) / len(per)
+        traffic_detail = {"source": tj["_source"], "round": tj["_round"], "per_shape_dram_bytes": per,
+                          "per_shape_operand_bytes": {k: v["operand_bytes"] for k, v in tj["shapes"].items()},
+                          "note": "traffic = mean over the four captured shapes; DRAM bytes are 0.95-1.12x the operand bytes (each operand "
+                                  "crosses HBM once; part of the output stays in the 126 MB L2 for the consumer)"}
     roofline = {"bound": "tensor", "kernel": "ibm::gemm::gemm_kernel (tcgen05.mma + TMA, all shapes of one training step)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_detail": traffic_detail,
                 "peak_source": pk["_source"] + ", sustained figure (kernel timed inside a long step)",
                 "launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms_per_step,
                 "step_model_flops_per_window": 3 * 2.57e9}
@@ -280,6 +292,13 @@ def main():
         out["clocks"] = clock_info
     if not args.no_aux:
         out["aux"] = trainer.aux_measurements(store, batches[0], pk, world)
+        # the other BASELINE configs (not the headline metric): configs[0] model on the GPU, Groundlink, configs[4] stream
+        from inferbiomechanics_b200 import bench_legs
+        del trainer, store
+        torch.cuda.empty_cache()
+        out["aux"]["feedforward_train"] = bench_legs.feedforward_train_leg(dev, world)
+        out["aux"]["groundlink_train"] = bench_legs.groundlink_train_leg(dev, world)
+        out["aux"]["transformer_analyze"] = bench_legs.transformer_analyze_leg(dev, world, pk)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg()
     if rank == 0:

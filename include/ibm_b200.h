@@ -215,6 +215,31 @@ int ibm_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed, 
 int ibm_conv_weight_to_dgrad(const float* w, int32_t cout, int32_t cin, int32_t kt, int32_t cout_pad,
                              void* dst_bf16, void* stream);
 
+/* ---- BatchNorm1d on the layer input  (src/models/FeedForwardRegressionBaseline.py:71-72; nn.BatchNorm1d defaults
+ *      eps=1e-5, momentum=0.1, affine, track_running_stats) ---- */
+
+/* floats of caller-owned scratch the two BatchNorm entry points need for C features */
+size_t ibm_batchnorm_workspace_floats(int32_t C);
+/* y = (x - mean) / sqrt(var + eps) * gamma + beta per column.  x,y bf16 [M, ld] (ld %% 8 == 0; columns C..ld of y are
+ * written 0); gamma/beta fp32[C].  training != 0: mean / biased variance of THIS batch (two-pass per row chunk, chunks
+ * merged with Chan's update), saved as save_mean / save_rstd fp32[C] for the backward pass; running_mean / running_var
+ * (fp32[C], may be NULL) are updated in place with `momentum` and the UNBIASED batch variance; M == 1 is an argument
+ * error like torch's ValueError.  training == 0: normalises with running_mean / running_var; save_* and workspace unused. */
+int ibm_batchnorm_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, int32_t C, const float* gamma,
+                      const float* beta, float* running_mean, float* running_var, float* save_mean, float* save_rstd,
+                      int32_t training, float momentum, float eps, float* workspace, void* stream);
+/* Backward of the above.  dgamma[c] += sum_m dy*xhat, dbeta[c] += sum_m dy (either may be NULL);
+ * dx = gamma*rstd*(dy - mean_m(dy) - xhat*mean_m(dy*xhat)) in training mode, gamma*rstd*dy in eval mode (dx may be NULL
+ * when only the parameter gradients are wanted, may alias dy).  (mean, rstd_or_var) = (save_mean, save_rstd) when
+ * training, (running_mean, running_var) otherwise.  act_out != NULL: dx is additionally multiplied by act'(.) expressed
+ * through the saved activation OUTPUT act_out (the activation that produced x's layer input; relu/sigmoid/tanh/elu).
+ * dx_colsum (fp32[C], may be NULL): += column sums of dx taken in fp32 before the bf16 rounding — the bias gradient of
+ * the Linear that feeds this BatchNorm (a sum of cancelling terms in training mode). */
+int ibm_batchnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, void* dx, int64_t lddx, int64_t M,
+                      int32_t C, const float* gamma, const float* mean, const float* rstd_or_var, int32_t training,
+                      float eps, const void* act_out, int64_t ldact, int32_t act, float* dgamma, float* dbeta,
+                      float* dx_colsum, float* workspace, void* stream);
+
 /* ---- residual + LayerNorm  (src/models/TransformerBaseline.py:31,36; nn.LayerNorm eps=1e-5) ---- */
 
 /* y = LN(s) * gamma + beta over the first d columns of each row (columns d..ld are written 0).

@@ -46,6 +46,8 @@ SIGNATURES = {
     "ibm_fold_pad_rows": [P, _i64, _i64, _i32, _i32, _i32, P],
     "ibm_dropout_bf16": [P, P, _i64, _f, _u64, _u64, P],
     "ibm_conv_weight_to_dgrad": [P, _i32, _i32, _i32, _i32, P, P],
+    "ibm_batchnorm_fwd": [P, _i64, P, _i64, _i64, _i32, P, P, P, P, P, P, _i32, _f, _f, P, P],
+    "ibm_batchnorm_bwd": [P, _i64, P, _i64, P, _i64, _i64, _i32, P, P, P, _i32, _f, P, _i64, _i32, P, P, P, P, P],
     "ibm_layernorm_fwd": [P, P, _i64, P, P, _i64, _i32, _f, P, P, P],
     "ibm_layernorm_bwd": [P, P, _i64, P, P, P, _i64, _i32, P, P, P, P, P],
     "ibm_attention_fwd": [P, _i64, P, _i64, P, _i64, P, _i64, _i64, _i32, _i32, _i32, _i32, _f, P],
@@ -58,6 +60,7 @@ _SPECIAL = {
     "ibm_version": ([], c_int32),
     "ibm_last_error": ([c_char_p, c_size_t], c_size_t),
     "ibm_workspace_bytes": ([], c_size_t),
+    "ibm_batchnorm_workspace_floats": ([c_int32], c_size_t),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))
 

@@ -52,9 +52,15 @@ class _Buffers:
 # FeedForward MLP
 # =============================================================================================
 class FeedForwardEngine:
-    """dims = [K0, h1, …, N_out]; every layer y = act(x W^T + b) except the last (no act, fp32 out)."""
+    """dims = [K0, h1, …, N_out]; every layer y = act(x W^T + b) except the last (no act, fp32 out).
 
-    def __init__(self, arena: ParamArena, layers: List[Tuple[str, str, int, int]], activation: str):
+    Optional per-layer ``[Dropout][BatchNorm1d]`` on the layer INPUT (FeedForward…py:68-72): ``bn`` is a list with one
+    entry per Linear (``None`` or ``(weight name, bias name, nn.BatchNorm1d module)`` — the module only holds the
+    running-statistics buffers and eps/momentum), ``dropout_p`` the probability of the Philox inverted dropout."""
+
+    DROPOUT_SEED = 0x66666e6e
+
+    def __init__(self, arena: ParamArena, layers: List[Tuple[str, str, int, int]], activation: str, bn=None, dropout_p: float = 0.0):
         self.arena = arena
         self.layers = layers                    # (weight name, bias name, N, K)
         self.act = activation
@@ -63,6 +69,14 @@ class FeedForwardEngine:
         self.out_cols = layers[-1][2]
         self.in_cols = layers[0][3]
         self.in_ld = _r8(self.in_cols)
+        self.bn = bn if bn is not None and any(b is not None for b in bn) else None
+        self.dropout_p = float(dropout_p)
+        self.step = 0                           # Philox offset base: one fresh mask per (training forward, layer)
+        if self.bn is not None:
+            maxc = max(K for (_, _, _, K) in layers)
+            self.bn_ws = ops.batchnorm_workspace(maxc, arena.device)
+            self.bn_stats = {i: (torch.zeros(K, device=arena.device), torch.ones(K, device=arena.device))
+                             for i, (_, _, _, K) in enumerate(layers) if self.bn[i] is not None}
 
     def input_buffer(self, B: int) -> torch.Tensor:
         s = self.buf.get((B,))
@@ -72,15 +86,36 @@ class FeedForwardEngine:
         s = self.buf.get((B,))
         return self.buf.tensor(s, "dout", (B, _r8(self.out_cols)), BF16, zero=True)
 
-    def forward(self, B: int) -> torch.Tensor:
-        """Consumes input_buffer(B); returns fp32 [B, ld>=N_out] (first N_out columns valid)."""
+    def forward(self, B: int, train: bool = False) -> torch.Tensor:
+        """Consumes input_buffer(B); returns fp32 [B, ld>=N_out] (first N_out columns valid).  ``train`` selects batch
+        statistics (and updates the running ones) for BatchNorm and switches dropout on, like nn.Module.training."""
         s = self.buf.get((B,))
         x = self.input_buffer(B)
         n_layers = len(self.layers)
+        drop = train and self.dropout_p > 0.0
+        if train:
+            self.step += 1
+        s["mode"] = (train, drop)
         for i, (wn, bn, N, K) in enumerate(self.layers):
             W = self.arena.weight_operand(wn, N, K)
             bias = self.arena.master_of(bn)
             last = i == n_layers - 1
+            if drop:                                                    # nn.Dropout(p) on the layer input
+                xd = self.buf.tensor(s, f"xd{i}", tuple(x.shape), BF16)
+                ops.dropout(x, xd, self.dropout_p, self.DROPOUT_SEED, n_layers * self.step + i)
+                x = xd
+            if self.bn is not None and self.bn[i] is not None:          # nn.BatchNorm1d(h0) on the (dropped) input
+                gname, bname, mod = self.bn[i]
+                xb = self.buf.tensor(s, f"xb{i}", tuple(x.shape), BF16, zero=True)
+                mean, rstd = self.bn_stats[i]
+                mom = 0.1 if mod.momentum is None else float(mod.momentum)
+                ops.batchnorm_fwd(x, xb, B, K, self.arena.master_of(gname), self.arena.master_of(bname), mod.running_mean,
+                                  mod.running_var, mean, rstd, train, mom, float(mod.eps), self.bn_ws)
+                if train:
+                    mod.num_batches_tracked += 1
+                s[f"prebn{i}"] = x
+                x = xb
+            s[f"in{i}"] = x                                             # what the GEMM consumed (weight-gradient operand)
             if last:
                 y = self.buf.tensor(s, "out", (B, ops.round_up(N, 4)), F32)
                 ops.gemm(x, W, y, B, N, K, bias=bias)
@@ -94,17 +129,36 @@ class FeedForwardEngine:
         """Consumes dout_buffer(B) (bf16 d loss/d out); accumulates weight/bias grads into the arena."""
         arena = accumulate_into or self.arena
         s = self.buf.get((B,))
+        train, drop = s.get("mode", (False, False))
         dy = self.dout_buffer(B)
-        for i in range(len(self.layers) - 1, -1, -1):
+        n_layers = len(self.layers)
+        bias_done = False                       # layer i's bias gradient already produced by BatchNorm i+1's backward
+        for i in range(n_layers - 1, -1, -1):
             wn, bn, N, K = self.layers[i]
-            x = self.input_buffer(B) if i == 0 else s[f"a{i - 1}"]
+            x = s[f"in{i}"]
+            has_bn = self.bn is not None and self.bn[i] is not None
             _wgrad(arena, wn, N, K, dy, x, B, self.buf, s)
-            ops.colsum(dy, B, N, arena.grad_of(bn))
-            if i > 0:
+            if not bias_done:
+                ops.colsum(dy, B, N, arena.grad_of(bn))
+            bias_done = False
+            if i > 0 or has_bn:
                 W = self.arena.weight_operand(wn, N, K)
-                dx = self.buf.tensor(s, f"da{i - 1}", (B, _r8(K)), BF16, zero=True)
-                # dX = (dY · W) ∘ act'(x): W [N,K] row-major is the MN-major B operand [K_red=N, N_out=K]
-                ops.gemm(dy, W, dx, B, K, N, b_mn=True, act=self.act, aux=x, aux_mode=2)
+                dx = self.buf.tensor(s, f"da{i - 1}" if i > 0 else "dx0", (B, _r8(K)), BF16, zero=True)
+                prev = s[f"a{i - 1}"] if i > 0 else None             # activation OUTPUT of layer i-1 (its derivative gate)
+                if not has_bn:
+                    # dX = (dY · W) ∘ act'(x): W [N,K] row-major is the MN-major B operand [K_red=N, N_out=K]
+                    ops.gemm(dy, W, dx, B, K, N, b_mn=True, act=self.act, aux=prev, aux_mode=2)
+                else:
+                    gname, bname, mod = self.bn[i]
+                    ops.gemm(dy, W, dx, B, K, N, b_mn=True)
+                    mean, rstd = self.bn_stats[i] if train else (mod.running_mean, mod.running_var)
+                    ops.batchnorm_bwd(dx, s[f"prebn{i}"], dx if i > 0 else None, B, K, self.arena.master_of(gname), mean, rstd,
+                                      train, float(mod.eps), arena.grad_of(gname), arena.grad_of(bname), self.bn_ws,
+                                      act_out=prev, act=self.act if prev is not None else None,
+                                      dx_colsum=arena.grad_of(self.layers[i - 1][1]) if i > 0 and not drop else None)
+                    bias_done = i > 0 and not drop   # fp32 column sums of dx = bias gradient of layer i-1 (no mask in between)
+                if drop and i > 0:                                      # same Philox (seed, offset) as the forward mask
+                    ops.dropout(dx, dx, self.dropout_p, self.DROPOUT_SEED, n_layers * self.step + i)
                 dy = dx
             if self.bucket_hook is not None:
                 self.bucket_hook(i)               # layer i's gradients are complete

@@ -29,7 +29,7 @@ class _FeedForwardFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, B, *params):
         eng = model.engine()
-        out = eng.forward(B)
+        out = eng.forward(B, train=model.training)
         ctx.model, ctx.B = model, B
         return out[:, :eng.out_cols].clone()
 
@@ -95,10 +95,12 @@ class FeedForwardBaseline(EngineModule):
         net = []
         dims = [self.input_size] + list(hidden_dims) + [self.output_size]
         self._linear_pos = []
+        self._bn_pos = []
         for i, (h0, h1) in enumerate(zip(dims[:-1], dims[1:])):
             if dropout:
                 net.append(nn.Dropout(dropout_prob))
             if batchnorm:
+                self._bn_pos.append(len(net))
                 net.append(nn.BatchNorm1d(h0))
             self._linear_pos.append((len(net), h1, h0))
             net.append(nn.Linear(h0, h1, dtype=torch.float32, device=device if device != 'cpu' else None))
@@ -109,13 +111,10 @@ class FeedForwardBaseline(EngineModule):
 
     def _build_engine(self, arena):
         layers = [(f"net.{pos}.weight", f"net.{pos}.bias", n, k) for pos, n, k in self._linear_pos]
-        return FeedForwardEngine(arena, layers, self.activation)
-
-    def _check_modes(self):
-        if self.batchnorm:
-            raise NotImplementedError("--batchnorm is not implemented on the B200 path yet (reference default is off, train.py:47)")
-        if self.dropout and self.training and self.dropout_prob > 0.0:
-            raise NotImplementedError("training-mode dropout is not implemented on the B200 path yet (reference default is off)")
+        # [Dropout][BatchNorm1d] sit on each Linear's input (FeedForward…py:68-72): BatchNorm1d over the packed bf16 rows
+        # (ibm_batchnorm_fwd/bwd, batch statistics when self.training), Philox inverted dropout (ibm_dropout_bf16)
+        bn = [(f"net.{p}.weight", f"net.{p}.bias", self.net[p]) for p in self._bn_pos] if self.batchnorm else None
+        return FeedForwardEngine(arena, layers, self.activation, bn=bn, dropout_p=self.dropout_prob if self.dropout else 0.0)
 
     def forward(self, input: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         # 1. same shape assertions as the reference (FeedForward…py:83-94)
@@ -129,7 +128,6 @@ class FeedForwardBaseline(EngineModule):
         assert input[InputDataKeys.ROOT_POS_HISTORY_IN_ROOT_FRAME].shape[-1] == self.stride * 3
         assert len(input[InputDataKeys.ROOT_EULER_HISTORY_IN_ROOT_FRAME].shape) == 3
         assert input[InputDataKeys.ROOT_EULER_HISTORY_IN_ROOT_FRAME].shape[-1] == self.stride * 3
-        self._check_modes()
         eng = self.engine()
         B, F = input[InputDataKeys.POS].shape[0], input[InputDataKeys.POS].shape[1]
         assert F * self.frame_width == self.input_size, "window length does not match history_len // stride"

@@ -118,6 +118,23 @@ def conv_weight_to_dgrad(w: torch.Tensor, dst: torch.Tensor, cout_pad: int):
     call("ibm_conv_weight_to_dgrad", _p(w), cout, cin, kt, cout_pad, _p(dst), stream_ptr())
 
 
+# ---- BatchNorm1d -----------------------------------------------------------------------------------
+def batchnorm_workspace(C: int, device) -> torch.Tensor:
+    return torch.zeros(_lib.load().ibm_batchnorm_workspace_floats(C), dtype=torch.float32, device=device)
+
+
+def batchnorm_fwd(x, y, M, C, gamma, beta, running_mean, running_var, save_mean, save_rstd, training, momentum, eps, ws):
+    call("ibm_batchnorm_fwd", _p(x), x.stride(0), _p(y), y.stride(0), M, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+         _p(save_mean), _p(save_rstd), int(training), momentum, eps, _p(ws), stream_ptr())
+
+
+def batchnorm_bwd(dy, x, dx, M, C, gamma, mean, rstd_or_var, training, eps, dgamma, dbeta, ws, act_out=None, act=None,
+                  dx_colsum=None):
+    call("ibm_batchnorm_bwd", _p(dy), dy.stride(0), _p(x), x.stride(0), _p(dx), 0 if dx is None else dx.stride(0), M, C, _p(gamma),
+         _p(mean), _p(rstd_or_var), int(training), eps, _p(act_out), 0 if act_out is None else act_out.stride(0), ACT[act],
+         _p(dgamma), _p(dbeta), _p(dx_colsum), _p(ws), stream_ptr())
+
+
 # ---- LayerNorm ----------------------------------------------------------------------------------
 def layernorm_fwd(s, y, gamma, beta, M, d, eps=1e-5, mean=None, rstd=None, ld=None):
     call("ibm_layernorm_fwd", _p(s), _p(y), s.stride(0) if ld is None else ld, _p(gamma), _p(beta), M, d, eps, _p(mean),

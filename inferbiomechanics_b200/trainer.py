@@ -82,7 +82,8 @@ class Trainer:
         if self.is_denoiser:
             first = [offs[f"layers.{l}.multihead_attention.in_proj_weight"][0] for l in range(self.model.num_layers)]
             return [0] + first + [offs["out_proj.weight"][0]]
-        return [offs[w][0] for (w, _, _, _) in self.eng.layers]
+        bn = getattr(self.eng, "bn", None)        # a layer's BatchNorm parameters precede its Linear in the arena
+        return [offs[bn[i][0] if bn is not None and bn[i] is not None else w][0] for i, (w, _, _, _) in enumerate(self.eng.layers)]
 
     # ---- one optimisation step on windows idx of a store -------------------------------------------
     def train_step(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
@@ -97,7 +98,7 @@ class Trainer:
             gviews = _views30(self.eng.dout(B).view(B, self.eng.F, 32))
         else:
             store.pack_feedforward(idx, self.eng.input_buffer(B))
-            out = self.eng.forward(B)
+            out = self.eng.forward(B, train=True)
             Fo = self.model.num_output_frames
             outs, labs = _views_ff(out, B, Fo), _views30(lab)
             gviews = _views_ff(self.eng.dout_buffer(B), B, Fo)
@@ -303,7 +304,7 @@ def _finish_denoiser_step(self, B: int, lab: torch.Tensor) -> torch.Tensor:
 
 def _finish_ff_step(self, B: int, lab: torch.Tensor) -> torch.Tensor:
     eng = self.eng
-    out = eng.forward(B)
+    out = eng.forward(B, train=True)
     Fo = self.model.num_output_frames
     outs, labs = _views_ff(out, B, Fo), _views30(lab)
     gviews = _views_ff(eng.dout_buffer(B), B, Fo)

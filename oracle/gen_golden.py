@@ -12,6 +12,8 @@ loss_call.npz          RegressionLossEvaluator.__call__ (src/loss/RegressionLoss
 ff.npz                 FeedForwardBaseline (src/models/FeedForwardRegressionBaseline.py) forward,
                        loss and parameter gradients; sigmoid/relu/tanh; all_frames/last_frame;
                        batchnorm (eval).
+ff_bn_train.npz        FeedForwardBaseline with batchnorm=True in training mode: outputs, loss, parameter
+                       gradients and the updated running statistics after one forward.
 groundlink.npz         Groundlink (src/models/Groundlink.py) forward + loss + gradients.
 transformer.npz        TransformerLayer stack + heads composed exactly as
                        TransformerBaseline.forward (src/models/TransformerBaseline.py:104-148), fp64.
@@ -133,6 +135,40 @@ def gen_ff(ref):
     np.savez_compressed(os.path.join(OUT, "ff.npz"), **d)
 
 
+def gen_ff_bn_train(ref):
+    """FeedForwardBaseline with batchnorm=True in TRAINING mode (batch statistics, running-stat update):
+    one forward + loss + backward of the reference on seeded inputs (FeedForward…py:68-77)."""
+    d = {}
+    D, T, s = 23, 50, 5
+    for ci, (name, act, hidden, B) in enumerate([("sigmoid_b16", "sigmoid", [64, 48], 16), ("relu_b300", "relu", [96], 300)]):
+        import io, contextlib
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = ref.FeedForwardBaseline(D, 2, T, "all_frames", act, s, 10, hidden_dims=hidden, batchnorm=True)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        seed = 1500 + ci
+        m.load_state_dict(seeded_state_dict(shapes, seed))
+        m.train()
+        F = T // s
+        inputs = seeded_inputs(B, F, D, s * 3, 2500 + ci)
+        _, labels = seeded_out_labels(B, F, 3500 + ci)
+        out = m({k: v.clone() for k, v in inputs.items()})
+        ev = ref.RegressionLossEvaluator(dataset=None, split="train")
+        loss = ev(None, dict(out), {k: v.clone() for k, v in labels.items()}, [], [], ns_args(*SELECTIONS["all"]))
+        loss.backward()
+        for k, v in out.items():
+            d[f"{name}/out/{k}"] = v.detach().numpy()
+        d[f"{name}/loss"] = loss.detach().numpy()
+        grads_summary(m, d, name)
+        for k, v in m.state_dict().items():
+            if "running_" in k:
+                d[f"{name}/buffer/{k}"] = v.numpy()
+            if k.endswith("num_batches_tracked"):
+                d[f"{name}/buffer/{k}"] = np.array(int(v))
+        d[f"{name}/meta"] = np.array([D, T, s, B, seed, 2500 + ci, 3500 + ci])
+        d[f"{name}/hidden"] = np.array(hidden)
+    np.savez_compressed(os.path.join(OUT, "ff_bn_train.npz"), **d)
+
+
 def gen_groundlink(ref):
     d = {}
     D, J, H = 23, 12, 10
@@ -212,8 +248,12 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)      # deterministic reduction order for the frozen vectors
     ref = load_reference()
+    if "--only-bn-train" in __import__("sys").argv:
+        gen_ff_bn_train(ref)
+        return
     gen_loss(ref)
     gen_ff(ref)
+    gen_ff_bn_train(ref)
     gen_groundlink(ref)
     gen_transformer(ref)
     gen_denoiser_layers(ref)

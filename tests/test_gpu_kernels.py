@@ -475,3 +475,66 @@ def test_colsum_cast_act():
     ops.conv_weight_to_gemm(w.cuda(), wg, 192)
     want = torch.zeros(128, 7, 192); want[:, :, :177] = w.permute(0, 2, 1)
     assert torch.equal(wg.cpu(), want.reshape(128, -1).to(torch.bfloat16))
+
+
+# ---------------------------------------- BatchNorm1d ---------------------------------------------
+@pytest.mark.parametrize("M,C", [(6, 10), (300, 1470), (4096, 512), (70001, 147)])
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_fwd_bwd_vs_torch(M, C, training):
+    """ibm_batchnorm_fwd/bwd against torch.nn.functional.batch_norm in fp32 on the same bf16-rounded rows
+    (nn.BatchNorm1d semantics, FeedForward…py:71-72): outputs within one bf16 rounding, statistics and parameter
+    gradients rtol 2e-3 (fp32 sums over M rows in a different order), running stats with the unbiased variance.
+    M = 300 and 70001 exercise ragged last chunks and the > 64-chunk regrouping; C = 1470 / 147 / 10 odd tails."""
+    from inferbiomechanics_b200 import ops
+    g = torch.Generator().manual_seed(M + C)
+    ld = ops.round_up(C, 8)
+    x32 = (torch.randn(M, C, generator=g) * (1 + torch.arange(C) % 5) + 3.0 * torch.randn(C, generator=g)).bfloat16().float()
+    x = torch.zeros(M, ld, dtype=torch.bfloat16, device="cuda")
+    x[:, :C] = x32.cuda()
+    gamma, beta = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+    rm, rv = torch.randn(C, generator=g).cuda(), (torch.rand(C, generator=g) + 0.5).cuda()
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y = torch.full((M, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+    mean, rstd = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ws = ops.batchnorm_workspace(C, "cuda")
+    ops.batchnorm_fwd(x, y, M, C, gamma, beta, rm, rv, mean, rstd, training, 0.1, 1e-5, ws)
+    xr = x32.cuda().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = torch.nn.functional.batch_norm(xr, rm_ref, rv_ref, gr, br, training=training, momentum=0.1, eps=1e-5)
+    err = (y[:, :C].float() - yr).abs().max().item()
+    assert err <= 2 ** -7 * yr.abs().max().item() + 1e-6, err            # one bf16 rounding of the output
+    assert (y[:, C:] == 0).all()
+    if training:
+        torch.testing.assert_close(rm, rm_ref, rtol=2e-4, atol=2e-5)
+        torch.testing.assert_close(rv, rv_ref, rtol=2e-3, atol=1e-5)
+        torch.testing.assert_close(mean, x32.cuda().mean(0), rtol=2e-4, atol=2e-5)
+    else:
+        assert torch.equal(rm, rm_ref) and torch.equal(rv, rv_ref)
+    # backward
+    dy32 = torch.randn(M, C, generator=g).bfloat16().float()
+    dy = torch.zeros(M, ld, dtype=torch.bfloat16, device="cuda")
+    dy[:, :C] = dy32.cuda()
+    yr.backward(dy32.cuda())
+    dgamma, dbeta = torch.ones(C, device="cuda"), torch.ones(C, device="cuda")     # accumulate (+=) semantics
+    dx = torch.empty(M, ld, dtype=torch.bfloat16, device="cuda")
+    m_, r_ = (mean, rstd) if training else (rm, rv)
+    cs = torch.zeros(C, device="cuda")
+    ops.batchnorm_bwd(dy, x, dx, M, C, gamma, m_, r_, training, 1e-5, dgamma, dbeta, ws, dx_colsum=cs)
+    scale = xr.grad.abs().max().item()
+    # fp32 column sums of dx (upstream bias gradient): ~0 in training mode, so measure against the sum of magnitudes
+    assert ((cs - xr.grad.sum(0)).abs() <= 2e-4 * xr.grad.abs().sum(0) + 1e-6).all()
+    assert (dx[:, :C].float() - xr.grad).abs().max().item() <= 2 ** -7 * scale + 2e-3 * scale
+    torch.testing.assert_close(dgamma - 1, gr.grad, rtol=3e-3, atol=3e-3 * gr.grad.abs().max().item())
+    torch.testing.assert_close(dbeta - 1, br.grad, rtol=3e-3, atol=3e-3 * br.grad.abs().max().item())
+    # in place (dx aliases dy): same result (the column sums are atomics over row chunks, so the last bit may differ)
+    ops.batchnorm_bwd(dy, x, dy, M, C, gamma, m_, r_, training, 1e-5, None, None, ws)
+    assert (dy[:, :C].float() - dx[:, :C].float()).abs().max().item() <= 2 ** -7 * scale
+
+
+def test_batchnorm_single_row_training_is_a_value_error():
+    from inferbiomechanics_b200 import ops
+    x = torch.zeros(1, 8, dtype=torch.bfloat16, device="cuda")
+    o = torch.ones(8, device="cuda")
+    with pytest.raises(ValueError):              # torch: "Expected more than 1 value per channel when training"
+        ops.batchnorm_fwd(x, x.clone(), 1, 8, o, o, o.clone(), o.clone(), o.clone(), o.clone(), True, 0.1, 1e-5,
+                          ops.batchnorm_workspace(8, "cuda"))

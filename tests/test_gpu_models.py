@@ -50,7 +50,8 @@ def l2close(got, ref, frac, what=""):
 # ---------------------------------------------------------------------------------------------------
 # FeedForwardBaseline: same class name / ctor / forward contract as the reference
 # ---------------------------------------------------------------------------------------------------
-FF_CASES = {"sigmoid_all": ("sigmoid", "all_frames"), "relu_last": ("relu", "last_frame"), "tanh_all": ("tanh", "all_frames")}
+FF_CASES = {"sigmoid_all": ("sigmoid", "all_frames"), "relu_last": ("relu", "last_frame"), "tanh_all": ("tanh", "all_frames"),
+            "sigmoid_bn": ("sigmoid", "all_frames")}      # sigmoid_bn: batchnorm=True in eval mode (running statistics)
 
 
 @pytest.mark.parametrize("name", list(FF_CASES))
@@ -61,10 +62,11 @@ def test_feedforward_dropin_matches_reference_golden(golden, name):
     act, fmt = FF_CASES[name]
     D, T, s, B, seed, iseed, lseed = (int(v) for v in g[f"{name}/meta"])
     hidden = [int(v) for v in g[f"{name}/hidden"]]
-    m = FeedForwardBaseline(D, 2, T, fmt, act, s, 10, hidden_dims=hidden)
+    m = FeedForwardBaseline(D, 2, T, fmt, act, s, 10, hidden_dims=hidden, batchnorm=name.endswith("_bn"))
     sd = seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed)
     m.load_state_dict(sd)                                   # reference state_dict keys load unchanged
     m = m.to("cuda")
+    m.eval()                                                # the fixtures were generated in eval mode
     F = T // s
     inputs = seeded_inputs(B, F, D, s * 3, iseed)           # CPU tensors, like the reference's DataLoader yields
     _, labels = seeded_out_labels(B, F if fmt == "all_frames" else 1, lseed)
@@ -88,6 +90,102 @@ def test_feedforward_dropin_matches_reference_golden(golden, name):
     assert len(ev.force_reported_metrics) == 1 and len(ev.losses) == 1
     ev.print_report(ALL)
     assert ev.force_reported_metrics == []
+
+
+@pytest.mark.parametrize("name", ["sigmoid_b16", "relu_b300"])
+def test_feedforward_batchnorm_training_matches_reference_golden(golden, name):
+    """batchnorm=True in TRAINING mode (batch statistics + running-stat update, FeedForward…py:68-77) against the imported
+    reference: outputs, loss, every parameter gradient (BatchNorm gamma/beta included) and the updated buffers."""
+    from inferbiomechanics_b200.loss.RegressionLossEvaluator import RegressionLossEvaluator
+    from inferbiomechanics_b200.models.FeedForwardRegressionBaseline import FeedForwardBaseline
+    g = golden("ff_bn_train.npz")
+    act = name.split("_")[0]
+    D, T, s, B, seed, iseed, lseed = (int(v) for v in g[f"{name}/meta"])
+    hidden = [int(v) for v in g[f"{name}/hidden"]]
+    m = FeedForwardBaseline(D, 2, T, "all_frames", act, s, 10, hidden_dims=hidden, batchnorm=True)
+    m.load_state_dict(seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed))
+    m = m.to("cuda")
+    m.train()
+    F = T // s
+    inputs = seeded_inputs(B, F, D, s * 3, iseed)
+    _, labels = seeded_out_labels(B, F, lseed)
+    # Tolerances.  B = 300: the usual ones (outputs 3e-2, gradients 6e-2 of max|ref|).  B = 16 with sigmoid: BatchNorm over 16
+    # rows of bf16 sigmoid activations (values near 0.5, batch std ~0.1) amplifies their 2^-9 relative rounding by
+    # value/std, measured 4.4 % on the outputs and 7 % on the last BatchNorm's gamma gradient: 6e-2 / 1e-1 there.
+    # Bias-like gradients upstream of a training-mode BatchNorm are sums of cancelling terms (a constant shift of the
+    # BatchNorm input has no effect), i.e. ~0 relative to the per-row terms; their error is bounded against the scale
+    # of the companion weight gradient (same per-row terms times O(1) inputs), not against their own near-zero value.
+    small = B < 64
+    out = m(inputs)
+    for k in Q:
+        close(out[k].detach(), g[f"{name}/out/{k}"], 6e-2 if small else 3e-2, k)
+    ev = RegressionLossEvaluator(dataset=None, split="train", device="cuda")
+    loss = ev(inputs, out, {k: v.clone() for k, v in labels.items()}, [], [], ALL)
+    np.testing.assert_allclose(loss.item(), float(g[f"{name}/loss"]), rtol=2e-2)
+    loss.backward()
+    gtol = 1e-1 if small else 6e-2
+    for n, p in m.named_parameters():
+        want = torch.as_tensor(g[f"{name}/grad_sample/{n}"]).double()
+        got = strided_sample(p.grad).double().cpu()
+        scale = want.abs().max().item()
+        if n.endswith(".bias") and not n.startswith(f"net.{len(m.net) - 1}."):
+            scale = max(scale, np.abs(g[f"{name}/grad_sample/{n[:-4]}weight"]).max())
+        assert (got - want).abs().max().item() <= gtol * scale + 1e-12, n
+    for k, v in m.state_dict().items():
+        if "running_" in k:
+            close(v, g[f"{name}/buffer/{k}"], 2e-2, k)
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(g[f"{name}/buffer/{k}"])
+
+
+def test_feedforward_dropout_training_matches_masked_emulation():
+    """dropout=True, dropout_prob=0.3 in training mode: the Philox masks are regenerated through the same C-ABI call
+    (ones in -> mask/(1-p) out) and the forward/backward of the drop-in is compared with a plain fp32 torch emulation
+    using those masks ([Dropout] Linear act per layer, FeedForward…py:68-77).  Eval mode ignores dropout."""
+    from inferbiomechanics_b200 import ops
+    from inferbiomechanics_b200.models.FeedForwardRegressionBaseline import FeedForwardBaseline
+    D, T, s, B, p = 23, 50, 5, 64, 0.3
+    torch.manual_seed(3)
+    m = FeedForwardBaseline(D, 2, T, "all_frames", "tanh", s, 10, hidden_dims=[64, 32], dropout=True, dropout_prob=p).to("cuda")
+    inputs = seeded_inputs(B, T // s, D, s * 3, 77)
+    m.eval()
+    m0 = FeedForwardBaseline(D, 2, T, "all_frames", "tanh", s, 10, hidden_dims=[64, 32]).to("cuda")
+    m0.load_state_dict({k.replace("net.1.", "net.0.").replace("net.4.", "net.2.").replace("net.7.", "net.4."): v
+                        for k, v in m.state_dict().items()})
+    e, e0 = m(inputs), m0(inputs)
+    for k in Q:
+        assert torch.equal(e[k], e0[k])                                  # eval: dropout is the identity
+    m.train()
+    out = m(inputs)
+    x = torch.cat([out[k].reshape(B, -1) for k in Q], dim=1)
+    gy = seeded_tensor(tuple(x.shape), 5).cuda()
+    (x * gy).sum().backward()
+    eng = m.engine()
+    # emulate with the regenerated masks
+    lins = [m.net[1], m.net[4], m.net[7]]
+    xin = eng.input_buffer(B)[:, :eng.in_cols].float()
+    ws = [l.weight.detach().float().clone().requires_grad_(True) for l in lins]
+    bs = [l.bias.detach().float().clone().requires_grad_(True) for l in lins]
+    h = xin
+    for i in range(3):
+        ones = torch.ones(B, ops.round_up(h.shape[1], 8), dtype=torch.bfloat16, device="cuda")
+        mask = torch.empty_like(ones)
+        ops.dropout(ones, mask, p, eng.DROPOUT_SEED, 3 * eng.step + i)
+        mk = mask[:, :h.shape[1]].float()
+        assert abs((mk == 0).float().mean().item() - p) < 0.03 and torch.allclose(mk[mk > 0], torch.tensor(1 / (1 - p), device="cuda"), rtol=1e-2)
+        h = (h * mk) @ ws[i].t() + bs[i]
+        if i < 2:
+            h = torch.tanh(h)
+    fo = T // s
+    ref = h                                                              # (B, 300), quantity-then-frame blocks like x
+    close(x.detach(), ref.detach(), 3e-2, "dropout forward")
+    (ref * gy).sum().backward()
+    for l, w, b in zip(lins, ws, bs):
+        close(l.weight.grad, w.grad, 6e-2, "dW")
+        close(l.bias.grad, b.grad, 6e-2, "db")
+    # a second training forward draws a different mask
+    out2 = m(inputs)
+    assert not torch.equal(out2[Q[0]], out[Q[0]])
 
 
 def test_feedforward_rejects_cpu_and_bad_shapes():
