@@ -131,6 +131,102 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
   }
 }
 
+// Narrow rows (ld <= 128, e.g. the TransformerBaseline's d = 108 padded to 112 columns; TransformerBaseline.py:79,87):
+// a warp per row would leave 18 of 32 lanes idle and pay two 5-step shuffle reductions per 224-byte row.  Here 8 lanes
+// share a row (lane sub owns the 16-byte chunks sub and 8 + sub, so a quarter-warp reads 128 contiguous bytes of shared
+// memory: no bank conflicts), a warp works on 4 rows per instruction, reductions are 3 shuffle steps, and gamma/beta of a
+// lane's 16 columns live in registers for the whole kernel.  Row groups of RN rows stream through the same per-warp
+// bulk-copy ring as the wide kernel.
+template <int RN>
+__global__ void __launch_bounds__(kThreads)
+layernorm_fwd_narrow_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ y, long long ld,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, long long M, int d, float eps,
+                            float* __restrict__ mean, float* __restrict__ rstd) {
+  extern __shared__ __align__(128) uint8_t smem_ln[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = lane & 7, rr = lane >> 3;
+  const uint32_t row_bytes = (uint32_t)ld * 2u;
+  const uint32_t group_bytes = RN * row_bytes;
+  uint8_t* ring = smem_ln + (size_t)wid * kStages * group_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ln + (size_t)kWarps * kStages * group_bytes) + wid * kStages;
+  if (lane == 0) {
+    for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  const int c0 = sub * 8, c1 = 64 + sub * 8;
+  const bool has0 = c0 < ld, has1 = c1 < ld;         // ld < 64: the upper lanes of a row group own no chunk at all
+  float gm[16], bt[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gm[j] = c0 + j < d ? __ldg(gamma + c0 + j) : 0.f;
+    bt[j] = c0 + j < d ? __ldg(beta + c0 + j) : 0.f;
+    gm[8 + j] = c1 + j < d ? __ldg(gamma + c1 + j) : 0.f;
+    bt[8 + j] = c1 + j < d ? __ldg(beta + c1 + j) : 0.f;
+  }
+  const long long n_groups = (M + RN - 1) / RN;
+  const long long gw = (long long)blockIdx.x * kWarps + wid, gstride = (long long)gridDim.x * kWarps;
+  auto issue = [&](long long grp, int st) {        // lane 0
+    const long long m0 = grp * RN;
+    const uint32_t bytes = (uint32_t)((M - m0 < RN ? M - m0 : RN)) * row_bytes;
+    mbar_arrive_expect_tx(&bars[st], bytes);
+    bulk_load(ring + (size_t)st * group_bytes, s + m0 * ld, bytes, &bars[st]);
+  };
+  if (lane == 0) {
+    for (int i = 0; i < kStages; ++i)
+      if (gw + i * gstride < n_groups) issue(gw + i * gstride, i);
+  }
+  const float inv_d = 1.f / (float)d;
+  int it = 0;
+  for (long long grp = gw; grp < n_groups; grp += gstride, ++it) {
+    const int st = it % kStages;
+    mbar_wait(&bars[st], (uint32_t)((it / kStages) & 1));
+    const uint8_t* tile = ring + (size_t)st * group_bytes;
+#pragma unroll
+    for (int r4 = 0; r4 < RN; r4 += 4) {
+      const int r = r4 + rr;
+      const long long m = grp * RN + r;
+      const bool live = m < M;                       // rows past M hold stale shared memory: computed, never stored
+      float va[8], vb[8], v[16];
+      if (has0) unpack8(lds16(tile + r * row_bytes + c0 * 2), va);
+      if (has1) unpack8(lds16(tile + r * row_bytes + c1 * 2), vb);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = has0 && c0 + j < d ? va[j] : 0.f;
+        v[8 + j] = has1 && c1 + j < d ? vb[j] : 0.f;
+        sum += v[j] + v[8 + j];
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mu = sum * inv_d;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c0 + j < d) { const float t = v[j] - mu; sq = fmaf(t, t, sq); }
+        if (has1 && c1 + j < d) { const float t = v[8 + j] - mu; sq = fmaf(t, t, sq); }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rs = rsqrtf(sq * inv_d + eps);
+      if (live) {
+        if (sub == 0) { if (mean) mean[m] = mu; if (rstd) rstd[m] = rs; }
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = fmaf((v[j] - mu) * rs, gm[j], bt[j]);     // gm = bt = 0 beyond d: pads get 0
+        if (has0)
+          st_stream16(y + m * ld + c0, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                  pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+        if (has1)
+          st_stream16(y + m * ld + c1, make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]),
+                                                  pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15])));
+      }
+    }
+    __syncwarp();                                   // every lane has read this stage
+    if (lane == 0 && grp + kStages * gstride < n_groups) issue(grp + kStages * gstride, st);
+  }
+}
+
 // Backward.  ds = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma,  xhat = (s-mu)*rstd.
 // Column reductions (dgamma, dbeta, colsum(ds)) are accumulated in registers over the rows a warp
 // visits, combined across the block's 8 warps in shared memory, then one fp32 atomic per column
@@ -285,6 +381,24 @@ static int launch_ln_fwd(const __nv_bfloat16* sp, __nv_bfloat16* yp, int64_t ld,
   return IBM_OK;
 }
 
+template <int RN>
+static int launch_ln_fwd_narrow(const __nv_bfloat16* sp, __nv_bfloat16* yp, int64_t ld, const float* gamma, const float* beta,
+                                int64_t M, int32_t d, float eps, float* mean, float* rstd, cudaStream_t st) {
+  auto kern = layernorm_fwd_narrow_kernel<RN>;
+  const size_t smem = (size_t)kWarps * kStages * RN * ld * 2 + kWarps * kStages * 8;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  int grid = 0;
+  int rc = ln_grid(kern, smem, ceil_div(M, RN), &grid);
+  if (rc) return rc;
+  kern<<<grid, kThreads, smem, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
 template <int CH, bool FULL>
 static int launch_ln_bwd(const __nv_bfloat16* dyp, const __nv_bfloat16* sp, int64_t ld, const float* gamma, const float* mean,
                          const float* rstd, int64_t M, int32_t d, __nv_bfloat16* dsp, float* dgamma, float* dbeta, float* dcolsum,
@@ -319,6 +433,7 @@ extern "C" int ibm_layernorm_fwd(const void* s, void* y, int64_t ld, const float
   auto* sp = static_cast<const __nv_bfloat16*>(s);
   auto* yp = static_cast<__nv_bfloat16*>(y);
   const bool full = d == ld && ld == (int64_t)ch * 256;
+  if (ld <= 128) return launch_ln_fwd_narrow<8>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd, st);
 #define IBM_LN_FWD(CHV, RV)                                                                              \
   return full ? launch_ln_fwd<CHV, RV, true>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd, st)         \
               : launch_ln_fwd<CHV, RV, false>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd, st)

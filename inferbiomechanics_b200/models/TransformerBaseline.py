@@ -147,6 +147,65 @@ class TransformerBaseline(nn.Module):
                                  v=z(8), blend=z(8), out=z(12, torch.float32), x32=z(dp, torch.float32))
         return self._bufs[M]
 
+    # ---- host-fed stream (BASELINE configs[4]: the analysis pass over a long window stream) -----------------
+    @torch.no_grad()
+    def forward_stream(self, batches):
+        """Generator over an iterable of host input dicts (pinned CPU tensors keyed like ``forward``): yields one output
+        dict of pinned CPU tensors per batch, in order.  The H2D copies of batch i+1 run on a copy stream into the other
+        half of a double-buffered staging area while batch i computes, and the D2H copies of batch i's three outputs
+        run on a third stream, so neither PCIe direction leaves the GPU idle (analyze.py:112-156 moves one window at a
+        time and synchronises on every ``.item()``).  Windows are independent: shard the stream across GPUs by window,
+        no collective."""
+        dev = next(self.parameters()).device
+        main = torch.cuda.current_stream(dev)
+        up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        slots = [dict(x=None, out=None, host=None, uploaded=torch.cuda.Event(), consumed=torch.cuda.Event(), done=torch.cuda.Event())
+                 for _ in range(2)]
+
+        def upload(batch, slot):
+            with torch.cuda.stream(up):
+                up.wait_event(slot["consumed"])
+                if slot["x"] is None or any(slot["x"][k].shape != v.shape for k, v in batch.items()):
+                    slot["x"] = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in batch.items()}
+                for k, v in batch.items():
+                    slot["x"][k].copy_(v, non_blocking=True)
+                slot["uploaded"].record(up)
+
+        def compute(slot):
+            main.wait_event(slot["uploaded"])
+            out = self.forward(slot["x"])
+            slot["consumed"].record(main)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(down):
+                down.wait_event(ready)
+                if slot["host"] is None or any(slot["host"][k].shape != v.shape for k, v in out.items()):
+                    slot["host"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+                for k, v in out.items():
+                    slot["host"][k].copy_(v, non_blocking=True)
+                slot["done"].record(down)
+            slot["out"] = out                          # keeps the device tensors alive until the copy has run
+
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        for s_ in slots:
+            s_["consumed"].record(main)
+        upload(cur, slots[0])
+        i, pending = 0, None
+        while cur is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(nxt, slots[(i + 1) & 1])        # waits (on the copy stream) until batch i-1 has been consumed
+            compute(slots[i & 1])                      # its pinned outputs replace batch i-2's, already handed out
+            if pending is not None:
+                pending["done"].synchronize()
+                yield pending["host"]                  # valid until the next item is requested
+            pending, cur, i = slots[i & 1], nxt, i + 1
+        pending["done"].synchronize()
+        yield pending["host"]
+
     # ---- forward (TransformerBaseline.py:104-148) ---------------------------------------------------------
     @torch.no_grad()
     def forward(self, x: Dict[str, torch.Tensor]):

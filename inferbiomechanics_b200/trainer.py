@@ -16,6 +16,7 @@ the reference's own autograd loop; this is the path bench.py times.
 from __future__ import annotations
 
 import argparse
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -76,6 +77,9 @@ class Trainer:
         self.arena.sync_shadow(force=True)
         self._lab: Dict[int, torch.Tensor] = {}
         self._gen = torch.Generator(device=dev).manual_seed(seed + 7919 * self.rank)
+        # CUDA-graph replay of the (launch-bound) FeedForward step: key -> [eager steps seen, graph, static idx, static result]
+        self._graphs: Dict[tuple, list] = {}
+        self.use_graphs = os.environ.get("IBM_TRAIN_GRAPHS", "1") != "0"
 
     def _group_boundaries(self) -> List[int]:
         offs = self.arena.offsets
@@ -86,8 +90,54 @@ class Trainer:
         return [offs[bn[i][0] if bn is not None and bn[i] is not None else w][0] for i, (w, _, _, _) in enumerate(self.eng.layers)]
 
     # ---- one optimisation step on windows idx of a store -------------------------------------------
+    def _graphable(self) -> bool:
+        """The FeedForward step is ~25 short launches: at the reference's batch sizes the host, not the GPU, paces it, so
+        it is captured once per (store, batch size) and replayed.  Not captured: the denoiser (device-side RNG state and
+        host-side Philox offsets change per step, and its step is GPU-bound anyway), multi-rank runs (the NCCL side
+        stream), optimizers whose kernel takes the step count by value (adam/adamax bias correction), dropout (the mask
+        offset is a host-side argument)."""
+        return (self.use_graphs and not self.is_denoiser and self.world == 1 and self.opt_type not in ("adam", "adamax")
+                and getattr(self.eng, "dropout_p", 0.0) == 0.0)
+
     def train_step(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
         """Returns the device-resident fp32[40] result (loss at [0]); nothing is synchronised."""
+        if self._graphable():
+            return self._train_step_graphed(store, idx)
+        return self._train_step_eager(store, idx)
+
+    def _train_step_graphed(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
+        key = (id(store), idx.numel())
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            g = self._graphs[key] = [0, None, None, None, store]     # holds the store: its id() cannot be recycled
+        if g[1] is None:
+            if g[0] < 2:                         # two eager steps first: every lazily created buffer / attribute exists
+                g[0] += 1
+                return self._train_step_eager(store, idx)
+            g[2] = idx.clone()
+            g[3] = torch.zeros(40, device=idx.device)
+            ring, self._result_ring = self._result_ring, [g[3]]
+            count = self.step_count
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    self._train_step_eager(store, g[2])
+            finally:
+                self._result_ring = ring
+            self.step_count = count              # capture does not execute: the replay below is this step
+            g[1] = graph
+        g[2].copy_(idx, non_blocking=True)
+        g[1].replay()
+        self.step_count += 1
+        self.arena._versions = self.arena._version_sum()
+        result = self._result_ring[self.step_count % len(self._result_ring)]
+        result.copy_(g[3], non_blocking=True)
+        return result
+
+    def _train_step_eager(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
         B = idx.numel()
         lab = self._labels(store, idx)
         self.arena.zero_grad()

@@ -216,7 +216,8 @@ def test_timestep_embedding_and_time_pos():
 
 # ---------------------------------------- LayerNorm ------------------------------------------------
 @pytest.mark.parametrize("M,d,ld", [(1000, 512, 512), (300, 108, 112), (77, 128, 128), (50, 1024, 1024), (129, 64, 64),
-                                    (5000, 256, 256), (3001, 768, 768), (70001, 512, 512), (9, 512, 512)])
+                                    (5000, 256, 256), (3001, 768, 768), (70001, 512, 512), (9, 512, 512),
+                                    (40999, 108, 112), (1001, 115, 120), (33, 40, 40), (5, 8, 8), (4096, 64, 72)])
 def test_layernorm_fwd_bwd(M, d, ld):
     from inferbiomechanics_b200 import ops
     g = torch.Generator().manual_seed(M + d)

@@ -49,3 +49,28 @@ def test_transformer_stream_is_window_independent():
     hi = m({k: v[32:] for k, v in x.items()})
     for k in (O.CONTACT, O.COM_ACC, O.CONTACT_FORCES):
         assert torch.equal(full[k], torch.cat([lo[k], hi[k]], dim=0))
+
+
+def test_transformer_forward_stream_matches_forward():
+    """forward_stream (host-fed, copies overlapped with compute on separate streams) yields, in order, exactly what
+    forward() returns for each batch — including a ragged last batch and a single-batch stream."""
+    from inferbiomechanics_b200.keys import InputDataKeys as K, OutputDataKeys as O
+    from inferbiomechanics_b200.models.TransformerBaseline import TransformerBaseline
+    T, D = 64, 23
+    torch.manual_seed(1)
+    m = TransformerBaseline(D, T, dtype=torch.float32).cuda()
+    g = torch.Generator().manual_seed(2)
+    chans = [(K.POS, D), (K.VEL, D), (K.ACC, D), (K.COM_POS, 3), (K.COM_VEL, 3), (K.COM_ACC, 3)]
+    batches = [{k: torch.randn(B, c, T, generator=g).pin_memory() for k, c in chans} for B in (16, 16, 16, 16, 5)]
+    want = [{k: v.cpu().clone() for k, v in m({k: v.cuda() for k, v in b.items()}).items()} for b in batches]
+    got = []
+    for out in m.forward_stream(batches):
+        assert all(not v.is_cuda and v.is_pinned() for v in out.values())
+        got.append({k: v.clone() for k, v in out.items()})            # valid until the next item is requested
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        for k in (O.CONTACT, O.COM_ACC, O.CONTACT_FORCES):
+            assert torch.equal(a[k], b[k])
+    one = list(m.forward_stream(batches[:1]))
+    assert len(one) == 1 and torch.equal(one[0][O.CONTACT], want[0][O.CONTACT])
+    assert list(m.forward_stream([])) == []
