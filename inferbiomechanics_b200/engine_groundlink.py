@@ -59,6 +59,10 @@ class GroundlinkEngine:
         self._wver = ver
         return self._w
 
+    def weights_changed(self) -> None:
+        """The fused optimizer writes the fp32 masters through raw pointers (no torch version bump): drop the cache."""
+        self._wver = None
+
     # ---- buffers ---------------------------------------------------------------------------------------------
     def _state(self, B: int, T: int):
         st = self.buf.get((B, T))

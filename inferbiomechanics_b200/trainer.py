@@ -10,7 +10,7 @@
     backward engine → flat fp32 grad arena       (bucketed NCCL allreduce fired layer by layer)
     fused optimizer → params + state + bf16 shadow (1 kernel, 1/W folded in)
 
-Works for ``FeedForwardBaseline`` and ``DiffusionDenoiser``.  The drop-in classes remain usable with
+Works for ``FeedForwardBaseline``, ``Groundlink`` and ``DiffusionDenoiser``.  The drop-in classes remain usable with
 the reference's own autograd loop; this is the path bench.py times.
 """
 from __future__ import annotations
@@ -28,6 +28,7 @@ from .keys import LOSS_QUANTITIES
 from .loss.RegressionLossEvaluator import COP_FORCE_THRESHOLD, component_weights
 from .models.DiffusionDenoiser import DiffusionDenoiser
 from .models.FeedForwardRegressionBaseline import FeedForwardBaseline
+from .models.Groundlink import Groundlink
 
 ALL_COMPONENTS = argparse.Namespace(predict_grf_components=list(range(6)), predict_cop_components=list(range(6)),
                                     predict_moment_components=list(range(6)), predict_wrench_components=list(range(12)))
@@ -57,6 +58,7 @@ class Trainer:
         self.step_count = 0
         self.seed = seed
         self.is_denoiser = isinstance(model, DiffusionDenoiser)
+        self.is_groundlink = isinstance(model, Groundlink)
         if self.is_denoiser:
             self.diffusion = diffusion or GaussianDiffusion(device=self.arena.device)
         n = self.arena.total
@@ -70,6 +72,8 @@ class Trainer:
         self.bucketer = parallel.GradBucketer(self.arena.grad, parallel.make_buckets(bounds, n, int(bucket_mb * (1 << 20) / 4)))
         if self.is_denoiser:
             self.eng.bucket_hook = lambda l: self.bucketer.group_done(l + 1)      # group 0 = stem, l+1 = layer l, L+1 = head
+        elif self.is_groundlink:
+            self.eng.bucket_hook = lambda i: self.bucketer.group_done(i)          # groups 0-3 = conv layers, 4 = the per-frame MLP
         else:
             self.eng.bucket_hook = lambda i: self.bucketer.group_done(i)          # group i = Linear layer i
         # DDP constructor semantics: everyone starts from rank 0's parameters (train.py:175)
@@ -86,6 +90,8 @@ class Trainer:
         if self.is_denoiser:
             first = [offs[f"layers.{l}.multihead_attention.in_proj_weight"][0] for l in range(self.model.num_layers)]
             return [0] + first + [offs["out_proj.weight"][0]]
+        if self.is_groundlink:
+            return [offs[f"cnn.{p}.weight"][0] for p in self.eng.conv_pos] + [offs[f"fc.{self.eng.fc_pos[0]}.weight"][0]]
         bn = getattr(self.eng, "bn", None)        # a layer's BatchNorm parameters precede its Linear in the arena
         return [offs[bn[i][0] if bn is not None and bn[i] is not None else w][0] for i, (w, _, _, _) in enumerate(self.eng.layers)]
 
@@ -96,7 +102,7 @@ class Trainer:
         host-side Philox offsets change per step, and its step is GPU-bound anyway), multi-rank runs (the NCCL side
         stream), optimizers whose kernel takes the step count by value (adam/adamax bias correction), dropout (the mask
         offset is a host-side argument)."""
-        return (self.use_graphs and not self.is_denoiser and self.world == 1 and self.opt_type not in ("adam", "adamax")
+        return (self.use_graphs and not self.is_denoiser and not self.is_groundlink and self.world == 1 and self.opt_type not in ("adam", "adamax")
                 and getattr(self.eng, "dropout_p", 0.0) == 0.0)
 
     def train_step(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
@@ -143,25 +149,15 @@ class Trainer:
         self.arena.zero_grad()
         self.bucketer.begin_step()
         if self.is_denoiser:
-            out = self._denoiser_forward(store, idx, lab, B)
-            outs, labs = _views30(out.view(B, self.eng.F, 32)), _views30(lab)
-            gviews = _views30(self.eng.dout(B).view(B, self.eng.F, 32))
-        else:
-            store.pack_feedforward(idx, self.eng.input_buffer(B))
-            out = self.eng.forward(B, train=True)
-            Fo = self.model.num_output_frames
-            outs, labs = _views_ff(out, B, Fo), _views30(lab)
-            gviews = _views_ff(self.eng.dout_buffer(B), B, Fo)
-        result = self._result_ring[self.step_count % len(self._result_ring)]
-        ops.regression_loss_fwd(outs, labs, self.weights, COP_FORCE_THRESHOLD, result=result)
-        ops.regression_loss_bwd(outs, labs, self.weights, gviews, threshold=COP_FORCE_THRESHOLD)
-        if self.is_denoiser:
-            self.eng.backward(B)
-        else:
-            self._ff_backward(B)
-        self.bucketer.finish()
-        self.optimizer_step()
-        return result
+            store.pack_rows(idx, self.eng.xc(B, True), col0=30)
+            return self._finish_denoiser_step(B, lab)
+        if self.is_groundlink:
+            buf, fs, we, col0 = self.eng.input_rows(B, store.F)         # padded-row layout: frame t of window b at row b*(T+6)+3+t
+            ops.pack_windows(store.frames, store.C, store.win_row0[idx], store.F, store.stride, out_bf16=buf, frame_stride=fs,
+                             win_extra=we, col0=col0)
+            return self._finish_groundlink_step(B, store.F, lab)
+        store.pack_feedforward(idx, self.eng.input_buffer(B))
+        return self._finish_ff_step(B, lab)
 
     def _labels(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
         B = idx.numel()
@@ -169,28 +165,13 @@ class Trainer:
             self._lab[B] = torch.empty(B, store.Fo, 30, dtype=torch.float32, device=self.arena.device)
         return store.labels(idx, self._lab[B])
 
-    def _denoiser_forward(self, store, idx, lab, B):
-        eng = self.eng
-        xc = eng.xc(B, True)
-        store.pack_rows(idx, xc, col0=30)
-        t = eng.t_buffer(B, True)
-        t.copy_(torch.randint(0, self.diffusion.T, (B,), device=t.device, generator=self._gen, dtype=torch.int32))
-        # x_t = q_sample(x0 = labels rows30, t, eps ~ Philox) written straight into the concat buffer as bf16
-        self.diffusion.q_sample(lab.view(B, -1), t, None, xt_bf16=xc, bf16_ld=eng.ld_in, seed=self.seed + self.rank,
-                                offset=self.step_count)
-        return eng.forward(B, train=True)
-
-    def _ff_backward(self, B: int) -> None:
-        eng = self.eng
-        # FeedForwardEngine.backward walks the layers from last to first; fire buckets as groups complete
-        eng.backward(B)
-        # (the MLP is 3 GEMM triples: the allreduce is one or two buckets, flushed in finish())
-
     def optimizer_step(self) -> None:
         self.step_count += 1
         ops.optimizer_step(self.opt_type, self.arena.master, self.arena.grad, self.state0, self.state1, self.arena.shadow,
                            self.lr, 1.0 / self.world, self.step_count)
         self.arena.mark_shadow_fresh()
+        if hasattr(self.eng, "weights_changed"):
+            self.eng.weights_changed()           # engines that cache re-laid-out weights (Groundlink's conv GEMM layouts)
 
     # ---- evaluation (no_grad forward + loss), used by analyze / dev-eval ------------------------------
     @torch.no_grad()
@@ -199,6 +180,15 @@ class Trainer:
         lab = self._labels(store, idx)
         if self.is_denoiser:
             raise NotImplementedError("denoiser evaluation = reverse sampling; use GaussianDiffusion.sample")
+        if self.is_groundlink:
+            T = store.F
+            buf, fs, we, col0 = self.eng.input_rows(B, T)
+            ops.pack_windows(store.frames, store.C, store.win_row0[idx], store.F, store.stride, out_bf16=buf, frame_stride=fs,
+                             win_extra=we, col0=col0)
+            out = self.eng.forward(B, T, False)
+            if store.Fo == 1:
+                out = out[:, -1:, :]
+            return ops.regression_loss_fwd(_views30(out), _views30(lab), self.weights)
         store.pack_feedforward(idx, self.eng.input_buffer(B))
         out = self.eng.forward(B)
         return ops.regression_loss_fwd(_views_ff(out, B, self.model.num_output_frames), _views30(lab), self.weights)
@@ -207,17 +197,20 @@ class Trainer:
 # =====================================================================================================
 # Host-fed step (the e2e path), profiling helpers used by bench.py
 # =====================================================================================================
-def _make_host_batch(self, B: int, seed: int = 0):
+def _make_host_batch(self, B: int, seed: int = 0, frames: Optional[int] = None):
     """Synthetic pinned host tensors shaped like a reference DataLoader batch."""
     from .keys import MODEL_INPUT_ORDER
     g = torch.Generator().manual_seed(seed)
-    F = self.eng.F if self.is_denoiser else self.model.num_frames
-    hist = self.model.root_history_len * 3 if self.is_denoiser else self.model.stride * 3
+    if self.is_groundlink and frames is None:
+        raise ValueError("Groundlink windows have no fixed length: pass frames=T")
+    F = frames if frames is not None else (self.eng.F if self.is_denoiser else self.model.num_frames)
+    hist = self.model.root_history_len * 3 if (self.is_denoiser or self.is_groundlink) else self.model.stride * 3
     widths = {"pos": 23, "vel": 23, "acc": 23, "rootLinearVelInRootFrame": 3, "rootAngularVelInRootFrame": 3,
               "rootLinearAccInRootFrame": 3, "rootAngularAccInRootFrame": 3, "jointCentersInRootFrame": 36,
               "rootPosHistoryInRootFrame": hist, "rootEulerHistoryInRootFrame": hist}
     inputs = {k: torch.randn(B, F, widths[k], generator=g).pin_memory() for k in MODEL_INPUT_ORDER}
-    Fo = F if self.is_denoiser else self.model.num_output_frames
+    Fo = F if self.is_denoiser else (1 if self.is_groundlink and self.model.output_data_format != "all_frames" else
+                                     F if self.is_groundlink else self.model.num_output_frames)
     scale = {LOSS_QUANTITIES[0]: 1.0, LOSS_QUANTITIES[1]: 10.0, LOSS_QUANTITIES[2]: 1.0, LOSS_QUANTITIES[3]: 1.0}
     labels = {k: (torch.randn(B, Fo, 12 if i == 3 else 6, generator=g) * scale[k]).pin_memory() for i, k in enumerate(LOSS_QUANTITIES)}
     return {"inputs": inputs, "labels": labels}
@@ -244,16 +237,8 @@ def _train_step_host(self, inputs, labels) -> float:
     srcs = [stage[k].view(B * F, -1) for k in MODEL_INPUT_ORDER]
     self.arena.zero_grad()
     self.bucketer.begin_step()
-    if self.is_denoiser:
-        eng = self.eng
-        xc = eng.xc(B, True)
-        ops.pack_inputs(srcs, B * F, F, out_bf16=xc, frame_stride=eng.ld_in, win_extra=0, col0=30)
-        result = self._finish_denoiser_step(B, lab)
-    else:
-        eng = self.eng
-        ops.pack_inputs(srcs, B * F, F, out_bf16=eng.input_buffer(B), frame_stride=self.model.frame_width,
-                        win_extra=eng.in_ld - self.model.input_size, col0=0)
-        result = self._finish_ff_step(B, lab)
+    self._pack_host_inputs(srcs, B, F)
+    result = self._finish_step(B, F, lab)
     return float(result[0].item())
 
 
@@ -300,15 +285,9 @@ def _train_steps_host(self, batches):
         srcs = [stage[k].view(B * F, -1) for k in MODEL_INPUT_ORDER]
         self.arena.zero_grad()
         self.bucketer.begin_step()
-        eng = self.eng
-        if self.is_denoiser:
-            ops.pack_inputs(srcs, B * F, F, out_bf16=eng.xc(B, True), frame_stride=eng.ld_in, win_extra=0, col0=30)
-            consumed.record(main)                         # staging slot is free once both packers have run
-            return self._finish_denoiser_step(B, lab)
-        ops.pack_inputs(srcs, B * F, F, out_bf16=eng.input_buffer(B), frame_stride=self.model.frame_width,
-                        win_extra=eng.in_ld - self.model.input_size, col0=0)
-        consumed.record(main)
-        return self._finish_ff_step(B, lab)
+        self._pack_host_inputs(srcs, B, F)
+        consumed.record(main)                             # staging slot is free once both packers have run
+        return self._finish_step(B, F, lab)
 
     try:
         nxt = upload(next(it), 0)
@@ -332,6 +311,45 @@ def _train_steps_host(self, batches):
         pending = (result, done)
     pending[1].synchronize()
     yield float(pending[0][0].item())
+
+
+def _pack_host_inputs(self, srcs, B: int, F: int) -> None:
+    """The ten per-key input tensors (FeedForward…py:97-108 concat order) -> the model's packed bf16 layout, one kernel."""
+    eng = self.eng
+    if self.is_denoiser:
+        ops.pack_inputs(srcs, B * F, F, out_bf16=eng.xc(B, True), frame_stride=eng.ld_in, win_extra=0, col0=30)
+    elif self.is_groundlink:
+        buf, fs, we, col0 = eng.input_rows(B, F)
+        ops.pack_inputs(srcs, B * F, F, out_bf16=buf, frame_stride=fs, win_extra=we, col0=col0)
+    else:
+        ops.pack_inputs(srcs, B * F, F, out_bf16=eng.input_buffer(B), frame_stride=self.model.frame_width,
+                        win_extra=eng.in_ld - self.model.input_size, col0=0)
+
+
+def _finish_step(self, B: int, F: int, lab: torch.Tensor) -> torch.Tensor:
+    if self.is_denoiser:
+        return self._finish_denoiser_step(B, lab)
+    if self.is_groundlink:
+        return self._finish_groundlink_step(B, F, lab)
+    return self._finish_ff_step(B, lab)
+
+
+def _finish_groundlink_step(self, B: int, T: int, lab: torch.Tensor) -> torch.Tensor:
+    """Groundlink (Groundlink.py:135-156): implicit-GEMM CNN + per-frame MLP forward, fused loss on the strided
+    (B, T, 32) output view, backward into the flat gradient arena, fused optimizer."""
+    eng = self.eng
+    out = eng.forward(B, T, True)
+    gout = eng.dout_view(B, T)
+    if lab.shape[1] == 1:                               # last_frame: only the final frame is an output (Groundlink.py:147-148)
+        out, gout = out[:, -1:, :], gout[:, -1:, :]
+    outs, labs, gviews = _views30(out), _views30(lab), _views30(gout)
+    result = self._result_ring[self.step_count % len(self._result_ring)]
+    ops.regression_loss_fwd(outs, labs, self.weights, COP_FORCE_THRESHOLD, result=result)
+    ops.regression_loss_bwd(outs, labs, self.weights, gviews, threshold=COP_FORCE_THRESHOLD)
+    eng.backward(B, T)
+    self.bucketer.finish()
+    self.optimizer_step()
+    return result
 
 
 def _finish_denoiser_step(self, B: int, lab: torch.Tensor) -> torch.Tensor:
@@ -502,5 +520,8 @@ Trainer.train_step_host = _train_step_host
 Trainer.train_steps_host = _train_steps_host
 Trainer._finish_denoiser_step = _finish_denoiser_step
 Trainer._finish_ff_step = _finish_ff_step
+Trainer._finish_groundlink_step = _finish_groundlink_step
+Trainer._finish_step = _finish_step
+Trainer._pack_host_inputs = _pack_host_inputs
 Trainer.profile_gemms = _profile_gemms
 Trainer.aux_measurements = _aux_measurements
