@@ -5,8 +5,7 @@ What changes underneath (and nothing a caller of the command sees): the two Data
 ``WindowStore``s sharded by the reference's DistributedSampler rule; model / loss / backward / optimizer are
 one ``Trainer.train_step`` (explicit kernel launches over flat parameter arenas, bucketed NCCL allreduce
 overlapped with backward, fused optimizer) instead of autograd + DDP + torch.optim; losses stay on the device
-and are read back only at report time.  ``groundlink`` runs the reference's own loop shape on the drop-in module
-(autograd bridge + torch.optim), since its engine is not wired into ``Trainer`` yet.
+and are read back only at report time, for all three model types (``feedforward``, ``groundlink``, ``diffusion``).
 Conscious fixes of reference defects that stop it running: ``DEV``/``mp``/``time`` are defined,
 ``any(params_to_optimize)`` is not evaluated on tensors.  One process per GPU under torchrun, as in the reference.
 """
@@ -143,7 +142,7 @@ class TrainCommand(AbstractCommand):
             logging.error('Invalid optimizer type: ' + args.opt_type)
             assert (False)
 
-        native = model_type in ('feedforward', 'diffusion')
+        native = model_type in ('feedforward', 'groundlink', 'diffusion')
         if native:
             trainer = Trainer(model, opt_type=args.opt_type, lr=args.learning_rate, args=args, seed=1234)
             optimizer = None

@@ -253,7 +253,9 @@ def _attn_ref(q, k, v, scale):
 
 
 @pytest.mark.parametrize("n_win,T,H,hd", [(3, 50, 8, 64), (2, 64, 2, 64), (2, 200, 3, 48), (5, 10, 4, 32), (1, 256, 1, 64), (4, 1, 2, 64),
-                                          (900, 50, 8, 64), (2000, 23, 3, 48)])
+                                          (900, 50, 8, 64), (2000, 23, 3, 48),
+                                          # long windows (64 < T <= 256): persistent one-CTA-per-(window, head) kernel
+                                          (3, 65, 2, 32), (2, 129, 4, 64), (700, 200, 3, 48), (2, 250, 1, 48), (5, 72, 3, 48)])
 def test_attention_forward(n_win, T, H, hd):
     from inferbiomechanics_b200 import ops
     d = H * hd

@@ -65,10 +65,25 @@ def case(name):
             return (lambda: ops.regression_loss_fwd(outs, labs, w, result=res)), Bb * F * 240
         g16 = v(torch.zeros(Bb, F, 32, dtype=torch.bfloat16, device=dev))
         return (lambda: ops.regression_loss_bwd(outs, labs, w, g16)), Bb * F * 300
+    # ---- TransformerBaseline analysis shapes (BASELINE configs[4]): 2048 windows x T=200, d=108 -> 112, 3 heads 36 -> 48
+    if name == "attn_fwd_t200":
+        Bt, Tt, Ht, hp = 2048, 200, 3, 48
+        qkv, o = bf(Bt * Tt, 3 * Ht * hp), torch.empty(Bt * Tt, Ht * hp, dtype=torch.bfloat16, device=dev)
+        return (lambda: ops.attention_fwd_fused(qkv, Ht * hp, o, Bt, Tt, Ht, hp, 1 / 6.0)), 2 * Bt * Tt * 4 * Ht * hp
+    if name == "attn_com_blend_t200":
+        Bt, Tt = 2048, 200
+        q, k, v, o = bf(Bt * Tt, 112), bf(Bt * Tt, 112), bf(Bt * Tt, 8), torch.empty(Bt * Tt, 8, dtype=torch.bfloat16, device=dev)
+        return (lambda: ops.attention_fwd(q, k, v, o, Bt, Tt, 1, 112, 8, 1.0)), 2 * Bt * Tt * (112 + 112 + 8 + 8)
+    if name == "ln_fwd_d108":
+        Mt = 2048 * 200
+        s_, y = bf(Mt, 112), torch.empty(Mt, 112, dtype=torch.bfloat16, device=dev)
+        g, b = torch.ones(108, device=dev), torch.zeros(108, device=dev)
+        return (lambda: ops.layernorm_fwd(s_, y, g, b, Mt, 108)), 2 * Mt * 2 * 112
     raise KeyError(name)
 
 
-CASES = ["attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "colsum_ffn", "loss_fwd", "loss_bwd"]
+CASES = ["attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "colsum_ffn", "loss_fwd", "loss_bwd", "attn_fwd_t200", "attn_com_blend_t200",
+         "ln_fwd_d108"]
 
 
 def run(name, iters=10):
