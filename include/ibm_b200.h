@@ -146,9 +146,12 @@ int ibm_ddpm_posterior_step(const float* x0_hat, int64_t x0_ld, const float* x_t
 int ibm_timestep_embed(const int32_t* t, int32_t t_is_scalar, int64_t B, int32_t dim, void* out_bf16,
                        void* stream);
 
-/* h[m,:] += temb[m / F, :] + pos[m % F, :]   (bf16 in place; temb bf16 [B,d]; pos fp32 [F,d]) */
+/* h[m,:] += temb[m / F, :] + pos[m % F, :]   (bf16 in place; temb bf16 [B,d]; pos fp32 [F,d]).
+ * t_row_dev != NULL (reverse sampling: every window is at the same timestep): temb is a table with one row per
+ * timestep and row t_row_dev[0] (a device int32) is added to every window, so the time MLP is evaluated once per
+ * model, not once per denoise step. */
 int ibm_add_time_pos(void* h_bf16, int64_t ld, const void* temb_bf16, int64_t temb_ld,
-                     const float* pos, int64_t M, int32_t F, int32_t d, void* stream);
+                     const float* pos, int64_t M, int32_t F, int32_t d, const int32_t* t_row_dev, void* stream);
 /* backward of the above: dtemb[b,:] = sum_f dh[b,f,:] (bf16 out); dpos[f,:] += sum_b dh[b,f,:] (fp32 atomic) */
 int ibm_add_time_pos_bwd(const void* dh_bf16, int64_t ld, void* dtemb_bf16, int64_t temb_ld,
                          float* dpos, int64_t M, int32_t F, int32_t d, void* stream);

@@ -119,16 +119,18 @@ timestep_embed_kernel(const int32_t* __restrict__ t, int t_is_scalar, long long 
 // ---- h += temb[b] + pos[f] -------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 add_time_pos_kernel(__nv_bfloat16* __restrict__ h, long long ld, const __nv_bfloat16* __restrict__ temb,
-                    long long temb_ld, const float* __restrict__ pos, long long M, int F, int d) {
+                    long long temb_ld, const float* __restrict__ pos, long long M, int F, int d,
+                    const int* __restrict__ t_row) {
   const int d8 = d >> 3;
   const long long n = M * d8;
+  const long long fixed_row = t_row ? (long long)__ldg(t_row) : -1;   // one table row for every window (sampling)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / d8;
     const int c = (int)(i - m * d8) * 8;
     const long long b = m / F;
     const int f = (int)(m - b * F);
     uint4 hv = *reinterpret_cast<const uint4*>(h + m * ld + c);
-    const uint4 tv = __ldg(reinterpret_cast<const uint4*>(temb + b * temb_ld + c));
+    const uint4 tv = __ldg(reinterpret_cast<const uint4*>(temb + (fixed_row >= 0 ? fixed_row : b) * temb_ld + c));
     const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + (long long)f * d + c));
     const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + (long long)f * d + c + 4));
     float2 a, e;
@@ -248,14 +250,14 @@ extern "C" int ibm_timestep_embed(const int32_t* t, int32_t t_is_scalar, int64_t
 }
 
 extern "C" int ibm_add_time_pos(void* h_bf16, int64_t ld, const void* temb_bf16, int64_t temb_ld, const float* pos,
-                                int64_t M, int32_t F, int32_t d, void* stream) {
+                                int64_t M, int32_t F, int32_t d, const int32_t* t_row_dev, void* stream) {
   using namespace ibm;
   IBM_CHECK_ARCH();
   IBM_CHECK_ARG(h_bf16 && temb_bf16 && pos && M > 0 && F > 0 && M % F == 0, "add_time_pos: bad argument");
   IBM_CHECK_ARG(d % 8 == 0 && ld % 8 == 0 && temb_ld % 8 == 0 && aligned16(h_bf16) && aligned16(temb_bf16) && aligned16(pos),
                 "add_time_pos: d, ld must be multiples of 8 and pointers 16-byte aligned");
   add_time_pos_kernel<<<ew_grid(M * (d / 8)), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(h_bf16), ld, static_cast<const __nv_bfloat16*>(temb_bf16), temb_ld, pos, M, F, d);
+      static_cast<__nv_bfloat16*>(h_bf16), ld, static_cast<const __nv_bfloat16*>(temb_bf16), temb_ld, pos, M, F, d, t_row_dev);
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }

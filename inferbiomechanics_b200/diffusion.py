@@ -37,6 +37,9 @@ class GaussianDiffusion:
         self.sigma = f(np.exp(0.5 * post_logvar))
         self.device = torch.device(device)
         self._graphs = {}
+        # reverse sampling: take the time MLP from the engine's per-timestep table (DenoiserEngine.temb_table) instead of
+        # evaluating it every step; False re-runs it per step (parity check, tests/test_gpu_models.py)
+        self.use_temb_table = True
 
     # ---- forward process -----------------------------------------------------------------------
     def q_sample(self, x0: torch.Tensor, t: torch.Tensor, eps: Optional[torch.Tensor] = None, *, xt_f32=None, xt_bf16=None,
@@ -78,7 +81,7 @@ class GaussianDiffusion:
         t_a.fill_(self.T - 1)
 
         def step(t_in, t_out, z):
-            x0_hat = eng.forward(B, train=False, t_scalar=t_in)
+            x0_hat = eng.forward(B, train=False, t_scalar=t_in, t_count=self.T if self.use_temb_table else 0)
             ops.posterior_step(x0_hat, 32, x, z, t_in, self.coef_x0, self.coef_xt, self.sigma, M, x_prev=x, xprev_bf16=xc,
                                bf16_ld=eng.ld_in, seed=seed, offset=0, t_next=t_out)
 

@@ -295,8 +295,31 @@ class DenoiserEngine:
         return self.buf.tensor(self.state(B, True), "dout", (B * self.F, 32), BF16, zero=True)
 
     # ---- forward ----
-    def forward(self, B: int, train: bool = True, t_scalar: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Consumes xc(B) and t_buffer(B) (or a device scalar timestep); returns x0_hat fp32 [M, 32]."""
+    def weights_changed(self) -> None:
+        """Called by the native trainer after its fused optimizer (which writes the masters through raw pointers)."""
+        self._w_epoch = getattr(self, "_w_epoch", 0) + 1
+
+    def temb_table(self, n_timesteps: int) -> torch.Tensor:
+        """bf16 [n, d]: the time MLP (Linear·SiLU·Linear of the sinusoidal embedding, DESIGN D-1) of EVERY timestep,
+        evaluated once per set of weights.  Reverse sampling runs all windows at the same timestep, so a denoise step
+        only adds row t of this table (ibm_add_time_pos with t_row) instead of re-running two GEMMs per step."""
+        A, d = self.arena, self.d
+        key = (A._version_sum(), getattr(self, "_w_epoch", 0), n_timesteps)
+        if getattr(self, "_temb_key", None) != key:
+            n = n_timesteps
+            t = torch.arange(n, dtype=torch.int32, device=A.device)
+            emb, pre, act = (torch.empty(n, d, dtype=BF16, device=A.device) for _ in range(3))
+            table = torch.empty(n, d, dtype=BF16, device=A.device)
+            ops.timestep_embed(t, emb, d)
+            ops.gemm(emb, A.shadow_of("time_mlp.0.weight", (d, d)), pre, n, d, d, bias=A.master_of("time_mlp.0.bias"))
+            ops.act_fwd(pre, act, "silu")
+            ops.gemm(act, A.shadow_of("time_mlp.2.weight", (d, d)), table, n, d, d, bias=A.master_of("time_mlp.2.bias"))
+            self._temb_table, self._temb_key = table, key
+        return self._temb_table
+
+    def forward(self, B: int, train: bool = True, t_scalar: Optional[torch.Tensor] = None, t_count: int = 0) -> torch.Tensor:
+        """Consumes xc(B) and t_buffer(B) (or a device scalar timestep); returns x0_hat fp32 [M, 32].
+        ``t_count`` > 0 with ``t_scalar``: timesteps are < t_count and the time MLP comes from ``temb_table``."""
         A, d, F = self.arena, self.d, self.F
         M = B * F
         st = self.state(B, train)
@@ -304,15 +327,18 @@ class DenoiserEngine:
         xc = self.xc(B, train)
         h0 = T(st, "h0", (M, d), BF16)
         ops.gemm(xc, A.weight_operand("in_proj.weight", d, self.k_in), h0, M, d, self.k_in, bias=A.master_of("in_proj.bias"))
-        emb, pre, act, temb = (T(st, k, (B, d), BF16) for k in ("emb", "tpre", "tact", "temb"))
-        if t_scalar is not None:
-            ops.timestep_embed(t_scalar, emb, d, scalar=True)
+        if t_scalar is not None and t_count > 0 and not train:
+            ops.add_time_pos(h0, self.temb_table(t_count), A.master_of("pos_embedding", (F, d)), M, F, d, t_row=t_scalar)
         else:
-            ops.timestep_embed(self.t_buffer(B, train), emb, d)
-        ops.gemm(emb, A.shadow_of("time_mlp.0.weight", (d, d)), pre, B, d, d, bias=A.master_of("time_mlp.0.bias"))
-        ops.act_fwd(pre, act, "silu")
-        ops.gemm(act, A.shadow_of("time_mlp.2.weight", (d, d)), temb, B, d, d, bias=A.master_of("time_mlp.2.bias"))
-        ops.add_time_pos(h0, temb, A.master_of("pos_embedding", (F, d)), M, F, d)
+            emb, pre, act, temb = (T(st, k, (B, d), BF16) for k in ("emb", "tpre", "tact", "temb"))
+            if t_scalar is not None:
+                ops.timestep_embed(t_scalar, emb, d, scalar=True)
+            else:
+                ops.timestep_embed(self.t_buffer(B, train), emb, d)
+            ops.gemm(emb, A.shadow_of("time_mlp.0.weight", (d, d)), pre, B, d, d, bias=A.master_of("time_mlp.0.bias"))
+            ops.act_fwd(pre, act, "silu")
+            ops.gemm(act, A.shadow_of("time_mlp.2.weight", (d, d)), temb, B, d, d, bias=A.master_of("time_mlp.2.bias"))
+            ops.add_time_pos(h0, temb, A.master_of("pos_embedding", (F, d)), M, F, d)
         x = h0
         for l, layer in enumerate(self.layers):
             # inference re-uses one set of layer buffers; training keeps every layer's activations

@@ -220,8 +220,9 @@ def timestep_embed(t, out_bf16, dim, scalar=False):
     call("ibm_timestep_embed", _p(t), int(scalar), B, dim, _p(out_bf16), stream_ptr())
 
 
-def add_time_pos(h, temb, pos, M, F, d):
-    call("ibm_add_time_pos", _p(h), h.stride(0), _p(temb), temb.stride(0), _p(pos), M, F, d, stream_ptr())
+def add_time_pos(h, temb, pos, M, F, d, t_row=None):
+    """t_row (device int32[1]): temb is a per-timestep table and row t_row[0] is added to every window."""
+    call("ibm_add_time_pos", _p(h), h.stride(0), _p(temb), temb.stride(0), _p(pos), M, F, d, _p(t_row), stream_ptr())
 
 
 def add_time_pos_bwd(dh, dtemb, dpos, M, F, d):

@@ -488,6 +488,22 @@ def _aux_measurements(self, store, idx, pk, world):
         out["posterior_step"] = entry(_time_kernel(lambda: ops.posterior_step(rows, 32, x0.view(M, 30), eps.view(M, 30), tdev, d.coef_x0,
                                                                               d.coef_xt, d.sigma, M, x_prev=xp)), M * 480.0)
         del rows, lab, g16buf, eps, xt, xp
+        # the same two kernels over an analysis-sized stream (65 536 windows = 3.3 M rows, 786 MB forward): the fixed costs of
+        # a 40 us launch (ramp-up, last-block fp64 reduction) are amortised, which is the regime of the analyze pass
+        Bs = 65536
+        Ms = Bs * F
+        rows = torch.randn(Ms, 32, device=dev)
+        lab = torch.randn(Bs, F, 30, device=dev) * 5
+        outs, labs = _views30(rows.view(Bs, F, 32)), _views30(lab)
+        g16buf = torch.zeros(Ms, 32, dtype=torch.bfloat16, device=dev)
+        g16 = _views30(g16buf.view(Bs, F, 32))
+        e = entry(_time_kernel(lambda: ops.regression_loss_fwd(outs, labs, self.weights, result=res), iters=10), Ms * 240.0)
+        e["rows"] = Ms
+        out["loss_fwd_stream"] = e
+        e = entry(_time_kernel(lambda: ops.regression_loss_bwd(outs, labs, self.weights, g16), iters=10), Ms * 300.0)
+        e["rows"] = Ms
+        out["loss_bwd_bf16_stream"] = e
+        del rows, lab, g16buf, outs, labs, g16
         # per-shape table of the GEMM launches of one training step (from profile_gemms)
         shapes = {}
         for ms, fl, shp in getattr(self, "last_gemm_records", []):

@@ -206,6 +206,11 @@ def test_timestep_embedding_and_time_pos():
     ops.add_time_pos(hd, temb.cuda(), pos.cuda(), B * F, F, d)
     want = (h.float().view(B, F, d) + temb.float().unsqueeze(1) + pos.unsqueeze(0)).view(B * F, d)
     assert torch.equal(hd.cpu(), want.to(torch.bfloat16))
+    # table mode (reverse sampling): every window adds row t_row[0] of a per-timestep table
+    hd2 = h.cuda()
+    ops.add_time_pos(hd2, temb.cuda(), pos.cuda(), B * F, F, d, t_row=torch.tensor([17], dtype=torch.int32, device="cuda"))
+    want2 = (h.float().view(B, F, d) + temb[17].float().view(1, 1, d) + pos.unsqueeze(0)).view(B * F, d)
+    assert torch.equal(hd2.cpu(), want2.to(torch.bfloat16))
     dh = torch.randn(B * F, d, generator=g).to(torch.bfloat16)
     dtemb = torch.empty(B, d, dtype=torch.bfloat16, device="cuda")
     dpos = torch.zeros(F, d, device="cuda")

@@ -406,6 +406,11 @@ def test_sampling_graph_equals_eager():
     assert torch.isfinite(a).all()
     torch.testing.assert_close(a, b, rtol=0, atol=0)
     torch.testing.assert_close(a, c, rtol=0, atol=0)
+    # the per-timestep time-MLP table (evaluated once per set of weights) gives the bits of the per-step evaluation
+    gd2 = GaussianDiffusion(num_timesteps=20, device="cuda")
+    gd2.use_temb_table = False
+    d = gd2.sample(m, B, seed=5, use_graph=False)
+    torch.testing.assert_close(a, d, rtol=0, atol=0)
 
 
 # ---------------------------------------------------------------------------------------------------
