@@ -31,6 +31,8 @@ cap ln_fwd layernorm_fwd python tools/kernel_probe.py ln_fwd
 cap ln_bwd layernorm_bwd python tools/kernel_probe.py ln_bwd
 cap loss_fwd loss_rows python tools/kernel_probe.py loss_fwd
 cap loss_bwd loss_rows python tools/kernel_probe.py loss_bwd
+cap attn_fwd_t200 attn_fwd_long python tools/kernel_probe.py attn_fwd_t200
+cap ln_fwd_d108 layernorm_fwd_narrow python tools/kernel_probe.py ln_fwd_d108
 python tools/kernel_probe.py > $O/${TAG}_kernel_probe.log 2>&1
 python tools/gemm_probe.py > $O/${TAG}_gemm_probe.log 2>&1
 ls -la $O | grep ${TAG} | wc -l
