@@ -76,50 +76,65 @@ def feedforward_train_leg(dev, world: int, steps: int = 20) -> dict:
     return out
 
 
-def groundlink_train_leg(dev, world: int, steps: int = 10, B: int = 1024, T: int = 50) -> dict:
-    """Groundlink (Groundlink.py:20-156) training step through the drop-in module + fused loss: implicit-GEMM temporal
-    CNN + per-frame MLP, forward + backward, 110.0 MFLOP/window forward at T=50, ~3x for the step."""
+def groundlink_train_leg(dev, world: int, steps: int = 10, B: int = 4096, T: int = 50) -> dict:
+    """Groundlink (Groundlink.py:20-156) training: implicit-GEMM temporal CNN + per-frame MLP, forward + backward with
+    Dropout(0.2) active, 110.0 MFLOP/window forward at T=50, ~3x for the step.  Two paths over the same
+    kernels: the native ``Trainer`` step (window store -> padded-row packer -> fused loss -> fused RMSprop) and the reference's
+    loop shape (module forward -> evaluator -> loss.backward() -> torch.optim.RMSprop.step())."""
     import argparse
+    from .data.window_store import WindowStore
+    from .keys import LOSS_QUANTITIES, MODEL_INPUT_ORDER
     from .loss.RegressionLossEvaluator import RegressionLossEvaluator
     from .models.Groundlink import Groundlink
+    from .trainer import Trainer
     torch.manual_seed(0)
-    m = Groundlink(23, 12, 10, "all_frames").to(dev)
-    m.train()
+    out = {"batch": B, "frames": T}
+
+    def timed(step):
+        for _ in range(3):
+            step()
+        e0, e1 = _events()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"windows_per_s": world * B / (ms * 1e-3), "ms_per_step": ms, "tflops_model": 3 * 110.016e6 * B / (ms * 1e-3) / 1e12}
+
+    store = WindowStore.synthetic(2 * B, T, 1, 177, "all_frames", seed=5, device=dev)
+    idx = store.shard(0, 1)
+    batches = [idx[:B], idx[B:2 * B]]
+    m = Groundlink(23, 12, 10, "all_frames").to(dev).train()
+    tr = Trainer(m, opt_type="rmsprop", lr=1e-4)
+    it = [0]
+
+    def native():
+        it[0] += 1
+        tr.train_step(store, batches[it[0] & 1])
+
+    out["native_trainer"] = timed(native)
+    del tr, m
+
+    m = Groundlink(23, 12, 10, "all_frames").to(dev).train()
     opt = torch.optim.RMSprop(m.parameters(), lr=1e-4)
     ev = RegressionLossEvaluator(dataset=None, split="train", device=str(dev))
     args = argparse.Namespace(predict_grf_components=list(range(6)), predict_cop_components=list(range(6)),
                               predict_moment_components=list(range(6)), predict_wrench_components=list(range(12)))
-    g = torch.Generator(device=dev).manual_seed(5)
-    widths = {"pos": 23, "vel": 23, "acc": 23, "rootLinearVelInRootFrame": 3, "rootAngularVelInRootFrame": 3,
-              "rootLinearAccInRootFrame": 3, "rootAngularAccInRootFrame": 3, "jointCentersInRootFrame": 36,
-              "rootPosHistoryInRootFrame": 30, "rootEulerHistoryInRootFrame": 30}
-    x = {k: torch.randn(B, T, c, device=dev, generator=g) for k, c in widths.items()}
-    from .keys import OutputDataKeys as O
-    labels = {O.GROUND_CONTACT_COPS_IN_ROOT_FRAME: torch.randn(B, T, 6, device=dev, generator=g),
-              O.GROUND_CONTACT_FORCES_IN_ROOT_FRAME: torch.randn(B, T, 6, device=dev, generator=g) * 10,
-              O.GROUND_CONTACT_TORQUES_IN_ROOT_FRAME: torch.randn(B, T, 6, device=dev, generator=g),
-              O.GROUND_CONTACT_WRENCHES_IN_ROOT_FRAME: torch.randn(B, T, 12, device=dev, generator=g)}
+    widths = [23, 23, 23, 3, 3, 3, 3, 36, 30, 30]
+    x = dict(zip(MODEL_INPUT_ORDER, [t.contiguous() for t in torch.split(store.pack_f32(batches[0]), widths, dim=-1)]))
+    labels = dict(zip(LOSS_QUANTITIES, [t.contiguous() for t in torch.split(store.labels(batches[0]), [6, 6, 6, 12], dim=-1)]))
 
-    def step():
+    def module_loop():
         opt.zero_grad()
         loss = ev(x, m(x), labels, [], [], args, compute_report=False)
         loss.backward()
         opt.step()
         ev._reset_lists()
 
-    for _ in range(3):
-        step()
-    e0, e1 = _events()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"windows_per_s": world * B / (ms * 1e-3), "ms_per_step": ms, "batch": B, "frames": T,
-            "tflops_model": 3 * 110.016e6 * B / (ms * 1e-3) / 1e12,
-            "note": "reference loop shape (module forward -> evaluator -> loss.backward() -> torch.optim.RMSprop.step())"}
+    out["module_loop"] = timed(module_loop)
+    return out
 
 
 def transformer_analyze_leg(dev, world: int, pk: dict, B: int = 2048, T: int = 200, n_batches: int = 6) -> dict:
