@@ -46,17 +46,29 @@ def split30(x: torch.Tensor) -> Dict[str, torch.Tensor]:
 
 def feedforward_forward(sd: Mapping[str, torch.Tensor], inputs: Mapping[str, torch.Tensor],
                         activation: str, num_output_frames: int,
-                        batchnorm: bool = False, dropout: bool = False) -> Dict[str, torch.Tensor]:
+                        batchnorm: bool = False, dropout: bool = False, training: bool = False,
+                        new_stats: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """``training`` with ``batchnorm``: nn.BatchNorm1d's training mode (FeedForward…py:71-72) — normalise with the batch
+    mean / biased batch variance; the running statistics would become (1-0.1)·running + 0.1·(mean, UNBIASED variance),
+    returned through ``new_stats`` (keyed like the state_dict) instead of being written into ``sd``."""
     x = concat_inputs(inputs)
     B = x.shape[0]
     x = x.reshape(B, -1)
     # nn.Sequential positions: per layer [Dropout?][BatchNorm1d?] Linear [act]
     lin_keys = sorted({int(k.split(".")[1]) for k in sd if k.endswith(".weight") and sd[k].dim() == 2})
     for li, pos in enumerate(lin_keys):
-        if batchnorm:  # eval-mode BN on the layer INPUT (FeedForward…py:71-72)
+        if batchnorm:  # BN on the layer INPUT (FeedForward…py:71-72)
             p = pos - 1
             rm, rv = sd[f"net.{p}.running_mean"], sd[f"net.{p}.running_var"]
-            x = (x - rm) / torch.sqrt(rv + 1e-5) * sd[f"net.{p}.weight"] + sd[f"net.{p}.bias"]
+            if training:
+                mean, var = x.mean(0), x.var(0, unbiased=False)
+                if new_stats is not None:
+                    n = x.shape[0]
+                    new_stats[f"net.{p}.running_mean"] = (0.9 * rm + 0.1 * mean).detach()
+                    new_stats[f"net.{p}.running_var"] = (0.9 * rv + 0.1 * var * n / (n - 1)).detach()
+                x = (x - mean) / torch.sqrt(var + 1e-5) * sd[f"net.{p}.weight"] + sd[f"net.{p}.bias"]
+            else:
+                x = (x - rm) / torch.sqrt(rv + 1e-5) * sd[f"net.{p}.weight"] + sd[f"net.{p}.bias"]
         x = x @ sd[f"net.{pos}.weight"].t() + sd[f"net.{pos}.bias"]
         if li < len(lin_keys) - 1:
             x = _ACT[activation](x)

@@ -59,6 +59,40 @@ def test_feedforward_golden(golden, name):
             np.testing.assert_allclose(strided_sample(p.grad).numpy(), g[f"{name}/grad_sample/{k}"], rtol=1e-4, atol=1e-7)
 
 
+@pytest.mark.parametrize("name", ["sigmoid_b16", "relu_b300"])
+def test_feedforward_batchnorm_training_golden(golden, name):
+    """Oracle BatchNorm1d in TRAINING mode (batch statistics, running-stat update with the unbiased variance) against the
+    imported reference: outputs, loss, every parameter gradient and the updated buffers (tests/golden/ff_bn_train.npz)."""
+    g = golden("ff_bn_train.npz")
+    act = name.split("_")[0]
+    D, T, s, B, seed, iseed, lseed = (int(v) for v in g[f"{name}/meta"])
+    hidden = [int(v) for v in g[f"{name}/hidden"]]
+    sd = seeded_state_dict(ff_shapes(D, T, s, hidden, "all_frames", True), seed)
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+              for k, v in sd.items()}
+    F = T // s
+    inputs = seeded_inputs(B, F, D, s * 3, iseed)
+    _, labels = seeded_out_labels(B, F, lseed)
+    stats = {}
+    out = om.feedforward_forward(params, inputs, act, F, batchnorm=True, training=True, new_stats=stats)
+    for k, v in out.items():
+        np.testing.assert_allclose(v.detach().numpy(), g[f"{name}/out/{k}"], rtol=2e-4, atol=2e-5)
+    res = ol.regression_loss(out, labels, *ALL)
+    np.testing.assert_allclose(float(res["loss"].detach()), float(g[f"{name}/loss"]), rtol=1e-5)
+    res["loss"].backward()
+    for k, p in params.items():
+        if getattr(p, "grad", None) is not None:
+            want = g[f"{name}/grad_sample/{k}"]
+            # bias-like gradients upstream of a training-mode BatchNorm are sums of cancelling terms (even two fp32 CPU
+            # evaluations differ by a few % there, e.g. -7.42e-6 vs -7.66e-6): absolute bar from the companion weight gradient
+            scale = np.abs(want).max()
+            if k.endswith(".bias"):
+                scale = max(scale, np.abs(g[f"{name}/grad_sample/{k[:-4]}weight"]).max())
+            np.testing.assert_allclose(strided_sample(p.grad).numpy(), want, rtol=2e-3, atol=2e-4 * scale)
+    for k, v in stats.items():
+        np.testing.assert_allclose(v.numpy(), g[f"{name}/buffer/{k}"], rtol=1e-5, atol=1e-6)
+
+
 def groundlink_shapes(D=23, J=12, H=10):
     c = [3 * D + 12 + 3 * J + 6 * H, 128, 128, 256, 256]
     shapes = {}
