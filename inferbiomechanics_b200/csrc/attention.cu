@@ -12,6 +12,8 @@
 // accumulate) with an online softmax; one CTA = 4 warps = 64 query rows.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ibm {
@@ -389,31 +391,34 @@ attn_fwd_pipe_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __n
 // 256 x 256, i.e. 61 % -> 96 % useful tensor work).  CTAs are persistent over the windows of one head with a two-stage
 // cp.async ring for K/V, Q fragments come straight from global memory, scores stay in registers (online softmax over
 // 64-key chunks, ex2.approx), fragments via ldmatrix.
-template <int HD, int NJ, int MAXT, int MINB>
+template <int HQ, int HV, int NJ, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 attn_fwd_long_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
                      const __nv_bfloat16* __restrict__ v, int64_t ldv, __nv_bfloat16* __restrict__ o, int64_t ldo, int T,
                      int H, int64_t n_win, float scale_log2) {
-  constexpr int LD = HD + kPad;
-  constexpr int CPR = HD / 8;
+  constexpr int LDK = HQ + kPad, LDV = HV + kPad;      // HQ = width of q/k rows, HV = width of v/o rows (equal for MHA heads)
+  constexpr int CPRK = HQ / 8, CPRV = HV / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int nthreads = blockDim.x;
   const int Tp = (nthreads >> 5) * 16;                  // rows covered by the CTA's warps: (T + 15) & ~15
-  const int tile = Tp * LD;
+  const int tileK = Tp * LDK, tileV = Tp * LDV;
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(smem_attn);          // [2 stages][K | V]
   const int h = blockIdx.x % H;
   const int64_t cta = blockIdx.x / H, ctas = gridDim.x / H;
-  for (int i = threadIdx.x; i < 4 * tile / 8; i += nthreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 2 * (tileK + tileV) / 8; i += nthreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();                                      // rows >= T stay zero for the whole kernel
   auto load_item = [&](int64_t win, int stage) {
     const int64_t row0 = win * T;
-    __nv_bfloat16* Ks = base + stage * 2 * tile;
-    const __nv_bfloat16* ksrc = k + row0 * ldk + h * HD;
-    const __nv_bfloat16* vsrc = v + row0 * ldv + h * HD;
-    for (int i = threadIdx.x; i < T * CPR; i += nthreads) {
-      const int r = i / CPR, c = (i - r * CPR) * 8;
-      cp_async16(Ks + r * LD + c, ksrc + (int64_t)r * ldk + c);
-      cp_async16(Ks + tile + r * LD + c, vsrc + (int64_t)r * ldv + c);
+    __nv_bfloat16* Ks = base + stage * (tileK + tileV);
+    const __nv_bfloat16* ksrc = k + row0 * ldk + h * HQ;
+    const __nv_bfloat16* vsrc = v + row0 * ldv + h * HV;
+    for (int i = threadIdx.x; i < T * CPRK; i += nthreads) {
+      const int r = i / CPRK, c = (i - r * CPRK) * 8;
+      cp_async16(Ks + r * LDK + c, ksrc + (int64_t)r * ldk + c);
+    }
+    for (int i = threadIdx.x; i < T * CPRV; i += nthreads) {
+      const int r = i / CPRV, c = (i - r * CPRV) * 8;
+      cp_async16(Ks + tileK + r * LDV + c, vsrc + (int64_t)r * ldv + c);
     }
   };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -427,13 +432,13 @@ attn_fwd_long_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __n
     cp_async_commit();
     // this warp's 16 query rows as A fragments of m16n8k16, straight from global (every element is read exactly once;
     // issued before the wait so the latency overlaps the K/V arrival and the other CTA's math)
-    uint32_t qa[HD / 16][4];
+    uint32_t qa[HQ / 16][4];
     {
-      const __nv_bfloat16* q0 = q + (win * T + qr) * ldq + h * HD + 2 * t;
+      const __nv_bfloat16* q0 = q + (win * T + qr) * ldq + h * HQ + 2 * t;
       const __nv_bfloat16* q1 = q0 + 8 * ldq;
       const bool ok0 = qr < T, ok1 = qr + 8 < T;
 #pragma unroll
-      for (int kk = 0; kk < HD / 16; ++kk) {
+      for (int kk = 0; kk < HQ / 16; ++kk) {
         qa[kk][0] = ok0 ? __ldg(reinterpret_cast<const unsigned int*>(q0 + kk * 16)) : 0u;
         qa[kk][1] = ok1 ? __ldg(reinterpret_cast<const unsigned int*>(q1 + kk * 16)) : 0u;
         qa[kk][2] = ok0 ? __ldg(reinterpret_cast<const unsigned int*>(q0 + kk * 16 + 8)) : 0u;
@@ -442,38 +447,41 @@ attn_fwd_long_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __n
     }
     cp_async_wait<1>();
     __syncthreads();
-    const __nv_bfloat16* Ks = base + st * 2 * tile;
-    const __nv_bfloat16* Vs = Ks + tile;
+    const __nv_bfloat16* Ks = base + st * (tileK + tileV);
+    const __nv_bfloat16* Vs = Ks + tileK;
 
-    float oacc[HD / 8][4];
+    float oacc[HV / 8][4];
 #pragma unroll
-    for (int j = 0; j < HD / 8; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
+    for (int j = 0; j < HV / 8; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;      // running max of the raw scores, running sums
-    for (int kb = 0; kb < T; kb += NJ * 8) {
+    // one chunk of NJ*8 keys.  FULL chunks (every key valid) compile without the per-block predicates and the -inf
+    // masking; only the last, ragged chunk of a window takes the general path.
+    auto do_chunk = [&](const int kb, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
       const int Tl = T - kb;                            // keys left from this chunk on (may exceed the chunk)
       float s[NJ][4];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      const __nv_bfloat16* bp = Ks + (kb + (lane & 7)) * LD + (lane >> 3) * 8;
+      const __nv_bfloat16* bp = Ks + (kb + (lane & 7)) * LDK + (lane >> 3) * 8;
 #pragma unroll
-      for (int k2 = 0; k2 < HD / 32; ++k2) {
+      for (int k2 = 0; k2 < HQ / 32; ++k2) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          if (j * 8 < Tl) {
+          if (FULL || j * 8 < Tl) {
             uint32_t b[4];
-            ldsm_x4(b, bp + j * 8 * LD + k2 * 32);
+            ldsm_x4(b, bp + j * 8 * LDK + k2 * 32);
             mma16816(s[j], qa[2 * k2], b[0], b[1]);
             mma16816(s[j], qa[2 * k2 + 1], b[2], b[3]);
           }
         }
       }
-      if constexpr ((HD / 16) % 2 == 1) {
-        constexpr int kk = HD / 16 - 1;
+      if constexpr ((HQ / 16) % 2 == 1) {
+        constexpr int kk = HQ / 16 - 1;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          if (j * 8 < Tl) {
+          if (FULL || j * 8 < Tl) {
             uint32_t b0, b1;
-            ldsm_x2(b0, b1, Ks + (kb + j * 8 + (lane & 7)) * LD + kk * 16 + ((lane >> 3) & 1) * 8);
+            ldsm_x2(b0, b1, Ks + (kb + j * 8 + (lane & 7)) * LDK + kk * 16 + ((lane >> 3) & 1) * 8);
             mma16816(s[j], qa[kk], b0, b1);
           }
         }
@@ -482,10 +490,10 @@ attn_fwd_long_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __n
       float mx0 = m0, mx1 = m1;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        if (j * 8 + 8 <= Tl) {
+        if (FULL || j * 8 + 8 <= Tl) {
           mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
           mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
-        } else if (j * 8 < Tl) {
+        } else if (FULL || j * 8 < Tl) {
           const int key = j * 8 + 2 * t;
 #pragma unroll
           for (int e = 0; e < 4; ++e) s[j][e] = (key + (e & 1) < Tl) ? s[j][e] : -INFINITY;
@@ -501,7 +509,7 @@ attn_fwd_long_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __n
       float r0 = 0.f, r1 = 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        if (j * 8 < Tl) {
+        if (FULL || j * 8 < Tl) {
           s[j][0] = ex2(fmaf(s[j][0], scale_log2, -o0)); s[j][1] = ex2(fmaf(s[j][1], scale_log2, -o0));
           s[j][2] = ex2(fmaf(s[j][2], scale_log2, -o1)); s[j][3] = ex2(fmaf(s[j][3], scale_log2, -o1));
           r0 += s[j][0] + s[j][1];
@@ -513,26 +521,37 @@ attn_fwd_long_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __n
       l0 = l0 * c0 + r0;
       l1 = l1 * c1 + r1;
 #pragma unroll
-      for (int j = 0; j < HD / 8; ++j) { oacc[j][0] *= c0; oacc[j][1] *= c0; oacc[j][2] *= c1; oacc[j][3] *= c1; }
+      for (int j = 0; j < HV / 8; ++j) { oacc[j][0] *= c0; oacc[j][1] *= c0; oacc[j][2] *= c1; oacc[j][3] *= c1; }
 #pragma unroll
       for (int kk = 0; kk < NJ / 2; ++kk) {
-        if (kk * 16 < Tl) {
+        if (FULL || kk * 16 < Tl) {
           uint32_t pa[4];
           pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
           pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
           pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
           pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-          mma_ab16<HD, LD>(oacc, pa, Vs + (kb + kk * 16) * LD, lane);
+          if constexpr (HV >= 16) {
+            mma_ab16<HV, LDV>(oacc, pa, Vs + (kb + kk * 16) * LDV, lane);
+          } else {                                        // 8-wide values (the CoM blend): one n = 8 block
+            uint32_t b0, b1;
+            ldsm_x2_trans(b0, b1, Vs + (kb + kk * 16 + (lane & 15)) * LDV);
+            mma16816(oacc[0], pa, b0, b1);
+          }
         }
       }
+    };
+    {
+      int kb = 0;
+      for (; kb + NJ * 8 <= T; kb += NJ * 8) do_chunk(kb, std::true_type{});
+      if (kb < T) do_chunk(kb, std::false_type{});
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-    __nv_bfloat16* out0 = o + (win * T + qr) * ldo + h * HD + 2 * t;
+    __nv_bfloat16* out0 = o + (win * T + qr) * ldo + h * HV + 2 * t;
     __nv_bfloat16* out1 = out0 + 8 * ldo;
 #pragma unroll
-    for (int j = 0; j < HD / 8; ++j) {
+    for (int j = 0; j < HV / 8; ++j) {
       if (qr < T) *reinterpret_cast<uint32_t*>(out0 + j * 8) = pack_bf16x2(oacc[j][0] * inv0, oacc[j][1] * inv0);
       if (qr + 8 < T) *reinterpret_cast<uint32_t*>(out1 + j * 8) = pack_bf16x2(oacc[j][2] * inv1, oacc[j][3] * inv1);
     }
@@ -771,21 +790,21 @@ static int launch_fwd_pipe(const void* q, int64_t ldq, const void* k, int64_t ld
   return IBM_OK;
 }
 
-template <int HD>
+template <int HQ, int HV>
 static int launch_fwd_long(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                            int64_t n_win, int T, int H, float scale, cudaStream_t s) {
   const int warps = (T + 15) / 16;
   const int threads = warps * 32;
-  const size_t smem = (size_t)4 * ((T + 15) & ~15) * (HD + kPad) * 2;
+  const size_t smem = (size_t)2 * ((T + 15) & ~15) * ((HQ + kPad) + (HV + kPad)) * 2;
   // <= 208 frames (13 warps): 32-key chunks keep the kernel under 80 registers so that TWO CTAs share an SM (26 warps
   // instead of 13 hide the HMMA / MUFU latencies; ncu: 20 % warps active, 29 % fixed-latency stalls with one);
   // longer windows: one CTA of up to 16 warps, 64-key chunks
   const bool two = warps <= 13 && 2 * smem + 4096 <= 227 * 1024 && getenv("IBM_ATTN_LONG_ONE") == nullptr;
-  auto kern = two ? attn_fwd_long_kernel<HD, 4, 416, 2> : attn_fwd_long_kernel<HD, 8, 512, 1>;
+  auto kern = two ? attn_fwd_long_kernel<HQ, HV, 4, 416, 2> : attn_fwd_long_kernel<HQ, HV, 8, 512, 1>;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    IBM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_long_kernel<HD, 4, 416, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IBM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_long_kernel<HD, 8, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_long_kernel<HQ, HV, 4, 416, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_long_kernel<HQ, HV, 8, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   int per_sm = 0;
@@ -862,16 +881,18 @@ extern "C" int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int6
     if (hd_qk == 32) return attn::launch_fwd_pipe<32>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
   }
   // long windows (64 < T <= 256; the T = 200 analysis stream): one CTA per (window, head), K/V fetched once, persistent
-  if (T > 64 && hd_qk == hd_v && ldo % 2 == 0) {
+  if (T > 64 && ldo % 2 == 0) {
     static int use_long = -1;
     if (use_long < 0) {
       const char* e = getenv("IBM_ATTN_LONG");
       use_long = (e && e[0] == '0') ? 0 : 1;           // IBM_ATTN_LONG=0 keeps the one-shot kernel (A/B measurements)
     }
     if (use_long) {
-      if (hd_qk == 64) return attn::launch_fwd_long<64>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
-      if (hd_qk == 48) return attn::launch_fwd_long<48>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
-      if (hd_qk == 32) return attn::launch_fwd_long<32>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+      if (hd_qk == 64 && hd_v == 64) return attn::launch_fwd_long<64, 64>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+      if (hd_qk == 48 && hd_v == 48) return attn::launch_fwd_long<48, 48>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+      if (hd_qk == 32 && hd_v == 32) return attn::launch_fwd_long<32, 32>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+      // the CoM blend of the TransformerBaseline (SimpleAttention, TransformerBaseline.py:51-70): 112-wide q/k, 8-wide values
+      if (hd_qk == 112 && hd_v == 8) return attn::launch_fwd_long<112, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
     }
   }
   if (hd_qk == 64 && hd_v == 64) return attn::launch_fwd<64, 64>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);

@@ -328,10 +328,12 @@ def test_attention_backward(n_win, T, H, hd):
     assert torch.equal(dqkv, dqkv2)
 
 
-def test_simple_attention_head():
-    """SimpleAttention (TransformerBaseline.py:51-70): unscaled scores, value dim 3 (padded to 8)."""
+@pytest.mark.parametrize("n_win,T", [(2, 200), (3, 50), (600, 200), (2, 77), (1, 256)])
+def test_simple_attention_head(n_win, T):
+    """SimpleAttention (TransformerBaseline.py:51-70): unscaled scores, value dim 3 (padded to 8).  T > 64 runs the
+    persistent long-window kernel (one CTA per window, 112-wide q/k, 8-wide values), T <= 64 the one-shot kernel."""
     from inferbiomechanics_b200 import ops
-    n_win, T, d = 2, 200, 112
+    d = 112
     g = torch.Generator().manual_seed(9)
     q = torch.zeros(n_win * T, d, dtype=torch.bfloat16); k = torch.zeros_like(q)
     q[:, :108] = (torch.randn(n_win * T, 108, generator=g) * 0.3).to(torch.bfloat16)
