@@ -87,6 +87,13 @@ int ibm_pack_inputs(const void* const* h_src, const int32_t* h_widths, int32_t n
                     int32_t F, float* out_f32, void* out_bf16, int64_t bf16_frame_stride,
                     int64_t bf16_win_extra, int64_t bf16_col0, void* stream);
 
+/* TransformerBaseline input pack (src/models/TransformerBaseline.py:108-126): the reference concatenates n_src
+ * channel-major tensors (B, C_i, T) on dim 1, transposes to (B, T, C) and appends the learned temporal embedding
+ * emb[t, 0:E] (expand + cat, not add).  Here: fp32 sources -> bf16 rows [B*T, ld], row b*T+t = [src_0[b,:,t] | … |
+ * emb[t,:] | 0…], ld %% 8 == 0, ld >= sum C_i + E.  n_src <= 8.  Bit-exact RNE bf16 of the fp32 values. */
+int ibm_pack_channel_major(const void* const* srcs, const int32_t* channels, int32_t n_src, int64_t B, int32_t T,
+                           const float* emb, int32_t E, void* out_bf16, int64_t ld, void* stream);
+
 /* Label rows (Dataset.py:216-261): raw first-pass per-frame [cop 3nb | force 3nb | torque 3nb |
  * wrench 6nb] in the SUBJECT's body order → rows30 in the DATASET's body order, force/torque/
  * wrench divided by the subject mass (IEEE fp32 division), absent bodies → 0.

@@ -24,6 +24,7 @@ SIGNATURES = {
     "ibm_window_valid_mask": [P, P, P, P, _i64, _i32, _i32, P, P],
     "ibm_pack_windows": [P, _i64, _i32, P, _i64, _i32, _i32, P, P, _i64, _i64, _i64, P],
     "ibm_pack_inputs": [P, P, _i32, _i64, _i32, P, P, _i64, _i64, _i64, P],
+    "ibm_pack_channel_major": [P, P, _i32, _i64, _i32, P, _i32, P, _i64, P],
     "ibm_pack_labels": [P, _i64, _i32, P, P, P, _i64, _i32, _i32, _i32, P, _i64, P],
     "ibm_regression_loss_fwd": [P, P, P, P, _i64, _i64, P, _f, P, P, P],
     "ibm_regression_loss_bwd": [P, P, P, P, _i64, _i64, P, _f, P, P, P, _i32, P],

@@ -188,6 +188,80 @@ extern "C" int ibm_pack_labels(const float* raw, int64_t raw_ld, int32_t nb, con
   return IBM_OK;
 }
 
+// ---- channel-major windows -> frame rows (TransformerBaseline.forward, TransformerBaseline.py:108-126) ----------------
+// The transformer's inputs arrive as (B, C_i, T) tensors (channel-major, concatenated on dim 1 and transposed by the
+// reference); the layer stack wants bf16 rows [B*T, ld] with the learned temporal embedding of frame t appended.  One
+// block = 64 frames of one window: the (C, 64) slab goes through shared memory so that both the reads (along T) and
+// the writes (along the row) are coalesced.
+namespace ibm {
+constexpr int kCmFrames = 64;
+struct ChanSrc {
+  const float* ptr[8];
+  int32_t ch[8];
+  int32_t first[9];      // first output column of each source
+  int32_t n;
+};
+__global__ void __launch_bounds__(kThreads)
+pack_channel_major_kernel(ChanSrc src, int T, const float* __restrict__ emb, int E, __nv_bfloat16* __restrict__ out,
+                          long long ld) {
+  extern __shared__ float tile[];                       // [C][kCmFrames + 1]
+  const long long b = blockIdx.x;
+  const int t0 = blockIdx.y * kCmFrames;
+  const int nt = min(kCmFrames, T - t0);
+  const int C = src.first[src.n];
+  for (int s = 0; s < src.n; ++s) {
+    const float* p = src.ptr[s] + b * (long long)src.ch[s] * T + t0;
+    for (int i = threadIdx.x; i < src.ch[s] * kCmFrames; i += kThreads) {
+      const int c = i / kCmFrames, f = i - c * kCmFrames;
+      if (f < nt) tile[(src.first[s] + c) * (kCmFrames + 1) + f] = __ldg(p + (long long)c * T + f);
+    }
+  }
+  __syncthreads();
+  const int pairs = (int)(ld >> 1);
+  for (int i = threadIdx.x; i < nt * pairs; i += kThreads) {
+    const int f = i / pairs, c = 2 * (i - f * pairs);
+    float v[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int cc = c + j;
+      v[j] = cc < C ? tile[cc * (kCmFrames + 1) + f] : (cc < C + E ? __ldg(emb + (long long)(t0 + f) * E + (cc - C)) : 0.f);
+    }
+    *reinterpret_cast<uint32_t*>(out + (b * T + t0 + f) * ld + c) = pack_bf16x2(v[0], v[1]);
+  }
+}
+}  // namespace ibm
+
+extern "C" int ibm_pack_channel_major(const void* const* h_src, const int32_t* h_channels, int32_t n_src, int64_t B, int32_t T,
+                                      const float* emb, int32_t E, void* out_bf16, int64_t ld, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(h_src && h_channels && n_src > 0 && n_src <= 8 && B > 0 && T > 0 && out_bf16, "pack_channel_major: bad argument");
+  IBM_CHECK_ARG(E >= 0 && (E == 0 || emb), "pack_channel_major: embedding width without a table");
+  ChanSrc src;
+  src.n = n_src;
+  src.first[0] = 0;
+  for (int i = 0; i < 8; ++i) {
+    src.ptr[i] = i < n_src ? static_cast<const float*>(h_src[i]) : nullptr;
+    src.ch[i] = i < n_src ? h_channels[i] : 0;
+    IBM_CHECK_ARG(i >= n_src || (src.ptr[i] && src.ch[i] > 0), "pack_channel_major: null source %d", i);
+    src.first[i + 1] = src.first[i] + src.ch[i];
+  }
+  const int C = src.first[n_src];
+  IBM_CHECK_ARG(ld % 8 == 0 && ld >= C + E && C <= 256, "pack_channel_major: ld must be a multiple of 8 and >= C + E (C <= 256)");
+  IBM_CHECK_ARG(B < (1ll << 31), "pack_channel_major: too many windows for one launch");
+  const size_t smem = (size_t)C * (kCmFrames + 1) * sizeof(float);
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    IBM_CHECK_CUDA(cudaFuncSetAttribute(pack_channel_major_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid((unsigned)B, (unsigned)ceil_div(T, kCmFrames));
+  pack_channel_major_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(src, T, emb, E,
+                                                                                         static_cast<__nv_bfloat16*>(out_bf16), ld);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
 extern "C" int ibm_pack_inputs(const void* const* h_src, const int32_t* h_widths, int32_t n_src, int64_t n_rows, int32_t F,
                                float* out_f32, void* out_bf16, int64_t bf16_frame_stride, int64_t bf16_win_extra,
                                int64_t bf16_col0, void* stream) {

@@ -144,7 +144,7 @@ class TransformerBaseline(nn.Module):
             H, hp, dp, fp = self.num_heads, P["hp"], P["dp"], P["fp"]
             z = lambda c, dt=BF16: torch.zeros(M, c, dtype=dt, device=dev)
             self._bufs[M] = dict(xa=z(dp), xb=z(dp), qkv=z(3 * H * hp), o=z(H * hp), s=z(dp), x1=z(dp), h=z(fp), q=z(dp), k=z(dp),
-                                 v=z(8), blend=z(8), out=z(12, torch.float32), x32=z(dp, torch.float32))
+                                 v=z(8), blend=z(8), out=z(12, torch.float32))
         return self._bufs[M]
 
     # ---- host-fed stream (BASELINE configs[4]: the analysis pass over a long window stream) -----------------
@@ -217,19 +217,15 @@ class TransformerBaseline(nn.Module):
         d, dp, H, hp = P["d"], P["dp"], self.num_heads, P["hp"]
         batch_size = x[InputDataKeys.POS].size(0)
         # (q, dq, ddq, com_pos, com_vel, com_acc) per timestep; inputs are (B, C, T) → (B, T, C)   (…:108-116)
-        parts = [x[k].to(dev, torch.float32) for k in (InputDataKeys.POS, InputDataKeys.VEL, InputDataKeys.ACC, InputDataKeys.COM_POS,
-                                                       InputDataKeys.COM_VEL, InputDataKeys.COM_ACC)]
+        parts = [x[k].to(dev, torch.float32).contiguous() for k in (InputDataKeys.POS, InputDataKeys.VEL, InputDataKeys.ACC,
+                                                                    InputDataKeys.COM_POS, InputDataKeys.COM_VEL, InputDataKeys.COM_ACC)]
         T = parts[0].size(2)
         assert T == self.window_size, "TemporalEmbedding.expand needs T == window_size (…:121-123)"
         M = batch_size * T
         b = self._act_buffers(M, dev, P)
-        x32 = b["x32"].view(batch_size, T, dp)
-        c0 = 0
-        for t in parts:                                            # transpose(1,2) + concat, written straight into the padded rows
-            x32[:, :, c0:c0 + t.size(1)] = t.transpose(1, 2)
-            c0 += t.size(1)
-        x32[:, :, c0:c0 + self.temporal_embedding_dim] = P["emb"][:T].unsqueeze(0)     # embedding concatenated, not added (…:119-126)
-        ops.cast_f32_bf16(b["x32"], b["xa"])
+        # cat(dim=1) + transpose(1, 2) + temporal embedding CONCATENATED, not added (…:108-126): one kernel, (B, C, T) fp32 in,
+        # bf16 rows [B*T, 112] out
+        ops.pack_channel_major(parts, T, P["emb"], b["xa"])
         cur, nxt = b["xa"], b["xb"]
         scale = 1.0 / math.sqrt(P["hd"])
         for L in P["layers"]:
@@ -245,7 +241,7 @@ class TransformerBaseline(nn.Module):
         # CoM acceleration as an (unscaled) attention blend over the input CoM accelerations (…:51-70, 135-137)
         ops.gemm(cur, P["wq"], b["q"], M, dp, dp, bias=P["bq"])
         ops.gemm(cur, P["wk"], b["k"], M, dp, dp, bias=P["bk"])
-        b["v"][:, :3] = parts[5].transpose(1, 2).reshape(M, 3).to(BF16)
+        ops.pack_channel_major(parts[5:6], T, None, b["v"])            # CoM accelerations as the (3 -> 8)-wide values of the blend
         ops.attention_fwd(b["q"], b["k"], b["v"], b["blend"], batch_size, T, 1, dp, 8, 1.0)
         out = b["out"].view(batch_size, T, 12)
         dt = self.fc.weight.dtype

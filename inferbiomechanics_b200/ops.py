@@ -43,6 +43,16 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def pack_channel_major(srcs, T, emb, out_bf16):
+    """srcs: contiguous fp32 CUDA tensors (B, C_i, T); emb fp32 [>=T, E] or None; out bf16 [B*T, ld]."""
+    n = len(srcs)
+    B = srcs[0].shape[0]
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    chans = (ctypes.c_int32 * n)(*[t.shape[1] for t in srcs])
+    call("ibm_pack_channel_major", ptrs, chans, n, B, T, _p(emb), 0 if emb is None else emb.shape[1], _p(out_bf16), out_bf16.stride(0),
+         stream_ptr())
+
+
 # ---- GEMM ---------------------------------------------------------------------------------------
 def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, M: int, N: int, K: int, *, lda=None, ldb=None, ldd=None,
          a_mn=False, b_mn=False, bias: Optional[torch.Tensor] = None, act="none", aux: Optional[torch.Tensor] = None,

@@ -548,3 +548,25 @@ def test_batchnorm_single_row_training_is_a_value_error():
     with pytest.raises(ValueError):              # torch: "Expected more than 1 value per channel when training"
         ops.batchnorm_fwd(x, x.clone(), 1, 8, o, o, o.clone(), o.clone(), o.clone(), o.clone(), True, 0.1, 1e-5,
                           ops.batchnorm_workspace(8, "cuda"))
+
+
+@pytest.mark.parametrize("B,T,E", [(3, 200, 30), (1, 20, 30), (5, 64, 0), (2, 65, 7), (300, 50, 30)])
+def test_pack_channel_major_bit_exact(B, T, E):
+    """TransformerBaseline input pack (TransformerBaseline.py:108-126: cat on the channel dim, transpose(1, 2), temporal
+    embedding concatenated): bf16 rows equal torch's own cat/transpose/cat followed by an RNE cast, bit for bit; pad
+    columns are zero."""
+    from inferbiomechanics_b200 import ops
+    g = torch.Generator().manual_seed(B * T + E)
+    chans = [23, 23, 23, 3, 3, 3]
+    srcs = [torch.randn(B, c, T, generator=g) for c in chans]
+    emb = torch.randn(T + 3, E, generator=g) if E else None
+    C = sum(chans)
+    ld = ops.round_up(C + E, 8)
+    out = torch.full((B * T, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.pack_channel_major([s.cuda() for s in srcs], T, None if emb is None else emb.cuda(), out)
+    want = torch.cat(srcs, dim=1).transpose(1, 2)
+    if E:
+        want = torch.cat([want, emb[:T].unsqueeze(0).expand(B, T, E)], dim=2)
+    want = want.reshape(B * T, C + E).to(torch.bfloat16)
+    assert torch.equal(out[:, :C + E].cpu(), want)
+    assert (out[:, C + E:] == 0).all()
