@@ -131,8 +131,9 @@ class TransformerBaseline(nn.Module):
         self._prep = dict(
             d=d, dp=dp, hd=hd, hp=hp, fp=fp, layers=layers,
             fc_w=padw(self.fc.weight, self.output_vector_dim, dp), fc_b=self.fc.bias.detach().to(dev, torch.float32).contiguous(),
-            wq=padw(self.com_attention.query_linear.weight, dp, dp), bq=padb(self.com_attention.query_linear.bias, dp),
-            wk=padw(self.com_attention.key_linear.weight, dp, dp), bk=padb(self.com_attention.key_linear.bias, dp),
+            # the CoM blend's query and key projections (SimpleAttention, …:54-55,60-61) as ONE [2*dp, dp] GEMM: rows 0..dp-1 = Wq
+            wqk=torch.cat([padw(self.com_attention.query_linear.weight, dp, dp), padw(self.com_attention.key_linear.weight, dp, dp)]),
+            bqk=torch.cat([padb(self.com_attention.query_linear.bias, dp), padb(self.com_attention.key_linear.bias, dp)]),
             emb=self.temporal_embedding.embedding.weight.detach().to(dev, torch.float32).contiguous())
         self._prep_version = ver
         return self._prep
@@ -143,7 +144,7 @@ class TransformerBaseline(nn.Module):
                 self._bufs.pop(next(iter(self._bufs)))
             H, hp, dp, fp = self.num_heads, P["hp"], P["dp"], P["fp"]
             z = lambda c, dt=BF16: torch.zeros(M, c, dtype=dt, device=dev)
-            self._bufs[M] = dict(xa=z(dp), xb=z(dp), qkv=z(3 * H * hp), o=z(H * hp), s=z(dp), x1=z(dp), h=z(fp), q=z(dp), k=z(dp),
+            self._bufs[M] = dict(xa=z(dp), xb=z(dp), qkv=z(3 * H * hp), o=z(H * hp), s=z(dp), x1=z(dp), h=z(fp), qk=z(2 * dp),
                                  v=z(8), blend=z(8), out=z(12, torch.float32))
         return self._bufs[M]
 
@@ -239,10 +240,9 @@ class TransformerBaseline(nn.Module):
             cur, nxt = nxt, cur
         ops.gemm(cur, P["fc_w"], b["out"], M, self.output_vector_dim, dp, bias=P["fc_b"])
         # CoM acceleration as an (unscaled) attention blend over the input CoM accelerations (…:51-70, 135-137)
-        ops.gemm(cur, P["wq"], b["q"], M, dp, dp, bias=P["bq"])
-        ops.gemm(cur, P["wk"], b["k"], M, dp, dp, bias=P["bk"])
+        ops.gemm(cur, P["wqk"], b["qk"], M, 2 * dp, dp, bias=P["bqk"])
         ops.pack_channel_major(parts[5:6], T, None, b["v"])            # CoM accelerations as the (3 -> 8)-wide values of the blend
-        ops.attention_fwd(b["q"], b["k"], b["v"], b["blend"], batch_size, T, 1, dp, 8, 1.0)
+        ops.attention_fwd(b["qk"][:, :dp], b["qk"][:, dp:], b["v"], b["blend"], batch_size, T, 1, dp, 8, 1.0)
         out = b["out"].view(batch_size, T, 12)
         dt = self.fc.weight.dtype
         return {

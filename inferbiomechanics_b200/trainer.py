@@ -112,7 +112,7 @@ class Trainer:
         return self._train_step_eager(store, idx)
 
     def _train_step_graphed(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
-        key = (id(store), idx.numel())
+        key = (id(store), idx.numel(), self.lr, self.model.training)     # launch arguments baked into the captured step
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= 8:
