@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -236,7 +236,6 @@ def main():
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     ms_per_step = elapsed_ms.item() / args.steps
     value = world * B / (ms_per_step * 1e-3)
-    clock_info = clocks.stop() if rank == 0 else None
     final_loss = res[0].item()
 
     # ------------------------------------------------ e2e: host buffers through the public call ---------------------
@@ -255,6 +254,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (e2e_ms.item() / args.steps * 1e-3)
+    clock_info = clocks.stop() if rank == 0 else None          # samples cover both timed regions (value and e2e)
     h2d = sum(t.numel() * t.element_size() for t in host["inputs"].values()) + sum(t.numel() * t.element_size() for t in host["labels"].values())
 
     # ------------------------------------------------ roofline of the dominant kernel (tcgen05 GEMM) ----------------
