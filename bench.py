@@ -168,6 +168,33 @@ def cpu_baseline_leg() -> dict:
             "sample": f"{sample_b} windows/step x 3 timed steps (1 warm-up) of the same denoiser training step, torch CPU fp32"}
 
 
+def cpu_feedforward_leg() -> dict:
+    """BASELINE configs[0] on the host cores: the CPU port of the reference FeedForward training step (1470->512->512->300,
+    sigmoid, RMSprop 1e-4; train.py:240-284) at the reference's batch 32 and at a large batch, torch CPU fp32, all threads."""
+    import torch
+    from oracle import train as otrain
+    from oracle.seeded import seeded_state_dict
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    D, T, s = 23, 50, 5
+    F = T // s
+    k0 = (3 * D + 12 + 6 * s + 36) * F
+    shapes = {"net.0.weight": (512, k0), "net.0.bias": (512,), "net.2.weight": (512, 512), "net.2.bias": (512,),
+              "net.4.weight": (30 * F, 512), "net.4.bias": (30 * F,)}
+    tr = otrain.PortTrainer(seeded_state_dict(shapes, 7), lr=1e-4, opt="rmsprop")
+    out = {"cores": cores, "kind": "port"}
+    for B, n in ((32, 200), (4096, 8)):
+        inputs, labels = otrain.synthetic_batch(B, F, D, s * 3, 11)
+        for _ in range(3):
+            tr.step_feedforward(inputs, labels, "sigmoid", F)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            tr.step_feedforward(inputs, labels, "sigmoid", F)
+        dt = (time.perf_counter() - t0) / n
+        out[f"batch_{B}"] = {"windows_per_s": B / dt, "ms_per_step": dt * 1e3, "steps_timed": n}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,6 +328,8 @@ def main():
         out["aux"]["transformer_analyze"] = bench_legs.transformer_analyze_leg(dev, world, pk)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg()
+        if "aux" in out:
+            out["aux"]["feedforward_train"]["cpu_port"] = cpu_feedforward_leg()
     if rank == 0:
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
