@@ -69,6 +69,7 @@ class Trainer:
         self._result_ring = [torch.zeros(40, device=dev) for _ in range(8)]
         # layer groups for the bucketed allreduce
         bounds = self._group_boundaries()
+        bucket_mb = float(os.environ.get("IBM_BUCKET_MB", bucket_mb))      # experiments: bucket size of the gradient allreduce
         self.bucketer = parallel.GradBucketer(self.arena.grad, parallel.make_buckets(bounds, n, int(bucket_mb * (1 << 20) / 4)))
         if self.is_denoiser:
             self.eng.bucket_hook = lambda l: self.bucketer.group_done(l + 1)      # group 0 = stem, l+1 = layer l, L+1 = head
