@@ -150,7 +150,7 @@ def transformer_analyze_leg(dev, world: int, pk: dict, B: int = 2048, T: int = 2
     g = torch.Generator(device=dev).manual_seed(11)
     chans = [(K.POS, D), (K.VEL, D), (K.ACC, D), (K.COM_POS, 3), (K.COM_VEL, 3), (K.COM_ACC, 3)]
     x = {k: torch.randn(B, c, T, device=dev, generator=g) for k, c in chans}
-    for _ in range(3):
+    for _ in range(20):                               # ~50 ms of work: a GPU that was idle needs it to reach its clocks
         m(x)
     e0, e1 = _events()
     torch.cuda.synchronize()
@@ -179,6 +179,20 @@ def transformer_analyze_leg(dev, world: int, pk: dict, B: int = 2048, T: int = 2
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1) / (2 * n_batches)
     oh = o_last = next(iter(m.forward_stream([xh])))
+    # the host link on its own: the same pinned tensors copied H2D with nothing else running (explains the e2e figure, which is
+    # bound by max(compute, H2D) per batch)
+    xd = {k: torch.empty_like(v, device=dev) for k, v in xh.items()}
+    for k, v in xh.items():
+        xd[k].copy_(v, non_blocking=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(4):
+        for k, v in xh.items():
+            xd[k].copy_(v, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    h2d_only_ms = e0.elapsed_time(e1) / 4
+    del xd
     h2d = sum(v.numel() * v.element_size() for v in xh.values())
     d2h = sum(v.numel() * v.element_size() for v in oh.values())
     fl = 142065600.0 * B
@@ -186,6 +200,8 @@ def transformer_analyze_leg(dev, world: int, pk: dict, B: int = 2048, T: int = 2
             "ms_per_batch": ms, "batch_windows": B, "window_frames": T, "tflops": fl / (ms * 1e-3) / 1e12,
             "kernel_ms_per_batch": kern_ms, "kernels": kern,
             "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "windows/s", "ms_per_batch": ms_e2e, "h2d_bytes_per_batch": h2d,
-                    "d2h_bytes_per_batch": d2h, "api": "TransformerBaseline.forward_stream(iterable of pinned host input dicts)"},
+                    "d2h_bytes_per_batch": d2h, "h2d_alone_ms_per_batch": h2d_only_ms,
+                    "h2d_alone_gbs": sum(v.numel() * v.element_size() for v in xh.values()) / h2d_only_ms / 1e6,
+                    "api": "TransformerBaseline.forward_stream(iterable of pinned host input dicts)"},
             "full_stream": f"2^20 windows = {(1 << 20) / (world * B / (ms * 1e-3)):.2f} s at this rate on {world} GPU(s)",
             "note": "weak scaling (contiguous window shards, no collective); d=108 rows are padded to 112 bf16 columns, heads 36->48"}
