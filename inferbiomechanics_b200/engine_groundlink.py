@@ -26,7 +26,9 @@ PAD, KT = 3, 7
 
 
 class GroundlinkEngine:
-    def __init__(self, arena: ParamArena, c_in: int, features: List[int], fc_dropout: float):
+    CNN_DROPOUT_SEED = 0x636e6e64
+
+    def __init__(self, arena: ParamArena, c_in: int, features: List[int], fc_dropout: float, cnn_dropout: float = 0.0):
         self.arena = arena
         self.ch = [c_in] + list(features)                 # [177, 128, 128, 256, 256]
         self.ld = [_r8(c) for c in self.ch]               # row pitch of each layer's activation buffer
@@ -35,6 +37,7 @@ class GroundlinkEngine:
         self.conv_pos = (1, 4, 7, 10)                     # nn.Sequential positions
         self.fc_pos = (2, 5, 8)
         self.fc_dropout = fc_dropout
+        self.cnn_dropout = float(cnn_dropout)             # nn.Dropout before every Conv1d (Groundlink.py:41, default 0.0)
         self.buf = _Buffers(arena.device)
         self._wver = None
         self._w: Dict[str, torch.Tensor] = {}
@@ -104,16 +107,28 @@ class GroundlinkEngine:
         A = self.arena
         W = self._weights()
         st, Tp, Mp = self._state(B, T)
+        self.step += 1
+        cdrop = train and self.cnn_dropout > 0.0
+        st["cnn_dropped"] = cdrop
         ops.replicate_pad_rows(st["x0"], B, T, PAD, self.ld[0])
         for i, pos in enumerate(self.conv_pos):
             x, y_full = st[f"x{i}"], st[f"x{i + 1}_full"]
             slack = st["slack"]
+            if cdrop:
+                # Dropout on the conv INPUT, before the (replicate) padding the conv applies itself: mask the whole buffer with
+                # Philox(seed, 4*step + i) (zeros stay zeros), then let the pad rows replicate the DROPPED edge frames
+                xd_full = st.get(f"xd{i}_full")
+                if xd_full is None:
+                    xd_full = st[f"xd{i}_full"] = torch.zeros_like(st[f"x{i}_full"])
+                    st[f"xd{i}"] = xd_full[slack:slack + Mp]
+                ops.dropout(st[f"x{i}_full"], xd_full, self.cnn_dropout, self.CNN_DROPOUT_SEED, 4 * self.step + i)
+                ops.replicate_pad_rows(st[f"xd{i}"], B, T, PAD, self.ld[i])
+                x = st[f"xd{i}"]
             y_shift = y_full[slack + PAD: slack + PAD + Mp]             # the store lands 3 rows down: frame slots of layer i+1
             ops.gemm(x, W[f"f{i}"], y_shift, Mp, self.ch[i + 1], KT * self.ld[i], lda=self.ld[i], bias=A.master_of(f"cnn.{pos}.bias"),
                      act="elu", taps=KT)
             ops.replicate_pad_rows(st[f"x{i + 1}"], B, T, PAD, self.ld[i + 1])
         drop = train and self.fc_dropout > 0.0
-        self.step += 1
         y4 = st["x4"]
         a = y4
         if drop:
@@ -141,6 +156,7 @@ class GroundlinkEngine:
         g = A.grad_of
         st, Tp, Mp = self._state(B, T)
         drop = st.get("dropped", False)
+        cdrop = st.get("cnn_dropped", False)
         dout = st["dout"]
         p, s = self.fc_dropout, self.step
         # fc.8 (no bias)
@@ -172,11 +188,16 @@ class GroundlinkEngine:
             cout, cin = self.ch[i + 1], self.ch[i]
             G = st[f"g{i + 1}"]                              # d loss / d (ELU output of conv i), padded layout, already times ELU'
             ops.fold_pad_rows(G, B, T, PAD, self.ld[i + 1])  # replicate-pad adjoint; pad rows become zero
+            if cdrop and i + 1 <= 3:
+                # adjoint of the dropout in front of conv i+1: the same Philox mask over the identically shaped buffer (the ELU
+                # derivative fused into the producing dgrad commutes with it, and with the fold because pads replicate x)
+                Gfull = st[f"g{i + 1}_full"]
+                ops.dropout(Gfull, Gfull, self.cnn_dropout, self.CNN_DROPOUT_SEED, 4 * s + i + 1)
             ops.colsum(G, Mp, cout, g(f"cnn.{pos}.bias"))
             # wgrad: dW_j[co, ci] = sum_r G[r + 3, co] * Xp[r + j, ci]  (7 split-K MN-major GEMMs into GEMM-layout scratch)
             wg = self.buf.tensor(st, f"wg{i}", (cout, KT * self.cin_pad[i]), F32)
             wg.zero_()
-            Gf, Xf = st[f"g{i + 1}_full"], st[f"x{i}_full"]
+            Gf, Xf = st[f"g{i + 1}_full"], st[f"xd{i}_full" if cdrop else f"x{i}_full"]
             for j in range(KT):
                 ops.gemm(Gf[slack + PAD:], Xf[slack + j:], wg[:, j * self.cin_pad[i]:], cout, cin, Mp, lda=self.ld[i + 1], ldb=self.ld[i],
                          ldd=KT * self.cin_pad[i], a_mn=True, b_mn=True, accumulate=True)

@@ -104,7 +104,7 @@ class Groundlink(EngineModule):
         return net
 
     def _build_engine(self, arena):
-        return GroundlinkEngine(arena, self.input_size, self.cnn_features[1:], self.fc_dropout)
+        return GroundlinkEngine(arena, self.input_size, self.cnn_features[1:], self.fc_dropout, self.cnn_dropout)
 
     def forward(self, input: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         # 1. same shape assertions as the reference (Groundlink.py:107-118)
@@ -120,8 +120,6 @@ class Groundlink(EngineModule):
         assert input[InputDataKeys.ROOT_POS_HISTORY_IN_ROOT_FRAME].shape[-1] == self.root_history_len * 3
         assert len(input[InputDataKeys.ROOT_EULER_HISTORY_IN_ROOT_FRAME].shape) == 3
         assert input[InputDataKeys.ROOT_EULER_HISTORY_IN_ROOT_FRAME].shape[-1] == self.root_history_len * 3
-        if self.cnn_dropout > 0.0 and self.training:
-            raise NotImplementedError("cnn_dropout > 0 in training mode is not implemented (reference default is 0.0)")
         eng = self.engine()
         B, T = input[InputDataKeys.POS].shape[0], input[InputDataKeys.POS].shape[1]
         buf, fs, we, col0 = eng.input_rows(B, T)

@@ -124,3 +124,59 @@ def test_groundlink_native_trainer_matches_module_loop(fmt):
     # evaluation pass
     r = tr.eval_step(store, idx_all[:B])
     assert torch.isfinite(r[0])
+
+
+def test_groundlink_cnn_dropout_matches_masked_emulation():
+    """cnn_dropout > 0 in training mode (nn.Dropout in front of every Conv1d, Groundlink.py:41): the four Philox masks are
+    regenerated through the same C-ABI call over identically shaped buffers and the drop-in's forward / backward is
+    compared with a plain fp32 torch emulation using them (dropout -> replicate-pad conv -> ELU, x4; then the MLP with
+    fc_dropout = 0).  Tolerances as for the golden Groundlink test (bf16 operands through 7 layers)."""
+    import torch.nn.functional as Fn
+    from inferbiomechanics_b200 import ops
+    from inferbiomechanics_b200.models.Groundlink import Groundlink
+    B, T, p = 3, 20, 0.25
+    torch.manual_seed(11)
+    m = Groundlink(23, 12, 10, "all_frames", cnn_dropout=p, fc_dropout=0.0).cuda().train()
+    inputs = seeded_inputs(B, T, 23, 30, 21)
+    out = m(inputs)
+    y = torch.cat([out[k] for k in (ol.COP, ol.FORCE, ol.TORQUE, ol.WRENCH)], dim=-1)          # (B, T, 30)
+    gy = seeded_out_labels(B, T, 31)[0]
+    gy = torch.cat([gy[k] for k in (ol.COP, ol.FORCE, ol.TORQUE, ol.WRENCH)], dim=-1).cuda()
+    for q in m.parameters():
+        q.grad = None
+    (y * gy).sum().backward()
+    eng = m.engine()
+    st, Tp, Mp = eng._state(B, T)
+    slack = st["slack"]
+    masks = []
+    for i in range(4):
+        ones = torch.ones_like(st[f"x{i}_full"])
+        mk = torch.empty_like(ones)
+        ops.dropout(ones, mk, p, eng.CNN_DROPOUT_SEED, 4 * eng.step + i)
+        mk = mk[slack:slack + Mp].view(B, Tp, -1)[:, 3:3 + T, :eng.ch[i]].float()
+        assert abs((mk == 0).float().mean().item() - p) < 0.05
+        masks.append(mk)
+    x = st["x0"].view(B, Tp, -1)[:, 3:3 + T, :eng.ch[0]].float()                               # the packed (bf16-rounded) input frames
+    params = {n: q.detach().float().clone().requires_grad_(True) for n, q in m.named_parameters()}
+    h = x
+    for i, pos in enumerate((1, 4, 7, 10)):
+        h = (h * masks[i]).transpose(1, 2)                                                     # (B, C, T)
+        h = Fn.conv1d(Fn.pad(h, (3, 3), mode="replicate"), params[f"cnn.{pos}.weight"], params[f"cnn.{pos}.bias"])
+        h = Fn.elu(h).transpose(1, 2)
+    h = Fn.elu(h @ params["fc.2.weight"].t() + params["fc.2.bias"])
+    h = Fn.elu(h @ params["fc.5.weight"].t() + params["fc.5.bias"])
+    ref = h @ params["fc.8.weight"].t()
+    err = (y.detach() - ref.detach()).abs().max().item()
+    assert err <= 3e-2 * ref.abs().max().item(), f"forward: {err} vs {ref.abs().max().item()}"
+    (ref * gy).sum().backward()
+    for n, q in m.named_parameters():
+        got, want = q.grad.double().reshape(-1).cpu(), params[n].grad.double().reshape(-1).cpu()
+        rel = (got - want).norm().item() / (want.norm().item() + 1e-12)
+        cos = torch.dot(got, want).item() / (got.norm().item() * want.norm().item() + 1e-30)
+        assert rel <= 0.12 and cos >= 0.985, f"{n}: rel L2 {rel:.4f}, cosine {cos:.4f}"
+    # eval mode ignores the dropout; a second training forward draws new masks
+    m.eval()
+    e1 = m(inputs)[ol.FORCE].clone()
+    m.train()
+    t2 = m(inputs)[ol.FORCE]
+    assert not torch.equal(t2, out[ol.FORCE]) and not torch.equal(e1, t2)
