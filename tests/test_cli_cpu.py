@@ -60,3 +60,21 @@ def test_factory_and_checkpoint_loader_signatures(tmp_path, capsys):
     assert cmd.load_latest_checkpoint(model, checkpoint_dir=str(d)) == (2, 5)
     assert float(model.weight.detach()[0, 0]) == 3.0
     assert "Loaded checkpoint from epoch 2, batch 5" in capsys.readouterr().out
+
+
+def test_feedforward_state_dict_positions_with_batchnorm_and_dropout():
+    """nn.Sequential positions shift with --dropout / --batchnorm exactly as in the reference (SURVEY §9.3,
+    FeedForwardRegressionBaseline.py:68-75): per layer [Dropout, BatchNorm1d(h0), Linear, act], BatchNorm on the layer INPUT
+    (the raw 1470-vector included).  Pure constructor check: no GPU needed."""
+    from inferbiomechanics_b200.models.FeedForwardRegressionBaseline import FeedForwardBaseline
+    m = FeedForwardBaseline(23, 2, 50, "all_frames", "sigmoid", 5, 10, hidden_dims=[512, 512], batchnorm=True, dropout=True,
+                            dropout_prob=0.1)
+    sd = m.state_dict()
+    assert tuple(sd["net.1.running_mean"].shape) == (1470,) and "net.1.num_batches_tracked" in sd
+    assert tuple(sd["net.2.weight"].shape) == (512, 1470)
+    assert tuple(sd["net.5.weight"].shape) == (512,) and tuple(sd["net.6.weight"].shape) == (512, 512)
+    assert tuple(sd["net.9.running_var"].shape) == (512,) and tuple(sd["net.10.weight"].shape) == (300, 512)
+    plain = FeedForwardBaseline(23, 2, 50, "all_frames", "sigmoid", 5, 10).state_dict()
+    assert sorted(plain) == ["net.0.bias", "net.0.weight", "net.2.bias", "net.2.weight", "net.4.bias", "net.4.weight"]
+    only_bn = FeedForwardBaseline(23, 2, 50, "last_frame", "relu", 5, 10, hidden_dims=[64], batchnorm=True).state_dict()
+    assert tuple(only_bn["net.1.weight"].shape) == (64, 1470) and tuple(only_bn["net.4.weight"].shape) == (30, 64)
