@@ -435,3 +435,45 @@ def test_train_steps_host_pipeline_matches_stepwise():
     np.testing.assert_allclose(piped, stepwise, rtol=1e-5)          # same kernels, same order; only atomic order may differ
     assert stepwise[-1] < stepwise[0] * 1.5                          # finite, sane
     assert list(b.train_steps_host([])) == []
+
+
+def test_feedforward_trainer_with_batchnorm_matches_module_loop():
+    """Native Trainer on a batchnorm=True FeedForward (BatchNorm parameters lead each bucket group, training-mode statistics,
+    steps 3+ replayed from the captured CUDA graph) against the reference's loop shape on the same weights and windows
+    (module forward -> evaluator -> loss.backward() -> torch.optim.SGD): same kernels, so losses, parameters and the
+    BatchNorm buffers agree to rounding."""
+    from inferbiomechanics_b200.data.window_store import WindowStore
+    from inferbiomechanics_b200.keys import LOSS_QUANTITIES, MODEL_INPUT_ORDER
+    from inferbiomechanics_b200.loss.RegressionLossEvaluator import RegressionLossEvaluator
+    from inferbiomechanics_b200.models.FeedForwardRegressionBaseline import FeedForwardBaseline
+    from inferbiomechanics_b200.trainer import Trainer
+    T, s, B, lr = 50, 5, 64, 1e-4
+    store = WindowStore.synthetic(5 * B, T, s, 147, "all_frames", seed=3, trial_len=400)
+    torch.manual_seed(2)
+    a = FeedForwardBaseline(23, 2, T, "all_frames", "tanh", s, 10, hidden_dims=[64, 32], batchnorm=True).cuda().train()
+    b = FeedForwardBaseline(23, 2, T, "all_frames", "tanh", s, 10, hidden_dims=[64, 32], batchnorm=True).cuda().train()
+    b.load_state_dict(a.state_dict())
+    tr = Trainer(a, opt_type="sgd", lr=lr)
+    opt = torch.optim.SGD(b.parameters(), lr=lr)
+    ev = RegressionLossEvaluator(dataset=None, split="train", device="cuda")
+    widths = [23, 23, 23, 3, 3, 3, 3, 36, 15, 15]
+    idx_all = store.shard(0, 1)
+    for step in range(5):                                     # steps 0-1 eager, 2 captures, 3-4 replay
+        idx = idx_all[step * B:(step + 1) * B]
+        res = tr.train_step(store, idx)
+        x = store.pack_f32(idx)
+        inputs = dict(zip(MODEL_INPUT_ORDER, torch.split(x, widths, dim=-1)))
+        labels = dict(zip(LOSS_QUANTITIES, torch.split(store.labels(idx), [6, 6, 6, 12], dim=-1)))
+        opt.zero_grad()
+        loss = ev(inputs, b(inputs), labels, [], [], ALL)
+        loss.backward()
+        opt.step()
+        np.testing.assert_allclose(res[0].item(), loss.item(), rtol=2e-3)
+    assert any(g[1] is not None for g in tr._graphs.values()), "the FeedForward step should be running from its CUDA graph"
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if k.endswith("num_batches_tracked"):
+            assert int(sa[k]) == int(sb[k]) == 5
+        else:
+            d0 = (sa[k].float() - sb[k].float()).abs().max().item()
+            assert d0 <= 1e-3 * (sb[k].float().abs().max().item() + 1e-3), f"{k}: {d0}"
