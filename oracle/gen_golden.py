@@ -19,6 +19,9 @@ transformer.npz        TransformerLayer stack + heads composed exactly as
                        TransformerBaseline.forward (src/models/TransformerBaseline.py:104-148), fp64.
 denoiser_layers.npz    the reference TransformerLayer at the denoiser's width (d=64/128 test sizes,
                        fp32) — pins the layer the builder-owned denoiser re-uses.
+windows.npz            the reference's OWN AddBiomechanicsDataset (src/data/AddBiomechanicsDataset.py:64-139
+                       index, 161-285 __getitem__) run over synthetic subjects through oracle/fake_nimble.py,
+                       plus torch's DistributedSampler + DataLoader as wired at src/cli/train.py:143-150.
 """
 from __future__ import annotations
 
@@ -244,6 +247,93 @@ def gen_denoiser_layers(ref):
     np.savez_compressed(os.path.join(OUT, "denoiser_layers.npz"), **d)
 
 
+WINDOW_CASES = {
+    # name: (seed, n_subjects, T, stride, format, hist_cols, max_len, n_sampled_windows)
+    "ff_t50s5_all": (11, 6, 50, 5, "all_frames", 15, 170, 10),
+    "gl_t50s1_last": (12, 3, 50, 1, "last_frame", 30, 130, 4),
+    "t20s5_last": (13, 5, 20, 5, "last_frame", 15, 90, 8),
+    "t7s3_all": (14, 4, 7, 3, "all_frames", 9, 40, 8),       # T % stride != 0: 3 frames tested, 2 read
+}
+WINDOW_LABEL_KEYS = ("tau", "residualWrenchInRootFrame", "comAccInRootFrame", "groundContactWrenchesInRootFrame",
+                     "groundContactCenterOfPressureInRootFrame", "groundContactTorqueInRootFrame",
+                     "groundContactForceInRootFrame")
+
+
+def window_digest(items) -> str:
+    """sha256 over every window's input arrays (model concat order) then label arrays (WINDOW_LABEL_KEYS order)."""
+    import hashlib
+    from .windows import INPUT_ORDER
+    h = hashlib.sha256()
+    for inputs, labels in items:
+        for k in INPUT_ORDER:
+            h.update(np.ascontiguousarray(np.asarray(inputs[k], dtype=np.float32)).tobytes())
+        for k in WINDOW_LABEL_KEYS:
+            h.update(np.ascontiguousarray(np.asarray(labels[k], dtype=np.float32)).tobytes())
+    return h.hexdigest()
+
+
+def gen_windows(ref_unused=None):
+    """Run the reference's AddBiomechanicsDataset itself over synthetic subjects (fake nimblephysics reader)."""
+    import contextlib
+    import io
+    import tempfile
+    from torch.utils.data import DataLoader
+    from torch.utils.data.distributed import DistributedSampler
+    from . import fake_nimble
+    from .windows import make_synthetic_subjects
+    load_reference()                                   # puts /root/reference/src on sys.path
+    d = {}
+    for name, (seed, n_subj, T, s, fmt, hist, max_len, n_samp) in WINDOW_CASES.items():
+        subjects = make_synthetic_subjects(seed, n_subj, T, hist_cols=hist, max_len=max_len)
+        with tempfile.TemporaryDirectory() as tmp:
+            os.makedirs(os.path.join(tmp, "grp_a"))
+            os.makedirs(os.path.join(tmp, "grp_b"))
+            for i in range(n_subj):
+                open(os.path.join(tmp, "grp_a" if i % 2 else "grp_b", f"subj{i:02d}.b3d"), "w").close()
+            open(os.path.join(tmp, "grp_a", "VanDerZee2022_x.b3d"), "w").close()     # skipped: "vander" (Dataset.py:89)
+            open(os.path.join(tmp, "grp_b", "notes.txt"), "w").close()               # skipped: not .b3d
+            found = [os.path.join(r, f) for r, _, fs in os.walk(tmp) for f in fs
+                     if f.endswith(".b3d") and "vander" not in f.lower()]
+            assert len(found) == n_subj
+            # subject k of the synthetic list is the k-th file the reference's own os.walk discovers
+            fake_nimble.install({p: subjects[k] for k, p in enumerate(found)})
+            from data.AddBiomechanicsDataset import AddBiomechanicsDataset
+            with contextlib.redirect_stdout(io.StringIO()):
+                ds = AddBiomechanicsDataset(tmp, T, geometry_folder="", stride=s, output_data_format=fmt,
+                                            skip_loading_skeletons=True)
+            assert ds.subject_paths == found
+            N = len(ds)
+            d[f"{name}/windows"] = np.asarray(ds.windows, dtype=np.int32).reshape(N, 3)
+            d[f"{name}/meta"] = np.array([seed, n_subj, T, s, hist, max_len, ds.num_dofs, ds.num_contact_bodies])
+            d[f"{name}/format"] = np.array(fmt)
+            d[f"{name}/contact_bodies"] = np.array(ds.contact_bodies)
+            items = [ds[i] for i in range(N)]
+            d[f"{name}/digest"] = np.array(window_digest((it[0], it[1]) for it in items))
+            pick = np.unique(np.linspace(0, N - 1, n_samp).astype(np.int64))
+            d[f"{name}/sample_idx"] = pick
+            for i in pick:
+                inp, lab, si, ti = items[int(i)]
+                assert (si, ti) == tuple(ds.windows[int(i)][:2])
+                for k, v in inp.items():
+                    d[f"{name}/w{int(i)}/in/{k}"] = v.numpy()
+                for k, v in lab.items():
+                    d[f"{name}/w{int(i)}/label/{k}"] = v.numpy()
+            # train.py:143-150: DistributedSampler(shuffle=False, drop_last=True) + DataLoader(batch_size), rank 1 of 3
+            sampler = DistributedSampler(ds, num_replicas=3, rank=1, shuffle=False, drop_last=True)
+            d[f"{name}/sampler_r1w3"] = np.asarray(list(sampler), dtype=np.int64)
+            bs = 5
+            subj_idx, trial_idx, sizes, pos_sum = [], [], [], []
+            for batch in DataLoader(ds, batch_size=bs, sampler=sampler, num_workers=0):
+                inputs, labels, bsi, bti = batch
+                subj_idx.append(bsi.numpy()); trial_idx.append(bti.numpy()); sizes.append(len(bsi))
+                pos_sum.append(inputs["pos"].double().sum().item())
+            d[f"{name}/loader_bs5_sizes"] = np.asarray(sizes, dtype=np.int64)
+            d[f"{name}/loader_bs5_subject"] = np.concatenate(subj_idx) if subj_idx else np.zeros(0, np.int64)
+            d[f"{name}/loader_bs5_trial"] = np.concatenate(trial_idx) if trial_idx else np.zeros(0, np.int64)
+            d[f"{name}/loader_bs5_pos_sum"] = np.asarray(pos_sum)
+    np.savez_compressed(os.path.join(OUT, "windows.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)      # deterministic reduction order for the frozen vectors
@@ -251,12 +341,16 @@ def main():
     if "--only-bn-train" in __import__("sys").argv:
         gen_ff_bn_train(ref)
         return
+    if "--only-windows" in __import__("sys").argv:
+        gen_windows(ref)
+        return
     gen_loss(ref)
     gen_ff(ref)
     gen_ff_bn_train(ref)
     gen_groundlink(ref)
     gen_transformer(ref)
     gen_denoiser_layers(ref)
+    gen_windows(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -10,10 +10,12 @@ Follows ``/root/reference/src/data/AddBiomechanicsDataset.py``:
                             (``src/models/FeedForwardRegressionBaseline.py:97-108``) and
                             ``Groundlink.forward`` (``src/models/Groundlink.py:122-133``)
 
-Pinning: the reference class itself cannot run here (needs nimblephysics + .b3d files, neither
-shipped), and the reference has no test for it.  This restatement follows the cited lines; it is
-pinned by hand-computed cases in tests/test_oracle_windows.py only — integer/bit-exact work, so a
-line-by-line restatement is checkable by reading.
+Pinning: the reference class ITSELF runs in the build container over these synthetic subjects through
+``oracle/fake_nimble.py`` (a reader-only stand-in for nimblephysics); ``oracle/gen_golden.py::gen_windows``
+freezes its ``windows`` list, ``__getitem__`` dicts (sampled windows verbatim, all windows by digest) and
+torch's DistributedSampler/DataLoader order in ``tests/golden/windows.npz``.  ``tests/test_windows_golden.py``
+holds this restatement (CPU) and the CUDA index/packers (``-m gpu``) to that fixture bit for bit;
+``tests/test_oracle_windows.py`` adds hand-computed cases.
 
 A synthetic "subject" stands in for ``nimble.biomechanics.SubjectOnDisk``: a dict with
 ``mass`` (float), ``contact_indices`` (for each dataset contact body, its index among the
