@@ -127,6 +127,32 @@ int ibm_regression_loss_bwd(const void* const* h_out, const int64_t* h_out_strid
                             const float* upstream, void* const* h_grad, const int64_t* h_grad_strides,
                             int32_t grad_dtype, void* stream);
 
+/* ---- the loss evaluator's four static helpers with their general contract -------------------------
+ * (src/loss/RegressionLossEvaluator.py:73-158; exercised by test/loss/test_RegressionLossEvaluator.py)
+ * All tensors are fp32 (B, F, C) views with unit channel stride; sb / sf = batch / frame strides in
+ * elements.  workspace: ibm_workspace_bytes() of zeroed device memory (left zeroed on return).
+ * IBM_E_ARG carries the reference's ValueError text (empty tensor, C % 3, C % vec_size, C != 6). */
+
+/* get_squared_diff_mean_vector (…py:73-83): result[c] = mean over (b, f) of (out-lab)^2, any C. */
+int ibm_sqdiff_mean_vector(const float* out_t, int64_t o_sb, int64_t o_sf, const float* lab_t, int64_t l_sb,
+                           int64_t l_sf, int64_t B, int64_t F, int32_t C, float* result, void* workspace,
+                           void* stream);
+/* its autograd backward: grad_out[b,f,c] = 2 upstream[c] (out-lab) / (B F) (contiguous (B,F,C)); grad_lab is
+ * the negative.  Either may be NULL. */
+int ibm_sqdiff_mean_vector_bwd(const float* out_t, int64_t o_sb, int64_t o_sf, const float* lab_t, int64_t l_sb,
+                               int64_t l_sf, int64_t B, int64_t F, int32_t C, const float* upstream,
+                               float* grad_out, float* grad_lab, void* stream);
+/* get_mask_by_threes (…py:85-108): mask[b,f,3g:3g+3] = (||x[b,f,3g:3g+3]||_2 > threshold) ? 1 : 0, strict >,
+ * bit-exact; mask is contiguous fp32 (B,F,C); C % 3 == 0. */
+int ibm_mask_by_threes(const float* x, int64_t sb, int64_t sf, int64_t B, int64_t F, int32_t C, float threshold,
+                       float* mask, void* stream);
+/* get_mean_norm_error (…py:119-141): result[0] = mean over (b, g) of ||(out-lab)[b, F-1, g v:(g+1) v]||_2 — last
+ * frame only; C % vec_size == 0.  fold_halves = 1 is get_com_acc_error (…py:143-158): C == 6, the two 3-vectors of
+ * each tensor are summed first. */
+int ibm_mean_norm_error(const float* out_t, int64_t o_sb, int64_t o_sf, const float* lab_t, int64_t l_sb, int64_t l_sf,
+                        int64_t B, int64_t F, int32_t C, int32_t vec_size, int32_t fold_halves, float* result,
+                        void* workspace, void* stream);
+
 /* ---- DDPM (builder-owned spec; NOT in the reference) --------------------------- */
 
 /* x_t = sqrt_abar[t_b] x0 + sqrt_1m_abar[t_b] eps.  x0/eps/xt_f32: fp32 [B, per_win] contiguous

@@ -28,6 +28,10 @@ SIGNATURES = {
     "ibm_pack_labels": [P, _i64, _i32, P, P, P, _i64, _i32, _i32, _i32, P, _i64, P],
     "ibm_regression_loss_fwd": [P, P, P, P, _i64, _i64, P, _f, P, P, P],
     "ibm_regression_loss_bwd": [P, P, P, P, _i64, _i64, P, _f, P, P, P, _i32, P],
+    "ibm_sqdiff_mean_vector": [P, _i64, _i64, P, _i64, _i64, _i64, _i64, _i32, P, P, P],
+    "ibm_sqdiff_mean_vector_bwd": [P, _i64, _i64, P, _i64, _i64, _i64, _i64, _i32, P, P, P, P],
+    "ibm_mask_by_threes": [P, _i64, _i64, _i64, _i64, _i32, _f, P, P],
+    "ibm_mean_norm_error": [P, _i64, _i64, P, _i64, _i64, _i64, _i64, _i32, _i32, _i32, P, P, P],
     "ibm_q_sample": [P, P, P, P, P, _i64, _i64, P, P, _i64, _u64, _u64, P, P],
     "ibm_ddpm_posterior_step": [P, _i64, P, P, P, P, P, P, _i64, P, P, _i64, _u64, _u64, P, P],
     "ibm_timestep_embed": [P, _i32, _i64, _i32, P, P],

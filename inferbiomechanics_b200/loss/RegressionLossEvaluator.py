@@ -88,6 +88,23 @@ class _LossFunction(torch.autograd.Function):
         return (None, None, *grads, None, None, None, None)
 
 
+class _SqDiffMean(torch.autograd.Function):
+    """mean((o-l)**2, dim=(0,1)) with the reference's autograd behaviour (…py:81-83)."""
+    @staticmethod
+    def forward(ctx, o, l):
+        ok, lk = _as_kernel_view(o.detach()), _as_kernel_view(l.detach())
+        ctx.save_for_backward(ok, lk)
+        return ops.sqdiff_mean_vector(ok, lk)
+
+    @staticmethod
+    def backward(ctx, g):
+        ok, lk = ctx.saved_tensors
+        go = torch.empty(ok.shape, dtype=torch.float32, device=ok.device) if ctx.needs_input_grad[0] else None
+        gl = torch.empty(ok.shape, dtype=torch.float32, device=ok.device) if ctx.needs_input_grad[1] else None
+        ops.sqdiff_mean_vector_bwd(ok, lk, g.contiguous().float(), go, gl)
+        return go, gl
+
+
 class RegressionLossEvaluator:
     def __init__(self, dataset, split: str, device='cpu'):
         self.dataset = dataset
@@ -103,15 +120,12 @@ class RegressionLossEvaluator:
         if not keep_wrench_moment:
             self._wm_results: List[torch.Tensor] = []
 
-    # ---- the reference's four static helpers (same maths, same ValueErrors), on the fused kernel ----
+    # ---- the reference's four static helpers (…py:73-158): same maths, same ValueErrors, same general
+    #      contract (any C / C % 3 / C % vec_size), each one launch of csrc/loss_helpers.cu -------------------
     @staticmethod
     def get_squared_diff_mean_vector(output_tensor: torch.Tensor, label_tensor: torch.Tensor) -> torch.Tensor:
         _check_pair(output_tensor, label_tensor)
-        C = output_tensor.shape[-1]
-        if C not in (6, 12):
-            raise ValueError('the fused kernel evaluates 6- or 12-channel quantities')
-        res = _helper_eval(output_tensor, label_tensor, slot=3 if C == 12 else 1)
-        return res[R_WRENCH] if C == 12 else res[R_FORCE]
+        return _SqDiffMean.apply(output_tensor, label_tensor)
 
     @staticmethod
     def get_mask_by_threes(tensor: torch.Tensor, threshold: float = 0.0) -> torch.Tensor:
@@ -122,38 +136,22 @@ class RegressionLossEvaluator:
                 raise ValueError('Mask tensor must not be empty')
             if tensor.shape[-1] % 3 != 0:
                 raise ValueError('Mask tensor must have a final dimension divisible by 3')
-            if tensor.shape[-1] != 6:
-                raise ValueError('the fused kernel masks 6-channel (two contact body) force tensors')
-            # d loss/d cop with unit weights and cop output = label + 1/2·N exposes the mask exactly:
-            # grad = 2 m (o - l)/N = m  → one backward launch, bit-exact {0,1}
-            B, F, _ = tensor.shape
-            lab_force = _as_kernel_view(tensor)
-            z6 = torch.zeros(B, F, 6, device=tensor.device)
-            z12 = torch.zeros(B, F, 12, device=tensor.device)
-            cop_out = torch.full((B, F, 6), 0.5 * B * F, device=tensor.device)
-            grads = [torch.empty_like(z6), torch.empty_like(z6), torch.empty_like(z6), torch.empty_like(z12)]
-            w = [1.0] * 6 + [0.0] * 24
-            ops.regression_loss_bwd([cop_out, lab_force, z6, z12], [z6, lab_force, z6, z12], w, grads, threshold=threshold)
-            return (grads[0] != 0).to(tensor.dtype)
+            return ops.mask_by_threes(_as_kernel_view(tensor), threshold)
 
     @staticmethod
     def get_mean_norm_error(output_tensor: torch.Tensor, label_tensor: torch.Tensor, vec_size: int = 3) -> torch.Tensor:
         _check_pair(output_tensor, label_tensor)
         if output_tensor.shape[-1] % vec_size != 0:
             raise ValueError('Tensors must have a final dimension divisible by vec_size=' + str(vec_size))
-        C = output_tensor.shape[-1]
-        if (C, vec_size) == (6, 3):
-            return _helper_eval(output_tensor, label_tensor, slot=1)[31]          # force report
-        if (C, vec_size) == (12, 6):
-            return _helper_eval(output_tensor, label_tensor, slot=3)[35]          # wrench report
-        raise ValueError('the fused kernel reports (6 channels, vec 3) and (12 channels, vec 6)')
+        return ops.mean_norm_error(_as_kernel_view(output_tensor.detach()), _as_kernel_view(label_tensor.detach()), vec_size)
 
     @staticmethod
     def get_com_acc_error(output_force_tensor: torch.Tensor, label_force_tensor: torch.Tensor) -> torch.Tensor:
         _check_pair(output_force_tensor, label_force_tensor)
         if output_force_tensor.shape[-1] != 6:
             raise ValueError('Output and label tensors must have a 6 dimensional final dimension')
-        return _helper_eval(output_force_tensor, label_force_tensor, slot=1)[36]
+        return ops.mean_norm_error(_as_kernel_view(output_force_tensor.detach()), _as_kernel_view(label_force_tensor.detach()),
+                                   3, fold_halves=True)
 
     # ---- the call -------------------------------------------------------------------------------
     def __call__(self,
@@ -278,15 +276,3 @@ class RegressionLossEvaluator:
         if reset:
             # the reference forgets to reset wrench_moment_reported_metrics (…py:412-426); preserved
             self._reset_lists(keep_wrench_moment=True)
-
-
-def _helper_eval(o: torch.Tensor, l: torch.Tensor, slot: int) -> torch.Tensor:
-    """Run the fused kernel with (o, l) in one quantity slot and zeros elsewhere."""
-    o, l = _as_kernel_view(o), _as_kernel_view(l)
-    B, F, _ = o.shape
-    z6 = torch.zeros(B, F, 6, device=o.device)
-    z12 = torch.zeros(B, F, 12, device=o.device)
-    outs = [z6, z6, z6, z12]
-    labs = [z6, z6, z6, z12]
-    outs[slot], labs[slot] = o, l
-    return ops.regression_loss_fwd(outs, labs, [1.0] * 30, COP_FORCE_THRESHOLD)

@@ -211,6 +211,39 @@ def regression_loss_bwd(outs, labs, weights30, grads: Sequence[torch.Tensor], up
          threshold, _p(upstream), _ptr_array(grads), _stride_array(grads), gd, stream_ptr())
 
 
+# ---- the evaluator's static helpers, general contract (csrc/loss_helpers.cu) -----------------------------
+def sqdiff_mean_vector(o: torch.Tensor, l: torch.Tensor) -> torch.Tensor:
+    _require_cuda(o, l)
+    B, F, C = o.shape
+    out = torch.empty(C, dtype=torch.float32, device=o.device)
+    call("ibm_sqdiff_mean_vector", _p(o), o.stride(0), o.stride(1), _p(l), l.stride(0), l.stride(1), B, F, C, _p(out),
+         _p(workspace(o.device)), stream_ptr())
+    return out
+
+
+def sqdiff_mean_vector_bwd(o, l, upstream, grad_out=None, grad_lab=None) -> None:
+    B, F, C = o.shape
+    call("ibm_sqdiff_mean_vector_bwd", _p(o), o.stride(0), o.stride(1), _p(l), l.stride(0), l.stride(1), B, F, C, _p(upstream),
+         _p(grad_out), _p(grad_lab), stream_ptr())
+
+
+def mask_by_threes(x: torch.Tensor, threshold: float) -> torch.Tensor:
+    _require_cuda(x)
+    B, F, C = x.shape
+    out = torch.empty(B, F, C, dtype=torch.float32, device=x.device)
+    call("ibm_mask_by_threes", _p(x), x.stride(0), x.stride(1), B, F, C, float(threshold), _p(out), stream_ptr())
+    return out
+
+
+def mean_norm_error(o: torch.Tensor, l: torch.Tensor, vec_size: int, fold_halves: bool = False) -> torch.Tensor:
+    _require_cuda(o, l)
+    B, F, C = o.shape
+    out = torch.empty(1, dtype=torch.float32, device=o.device)
+    call("ibm_mean_norm_error", _p(o), o.stride(0), o.stride(1), _p(l), l.stride(0), l.stride(1), B, F, C, int(vec_size),
+         1 if fold_halves else 0, _p(out), _p(workspace(o.device)), stream_ptr())
+    return out[0]
+
+
 # ---- DDPM -----------------------------------------------------------------------------------------
 def q_sample(x0, eps, t, sqrt_abar, sqrt_1m_abar, xt_f32=None, xt_bf16=None, bf16_ld=0, seed=0, offset=0, eps_out=None):
     B = x0.shape[0]
