@@ -112,6 +112,8 @@ def gen_ff(ref):
         "relu_last": dict(act="relu", fmt="last_frame", hidden=[32], bn=False),
         "tanh_all": dict(act="tanh", fmt="all_frames", hidden=[40, 40, 24], bn=False),
         "sigmoid_bn": dict(act="sigmoid", fmt="all_frames", hidden=[64, 48], bn=True),
+        # BASELINE configs[0] exactly: hidden [512, 512], sigmoid, batch 32 (train.py:37-53 defaults)
+        "sigmoid_cfg0": dict(act="sigmoid", fmt="all_frames", hidden=[512, 512], bn=False, B=32),
     }
     for ci, (name, c) in enumerate(cases.items()):
         import io, contextlib
@@ -122,6 +124,7 @@ def gen_ff(ref):
         m.load_state_dict(seeded_state_dict(shapes, seed))
         m.eval()
         F = T // s
+        B = c.get("B", 6)
         inputs = seeded_inputs(B, F, D, s * 3, 2000 + ci)
         Fo = F if c["fmt"] == "all_frames" else 1
         _, labels = seeded_out_labels(B, Fo, 3000 + ci)
@@ -340,6 +343,9 @@ def main():
     ref = load_reference()
     if "--only-bn-train" in __import__("sys").argv:
         gen_ff_bn_train(ref)
+        return
+    if "--only-ff" in __import__("sys").argv:
+        gen_ff(ref)
         return
     if "--only-windows" in __import__("sys").argv:
         gen_windows(ref)

@@ -114,28 +114,47 @@ def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1
     return (x - mu) / torch.sqrt(var + eps) * w + b
 
 
-def multihead_attention(x: torch.Tensor, in_w, in_b, out_w, out_b, num_heads: int) -> torch.Tensor:
+def _identity(x: torch.Tensor) -> torch.Tensor:
+    return x
+
+
+def bf16_ste(x: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 in the forward value, identity in the gradient (straight-through).  Passed as ``rnd`` to the
+    layer functions below it re-creates, in fp32 arithmetic, the points where the CUDA path STORES an activation as
+    bf16 (after every GEMM epilogue, softmax probabilities, LayerNorm outputs).  With bf16-rounded weights on top,
+    the oracle then takes the same ReLU gates as the kernels, so gradients can be compared at a tight bar instead of
+    the loose one a pure-fp32 oracle forces (a flipped gate changes its gradient entries completely)."""
+    return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
+
+
+def bf16_weights(sd: Mapping[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """GEMM weight matrices rounded to bf16 (the kernels' shadow arena); biases, LayerNorm parameters and the
+    positional table stay fp32 (read from the master arena).  Straight-through, so gradients flow to ``sd``."""
+    return {k: (bf16_ste(v) if v.dim() == 2 and k != "pos_embedding" else v) for k, v in sd.items()}
+
+
+def multihead_attention(x: torch.Tensor, in_w, in_b, out_w, out_b, num_heads: int, rnd=_identity) -> torch.Tensor:
     B, T, d = x.shape
     hd = d // num_heads
-    qkv = x @ in_w.t() + in_b
+    qkv = rnd(x @ in_w.t() + in_b)
     q, k, v = qkv.split(d, dim=-1)
     sh = lambda t: t.reshape(B, T, num_heads, hd).transpose(1, 2)      # (B,H,T,hd)
     q, k, v = sh(q), sh(k), sh(v)
     s = (q @ k.transpose(-2, -1)) / math.sqrt(hd)
-    p = torch.softmax(s, dim=-1)
-    o = (p @ v).transpose(1, 2).reshape(B, T, d)
+    p = rnd(torch.softmax(s, dim=-1))
+    o = rnd((p @ v).transpose(1, 2).reshape(B, T, d))
     return o @ out_w.t() + out_b
 
 
-def transformer_layer(sd: Mapping[str, torch.Tensor], prefix: str, x: torch.Tensor, num_heads: int) -> torch.Tensor:
+def transformer_layer(sd: Mapping[str, torch.Tensor], prefix: str, x: torch.Tensor, num_heads: int, rnd=_identity) -> torch.Tensor:
     g = lambda n: sd[prefix + n]
     a = multihead_attention(x, g("multihead_attention.in_proj_weight"), g("multihead_attention.in_proj_bias"),
                             g("multihead_attention.out_proj.weight"), g("multihead_attention.out_proj.bias"),
-                            num_heads)
-    x = layer_norm(x + a, g("norm1.weight"), g("norm1.bias"))
-    h = torch.clamp_min(x @ g("feedforward.0.weight").t() + g("feedforward.0.bias"), 0.0)
+                            num_heads, rnd)
+    x = rnd(layer_norm(rnd(x + a), g("norm1.weight"), g("norm1.bias")))
+    h = rnd(torch.clamp_min(x @ g("feedforward.0.weight").t() + g("feedforward.0.bias"), 0.0))
     f = h @ g("feedforward.2.weight").t() + g("feedforward.2.bias")
-    return layer_norm(x + f, g("norm2.weight"), g("norm2.bias"))
+    return rnd(layer_norm(rnd(x + f), g("norm2.weight"), g("norm2.bias")))
 
 
 def transformer_forward(sd: Mapping[str, torch.Tensor], x: Mapping[str, torch.Tensor], num_layers: int,
@@ -173,15 +192,16 @@ def sinusoidal_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
 
 
 def denoiser_forward(sd: Mapping[str, torch.Tensor], cond: torch.Tensor, x_t: torch.Tensor, t: torch.Tensor,
-                     num_layers: int, num_heads: int) -> torch.Tensor:
-    """cond (B,F,C_in) packed kinematics; x_t (B,F,30); t (B,) int64 → x0_hat (B,F,30)."""
+                     num_layers: int, num_heads: int, rnd=_identity) -> torch.Tensor:
+    """cond (B,F,C_in) packed kinematics; x_t (B,F,30); t (B,) int64 → x0_hat (B,F,30).
+    ``rnd`` = ``bf16_ste`` (with ``sd = bf16_weights(sd)``) mirrors the kernels' bf16 storage points."""
     d = sd["in_proj.weight"].shape[0]
-    h = torch.cat([x_t, cond], dim=-1) @ sd["in_proj.weight"].t() + sd["in_proj.bias"]
-    e = sinusoidal_embedding(t, d)
-    e = e @ sd["time_mlp.0.weight"].t() + sd["time_mlp.0.bias"]
-    e = e * (1.0 / (1.0 + torch.exp(-e)))                                   # SiLU
-    e = e @ sd["time_mlp.2.weight"].t() + sd["time_mlp.2.bias"]
-    h = h + e.unsqueeze(1) + sd["pos_embedding"][: h.shape[1]].unsqueeze(0)
+    h = rnd(rnd(torch.cat([x_t, cond], dim=-1)) @ sd["in_proj.weight"].t() + sd["in_proj.bias"])
+    e = rnd(sinusoidal_embedding(t, d))
+    e = rnd(e @ sd["time_mlp.0.weight"].t() + sd["time_mlp.0.bias"])
+    e = rnd(e * (1.0 / (1.0 + torch.exp(-e))))                              # SiLU
+    e = rnd(e @ sd["time_mlp.2.weight"].t() + sd["time_mlp.2.bias"])
+    h = rnd(h + e.unsqueeze(1) + sd["pos_embedding"][: h.shape[1]].unsqueeze(0))
     for l in range(num_layers):
-        h = transformer_layer(sd, f"layers.{l}.", h, num_heads)
+        h = transformer_layer(sd, f"layers.{l}.", h, num_heads, rnd)
     return h @ sd["out_proj.weight"].t() + sd["out_proj.bias"]

@@ -237,3 +237,96 @@ def test_gemm_pad_column_contract():
     leaked = (out.double().cpu() - ref).abs().max().item()
     assert leaked < 1e-3 or abs(leaked - 4.0) < 1e-2, leaked
     print("TMA inner-dimension bound granularity:", "16-byte chunk (pads must be zero)" if leaked > 1 else "element")
+
+
+# ---------------------------------------------------------------------------------------------------
+# The EXACT GEMM shapes of the benchmarked denoiser step (BASELINE configs[1]: 4096 windows x 50 frames = 204 800
+# rows, d = 512, FFN 2048, fused QKV 1536): forward / dgrad epilogue variants as engine.EncoderLayerPlan issues
+# them, and the weight gradients with their 204 800-long reduction (default split-K + TMA reduce-add).
+# Operands are generated on the device and the fp64 reference product runs on the device too (the CPU would
+# need minutes for 4 x 10^11 multiply-adds); same tolerance as above.
+# ---------------------------------------------------------------------------------------------------
+M_BENCH = 204800
+
+
+def _dev(rows, cols, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(rows, cols, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+def _check_dev(out, ref, bf16_out, what):
+    scale = ref.abs().max().item() + 1e-30
+    err = (out.double() - ref).abs().max().item()
+    tol = (1.0 / 128 if bf16_out else 2e-4) * scale
+    assert err <= tol, f"{what}: max abs err {err:.4g} > {tol:.4g} (scale {scale:.4g})"
+
+
+@pytest.mark.parametrize("name,N,K,kind", [
+    ("qkv", 1536, 512, "bias"), ("out_proj", 512, 512, "residual"), ("ffn1", 2048, 512, "relu_mask"), ("ffn2", 512, 2048, "residual"),
+])
+def test_gemm_bench_shapes_forward(name, N, K, kind):
+    from inferbiomechanics_b200 import ops
+    M = M_BENCH
+    A, W = _dev(M, K, 1), _dev(N, K, 2, 1.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=torch.Generator(device="cuda").manual_seed(3), device="cuda")
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ref = A.double() @ W.double().t() + bias.double()
+    if kind == "bias":
+        ops.gemm(A, W, out, M, N, K, bias=bias)
+    elif kind == "residual":
+        aux = _dev(M, N, 4)
+        ops.gemm(A, W, out, M, N, K, bias=bias, aux=aux, aux_mode=1)
+        ref += aux.double()
+    else:
+        mask = torch.zeros(M, N // 8, dtype=torch.uint8, device="cuda")
+        ops.gemm(A, W, out, M, N, K, bias=bias, act="relu", mask=mask, mask_mode=1)
+        ref.clamp_min_(0)
+        bits = (mask.unsqueeze(-1) >> torch.arange(8, device="cuda", dtype=torch.uint8)) & 1
+        assert torch.equal(bits.view(M, N).bool(), out > 0)
+    _check_dev(out, ref, True, f"{name} forward at M={M}")
+
+
+@pytest.mark.parametrize("name,N,K,kind", [
+    ("ffn2_dgrad", 2048, 512, "mask_colsum"), ("ffn1_dgrad", 512, 2048, "residual"), ("out_proj_dgrad", 512, 512, "plain"),
+    ("in_proj_dgrad", 512, 1536, "residual"),
+])
+def test_gemm_bench_shapes_dgrad(name, N, K, kind):
+    """dX[M,N] = dY[M,K] · W[K,N] (W row-major = MN-major B operand), epilogues as in EncoderLayerPlan.backward."""
+    from inferbiomechanics_b200 import ops
+    M = M_BENCH
+    dY, W = _dev(M, K, 11), _dev(K, N, 12, 1.0 / math.sqrt(K))
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ref = dY.double() @ W.double()
+    if kind == "plain":
+        ops.gemm(dY, W, out, M, N, K, b_mn=True)
+    elif kind == "residual":
+        aux = _dev(M, N, 13)
+        ops.gemm(dY, W, out, M, N, K, b_mn=True, aux=aux, aux_mode=1)
+        ref += aux.double()
+    else:
+        g = torch.Generator(device="cuda").manual_seed(14)
+        mask = torch.randint(0, 256, (M, N // 8), generator=g, device="cuda", dtype=torch.uint8)
+        cs = torch.zeros(N, device="cuda")
+        ops.gemm(dY, W, out, M, N, K, b_mn=True, mask=mask, mask_mode=2, colsum=cs)
+        bits = ((mask.unsqueeze(-1) >> torch.arange(8, device="cuda", dtype=torch.uint8)) & 1).view(M, N)
+        ref *= bits.double()
+        torch.testing.assert_close(cs.double(), out.double().sum(0), rtol=1e-4, atol=1e-3 * math.sqrt(M))
+    _check_dev(out, ref, True, f"{name} at M={M}")
+
+
+@pytest.mark.parametrize("name,Nout,Kin", [("ffn2_wgrad", 512, 2048), ("ffn1_wgrad", 2048, 512), ("out_proj_wgrad", 512, 512),
+                                           ("qkv_wgrad", 1536, 512), ("head_wgrad", 30, 512)])
+def test_gemm_bench_shapes_wgrad(name, Nout, Kin):
+    """dW[Nout,Kin] += dY^T · X over a 204 800-long reduction, the engine's default split-K."""
+    from inferbiomechanics_b200 import ops
+    M = M_BENCH
+    ldn = ops.round_up(Nout, 8)
+    dY = torch.zeros(M, ldn, dtype=torch.bfloat16, device="cuda")
+    dY[:, :Nout] = _dev(M, Nout, 21)
+    X = _dev(M, Kin, 22)
+    init = torch.randn(Nout, Kin, generator=torch.Generator(device="cuda").manual_seed(23), device="cuda")
+    dW = init.clone()
+    ops.gemm(dY, X, dW, Nout, Kin, M, a_mn=True, b_mn=True, accumulate=True)
+    ref = init.double() + dY[:, :Nout].double().t() @ X.double()
+    # fp32 accumulation of 204 800 products of unit-variance terms: scale ~ sqrt(M); same relative bar as above
+    _check_dev(dW, ref, False, f"{name} reduction {M}")

@@ -51,7 +51,8 @@ def l2close(got, ref, frac, what=""):
 # FeedForwardBaseline: same class name / ctor / forward contract as the reference
 # ---------------------------------------------------------------------------------------------------
 FF_CASES = {"sigmoid_all": ("sigmoid", "all_frames"), "relu_last": ("relu", "last_frame"), "tanh_all": ("tanh", "all_frames"),
-            "sigmoid_bn": ("sigmoid", "all_frames")}      # sigmoid_bn: batchnorm=True in eval mode (running statistics)
+            "sigmoid_bn": ("sigmoid", "all_frames"),      # sigmoid_bn: batchnorm=True in eval mode (running statistics)
+            "sigmoid_cfg0": ("sigmoid", "all_frames")}    # BASELINE configs[0] as stated: hidden [512, 512], batch 32
 
 
 @pytest.mark.parametrize("name", list(FF_CASES))
@@ -349,6 +350,64 @@ def test_denoiser_forward_backward_vs_oracle():
     loss.backward()
     for n, p in m.named_parameters():
         l2close(p.grad, params[n].grad, 0.15, n)
+
+
+def _denoiser_parity(B, F, d, heads, ff, L, seed, mirror_bar):
+    """One training forward + loss + backward of the denoiser through the drop-in module against
+    (1) the fp32 oracle (loose gradient bar: gate flips) and (2) the fp32 oracle evaluated on bf16-rounded weights
+    with straight-through bf16 rounding at the kernels' storage points (same ReLU gates → tight bar)."""
+    from inferbiomechanics_b200.keys import InputDataKeys
+    from inferbiomechanics_b200.loss.RegressionLossEvaluator import RegressionLossEvaluator
+    m, sd = _small_denoiser(F=F, d=d, heads=heads, ff=ff, L=L, seed=seed)
+    inputs = seeded_inputs(B, F, 23, 30, 900 + seed)
+    g = torch.Generator().manual_seed(seed)
+    x_t = torch.randn(B, F, 30, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    _, labels = seeded_out_labels(B, F, 901 + seed)
+    sel = [list(x) for x in SELECTIONS["all"]]
+    cond = om.concat_inputs(inputs)
+
+    def run_oracle(mirror):
+        params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        if mirror:
+            x0 = om.denoiser_forward(om.bf16_weights(params), cond, x_t, t, L, heads, rnd=om.bf16_ste)
+        else:
+            x0 = om.denoiser_forward(params, cond, x_t, t, L, heads)
+        loss = ol.regression_loss(om.split30(x0), labels, *sel)["loss"]
+        loss.backward()
+        return x0.detach(), loss.detach(), {k: v.grad for k, v in params.items()}
+
+    ref, ref_loss, ref_g = run_oracle(False)
+    mir, mir_loss, mir_g = run_oracle(True)
+    out = m({**inputs, InputDataKeys.X_T: x_t, InputDataKeys.TIMESTEP: t})
+    got = torch.cat([out[k] for k in Q], dim=-1)
+    close(got.detach(), ref, 3e-2, "x0_hat vs fp32 oracle")
+    close(got.detach(), mir, 1e-2, "x0_hat vs bf16-mirroring oracle")
+    ev = RegressionLossEvaluator(None, "train", device="cuda")
+    loss = ev(inputs, out, {k: v.clone() for k, v in labels.items()}, [], [], ALL)
+    np.testing.assert_allclose(loss.item(), ref_loss.item(), rtol=2e-2)
+    np.testing.assert_allclose(loss.item(), mir_loss.item(), rtol=5e-3)
+    for p in m.parameters():
+        p.grad = None
+    loss.backward()
+    worst = (0.0, "")
+    for n, p in m.named_parameters():
+        l2close(p.grad, ref_g[n], 0.15, n + " vs fp32 oracle")
+        gg, rr = p.grad.double().cpu().reshape(-1), mir_g[n].double().reshape(-1)
+        e = (gg - rr).norm().item() / (rr.norm().item() + 1e-30)
+        worst = max(worst, (e, n))
+        assert e <= mirror_bar, f"{n}: relative L2 error {e:.4g} vs the bf16-mirroring oracle > {mirror_bar}"
+    print(f"denoiser d={d} L={L} F={F} B={B}: worst gradient rel-L2 vs mirrored oracle {worst[0]:.4g} ({worst[1]})")
+
+
+def test_denoiser_small_vs_mirrored_oracle():
+    _denoiser_parity(B=6, F=10, d=128, heads=2, ff=256, L=2, seed=5, mirror_bar=2e-2)
+
+
+def test_denoiser_bench_config_step_vs_oracle():
+    """BASELINE configs[1] exactly — d=512, 8 heads x 64, FFN 2048, 8 layers, F=50 frames — at a batch the CPU oracle
+    finishes in seconds (B=8: 400 rows).  Every parameter gradient of the 25 M-parameter model is compared."""
+    _denoiser_parity(B=8, F=50, d=512, heads=8, ff=2048, L=8, seed=7, mirror_bar=2e-2)
 
 
 def test_denoiser_trainer_step_runs_and_learns():
