@@ -308,6 +308,19 @@ int ibm_attention_bwd(const void* qkv, int64_t ld_qkv, int64_t kv_off, const voi
                       void* dqkv, int64_t n_win, int32_t T, int32_t H, int32_t head_dim, float scale,
                       float* dbias_qkv, void* stream);
 
+/* Backward of the same attention for whole windows of up to 256 frames (the reference's own TransformerBaseline shapes:
+ * 3 heads x 36 -> 48 padded at T = window_size, TransformerBaseline.py:12-13,29; and SimpleAttention, …:51-70, with
+ * (hd_qk, hd_v) = (112, 8), dv = NULL because its values are a model INPUT).  q,k,v,o,d_o as in ibm_attention_fwd
+ * (o = the forward output); dq,dk,dv: bf16 outputs with their own leading dimensions (head h at columns h*hd).
+ * Probabilities are recomputed on chip.  dbias_q/k/v (each may be NULL): fp32 [H*hd] vectors the column sums of
+ * dq/dk/dv are ADDED to (in_proj_bias / query_linear.bias / key_linear.bias gradients).
+ * Supported: (64,64) (48,48) (32,32) with dv, (112,8) without. */
+int ibm_attention_bwd_long(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                           const void* o, int64_t ldo, const void* d_o, int64_t ld_do, void* dq, int64_t lddq,
+                           void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t n_win, int32_t T, int32_t H,
+                           int32_t hd_qk, int32_t hd_v, float scale, float* dbias_q, float* dbias_k, float* dbias_v,
+                           void* stream);
+
 /* ---- optimizers  (src/cli/train.py:183-197, 284; torch.optim defaults) ------------------------ */
 
 /* One fused step over a flat fp32 parameter arena: reads grad (scaled by grad_scale, e.g.

@@ -15,8 +15,13 @@ weight rows/columns), so results are those of the unpadded model.  GEMMs run in 
 fp32 accumulation; the reference computes in fp64 — tolerance stated in tests/test_gpu_transformer.py.
 The whole sequence (T <= 256) of a (window, head) stays in shared memory; long streams shard by window.
 
-Scope: inference (BASELINE configs[4], the analyze pass).  Training this model is not wired in the
-reference CLI either (it is imported nowhere); outputs carry no autograd graph.
+Inference (BASELINE configs[4], the analyze pass) runs under ``torch.no_grad()`` over re-used buffers.  With autograd
+enabled the outputs carry a graph (``_TransformerFunction``): the backward of the whole stack — both heads, the CoM blend
+(``ibm_attention_bwd_long`` without dv: its values are a model input), every layer (attention backward for whole
+windows of up to 256 frames, LayerNorm backward over the 108 valid of 112 columns, tcgen05 dgrad / wgrad GEMMs) and
+the temporal-embedding gradient (a sum over windows of the last 30 input-gradient columns) — runs on libibm_b200 and
+hands fp64 gradients back to the reference-shaped ``nn.Parameter``s, so ``loss.backward(); optimizer.step()`` works as
+on the reference.  Dropout > 0 in training mode is not implemented (the reference default is 0.0).
 """
 from __future__ import annotations
 
@@ -64,6 +69,23 @@ def _pad_head(n: int) -> int:
         if n <= c:
             return c
     raise NotImplementedError(f"head_dim {n} > 64 is not supported by the attention kernel")
+
+
+class _TransformerFunction(torch.autograd.Function):
+    """Autograd bridge for training: forward/backward are launch sequences over saved activations; the parameter
+    tensors are passed only so that autograd (and DDP's hooks) see them."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        out, blend, saved = model._forward_launches(x, save=True)
+        ctx.model, ctx.saved = model, saved
+        return out.clone(), blend.float()
+
+    @staticmethod
+    def backward(ctx, g_out, g_blend):
+        grads = ctx.model._backward_launches(ctx.saved, g_out, g_blend)
+        ctx.saved = None
+        return (None, None, *grads)
 
 
 class TransformerBaseline(nn.Module):
@@ -146,6 +168,7 @@ class TransformerBaseline(nn.Module):
             z = lambda c, dt=BF16: torch.zeros(M, c, dtype=dt, device=dev)
             self._bufs[M] = dict(xa=z(dp), xb=z(dp), qkv=z(3 * H * hp), o=z(H * hp), s=z(dp), x1=z(dp), h=z(fp), qk=z(2 * dp),
                                  v=z(8), blend=z(8), out=z(12, torch.float32))
+            self._bufs[M]["s2"] = self._bufs[M]["s"]      # inference: both pre-LayerNorm sums share one buffer
         return self._bufs[M]
 
     # ---- host-fed stream (BASELINE configs[4]: the analysis pass over a long window stream) -----------------
@@ -208,45 +231,148 @@ class TransformerBaseline(nn.Module):
         yield pending["host"]
 
     # ---- forward (TransformerBaseline.py:104-148) ---------------------------------------------------------
-    @torch.no_grad()
     def forward(self, x: Dict[str, torch.Tensor]):
         p0 = next(self.parameters())
         if not p0.is_cuda:
             raise _lib.IbmError("TransformerBaseline runs only on a B200: move it to CUDA (no CPU fallback)")
-        dev = p0.device
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if train:
+            if self.training and any(m.p > 0.0 for m in self.modules() if isinstance(m, nn.Dropout)):
+                raise NotImplementedError("TransformerBaseline training with dropout > 0 is not implemented on the B200 path")
+            out, blend = _TransformerFunction.apply(self, x, *self.parameters())
+        else:
+            with torch.no_grad():
+                out, blend, _ = self._forward_launches(x, save=False)
+        batch_size, T = out.shape[0], out.shape[1]
+        dt = self.fc.weight.dtype
+        return {
+            OutputDataKeys.CONTACT: torch.sigmoid(out[:, :, :2]).transpose(1, 2).to(dt),
+            OutputDataKeys.COM_ACC: blend.view(batch_size, T, 8)[:, :, :3].transpose(1, 2).to(dt),
+            OutputDataKeys.CONTACT_FORCES: out[:, :, 5:11].transpose(1, 2).to(dt),
+        }
+
+    def _forward_launches(self, x: Dict[str, torch.Tensor], save: bool):
+        """Returns (out fp32 (B, T, 12), blend bf16 (B*T, 8), saved activations or None).  ``save`` keeps every layer's
+        activations in fresh buffers for the backward; inference ping-pongs two."""
+        dev = next(self.parameters()).device
         P = self._prepare(dev)
         d, dp, H, hp = P["d"], P["dp"], self.num_heads, P["hp"]
         batch_size = x[InputDataKeys.POS].size(0)
         # (q, dq, ddq, com_pos, com_vel, com_acc) per timestep; inputs are (B, C, T) → (B, T, C)   (…:108-116)
-        parts = [x[k].to(dev, torch.float32).contiguous() for k in (InputDataKeys.POS, InputDataKeys.VEL, InputDataKeys.ACC,
-                                                                    InputDataKeys.COM_POS, InputDataKeys.COM_VEL, InputDataKeys.COM_ACC)]
+        parts = [x[k].detach().to(dev, torch.float32).contiguous() for k in (InputDataKeys.POS, InputDataKeys.VEL, InputDataKeys.ACC,
+                                                                             InputDataKeys.COM_POS, InputDataKeys.COM_VEL, InputDataKeys.COM_ACC)]
         T = parts[0].size(2)
         assert T == self.window_size, "TemporalEmbedding.expand needs T == window_size (…:121-123)"
         M = batch_size * T
-        b = self._act_buffers(M, dev, P)
+        b = self._train_buffers(M, dev, P) if save else self._act_buffers(M, dev, P)
         # cat(dim=1) + transpose(1, 2) + temporal embedding CONCATENATED, not added (…:108-126): one kernel, (B, C, T) fp32 in,
         # bf16 rows [B*T, 112] out
         ops.pack_channel_major(parts, T, P["emb"], b["xa"])
         cur, nxt = b["xa"], b["xb"]
         scale = 1.0 / math.sqrt(P["hd"])
-        for L in P["layers"]:
-            ops.gemm(cur, L["wqkv"], b["qkv"], M, 3 * H * hp, dp, bias=L["bqkv"])
-            ops.attention_fwd_fused(b["qkv"], H * hp, b["o"], batch_size, T, H, hp, scale)
-            ops.gemm(b["o"], L["wo"], b["s"], M, dp, H * hp, bias=L["bo"], aux=cur, aux_mode=1)
-            ops.layernorm_fwd(b["s"], b["x1"], L["g1"], L["be1"], M, d)
-            ops.gemm(b["x1"], L["w1"], b["h"], M, P["fp"], dp, bias=L["b1"], act="relu")
-            ops.gemm(b["h"], L["w2"], b["s"], M, dp, P["fp"], bias=L["b2"], aux=b["x1"], aux_mode=1)
-            ops.layernorm_fwd(b["s"], nxt, L["g2"], L["be2"], M, d)
-            cur, nxt = nxt, cur
+        acts = []
+        for li, L in enumerate(P["layers"]):
+            a = b["layers"][li] if save else b
+            if save:
+                nxt = a["x2"]
+            ops.gemm(cur, L["wqkv"], a["qkv"], M, 3 * H * hp, dp, bias=L["bqkv"])
+            ops.attention_fwd_fused(a["qkv"], H * hp, a["o"], batch_size, T, H, hp, scale)
+            ops.gemm(a["o"], L["wo"], a["s"], M, dp, H * hp, bias=L["bo"], aux=cur, aux_mode=1)
+            ops.layernorm_fwd(a["s"], a["x1"], L["g1"], L["be1"], M, d, mean=a.get("mean1"), rstd=a.get("rstd1"))
+            ops.gemm(a["x1"], L["w1"], a["h"], M, P["fp"], dp, bias=L["b1"], act="relu")
+            ops.gemm(a["h"], L["w2"], a["s2"], M, dp, P["fp"], bias=L["b2"], aux=a["x1"], aux_mode=1)
+            ops.layernorm_fwd(a["s2"], nxt, L["g2"], L["be2"], M, d, mean=a.get("mean2"), rstd=a.get("rstd2"))
+            if save:
+                acts.append(dict(a, x_in=cur))
+                cur = nxt
+            else:
+                cur, nxt = nxt, cur
         ops.gemm(cur, P["fc_w"], b["out"], M, self.output_vector_dim, dp, bias=P["fc_b"])
         # CoM acceleration as an (unscaled) attention blend over the input CoM accelerations (…:51-70, 135-137)
         ops.gemm(cur, P["wqk"], b["qk"], M, 2 * dp, dp, bias=P["bqk"])
         ops.pack_channel_major(parts[5:6], T, None, b["v"])            # CoM accelerations as the (3 -> 8)-wide values of the blend
         ops.attention_fwd(b["qk"][:, :dp], b["qk"][:, dp:], b["v"], b["blend"], batch_size, T, 1, dp, 8, 1.0)
-        out = b["out"].view(batch_size, T, 12)
-        dt = self.fc.weight.dtype
-        return {
-            OutputDataKeys.CONTACT: torch.sigmoid(out[:, :, :2]).transpose(1, 2).to(dt),
-            OutputDataKeys.COM_ACC: b["blend"].view(batch_size, T, 8)[:, :, :3].transpose(1, 2).to(dt),
-            OutputDataKeys.CONTACT_FORCES: out[:, :, 5:11].transpose(1, 2).to(dt),
-        }
+        saved = dict(acts=acts, last=cur, qk=b["qk"], v=b["v"], blend=b["blend"], M=M, B=batch_size, T=T, P=P) if save else None
+        return b["out"].view(batch_size, T, 12), b["blend"], saved
+
+    def _train_buffers(self, M: int, dev, P):
+        """Fresh activation buffers for one training forward (kept alive by the autograd node until its backward)."""
+        H, hp, dp, fp = self.num_heads, P["hp"], P["dp"], P["fp"]
+        z = lambda c, dt=BF16: torch.zeros(M, c, dtype=dt, device=dev)
+        f = lambda: torch.empty(M, dtype=torch.float32, device=dev)
+        layers = [dict(qkv=z(3 * H * hp), o=z(H * hp), s=z(dp), x1=z(dp), h=z(fp), s2=z(dp), x2=z(dp), mean1=f(), rstd1=f(), mean2=f(),
+                       rstd2=f()) for _ in range(self.num_layers)]
+        return dict(xa=z(dp), xb=None, layers=layers, qk=z(2 * dp), v=z(8), blend=z(8), out=z(12, torch.float32))
+
+    # ---- backward (autograd of TransformerBaseline.py:104-148 through the same kernels' transposes) -------------
+    def _backward_launches(self, sv, g_out: torch.Tensor, g_blend: torch.Tensor):
+        P, M, B, T = sv["P"], sv["M"], sv["B"], sv["T"]
+        d, dp, H, hp, hd, fp = P["d"], P["dp"], self.num_heads, P["hp"], P["hd"], P["fp"]
+        dev = sv["last"].device
+        zb = lambda c: torch.zeros(M, c, dtype=BF16, device=dev)
+        zf = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        scale = 1.0 / math.sqrt(hd)
+        # --- heads: fc (d -> 11) and the CoM blend's query / key projections, all reading the last layer's output ---
+        dout = zb(16)
+        ops.cast_pad(g_out.contiguous().view(M, 12), dout, M, 11)
+        g_fc_w, g_fc_b = zf(self.output_vector_dim, dp), zf(16)
+        ops.gemm(dout, sv["last"], g_fc_w, self.output_vector_dim, dp, M, a_mn=True, b_mn=True, accumulate=True)
+        ops.colsum(dout, M, self.output_vector_dim, g_fc_b)
+        dxa, dxb = zb(dp), zb(dp)
+        ops.gemm(dout, P["fc_w"], dxa, M, dp, self.output_vector_dim, b_mn=True)
+        dblend, dqk = zb(8), zb(2 * dp)
+        ops.cast_pad(g_blend.contiguous().view(M, 8), dblend, M, 3)
+        ops.attention_bwd_long(sv["qk"][:, :dp], sv["qk"][:, dp:], sv["v"], sv["blend"], dblend, dqk[:, :dp], dqk[:, dp:], None,
+                               B, T, 1, dp, 8, 1.0)
+        g_wqk, g_bqk = zf(2 * dp, dp), zf(2 * dp)
+        ops.gemm(dqk, sv["last"], g_wqk, 2 * dp, dp, M, a_mn=True, b_mn=True, accumulate=True)
+        ops.colsum(dqk, M, 2 * dp, g_bqk)
+        ops.gemm(dqk, P["wqk"], dxb, M, dp, 2 * dp, b_mn=True, aux=dxa, aux_mode=1)
+        dx, other = dxb, dxa
+        # --- layers, last to first (TransformerBaseline.py:24-38 reversed) ---
+        ds, dh, dx1, do, dqkv = zb(dp), zb(fp), zb(dp), zb(H * hp), zb(3 * H * hp)
+        lg = []
+        for li in range(self.num_layers - 1, -1, -1):
+            L, a = P["layers"][li], sv["acts"][li]
+            g = dict(wqkv=zf(3 * H * hp, dp), bqkv=zf(3 * H * hp), wo=zf(dp, H * hp), bo=zf(dp), w1=zf(fp, dp), b1=zf(fp),
+                     w2=zf(dp, fp), b2=zf(dp), g1=zf(dp), be1=zf(dp), g2=zf(dp), be2=zf(dp))
+            ops.layernorm_bwd(dx, a["s2"], L["g2"], a["mean2"], a["rstd2"], M, d, ds, g["g2"], g["be2"], g["b2"])
+            ops.gemm(ds, a["h"], g["w2"], dp, fp, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(ds, L["w2"], dh, M, fp, dp, b_mn=True, act="relu", aux=a["h"], aux_mode=2, colsum=g["b1"])
+            ops.gemm(dh, a["x1"], g["w1"], fp, dp, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dh, L["w1"], dx1, M, dp, fp, b_mn=True, aux=ds, aux_mode=1)
+            ops.layernorm_bwd(dx1, a["s"], L["g1"], a["mean1"], a["rstd1"], M, d, ds, g["g1"], g["be1"], g["bo"])
+            ops.gemm(ds, a["o"], g["wo"], dp, H * hp, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(ds, L["wo"], do, M, H * hp, dp, b_mn=True)
+            qkv, w = a["qkv"], H * hp
+            ops.attention_bwd_long(qkv[:, :w], qkv[:, w:2 * w], qkv[:, 2 * w:], a["o"], do, dqkv[:, :w], dqkv[:, w:2 * w],
+                                   dqkv[:, 2 * w:], B, T, H, hp, hp, scale, dbq=g["bqkv"][:w], dbk=g["bqkv"][w:2 * w],
+                                   dbv=g["bqkv"][2 * w:])
+            ops.gemm(dqkv, a["x_in"], g["wqkv"], 3 * w, dp, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dqkv, L["wqkv"], other, M, dp, 3 * w, b_mn=True, aux=ds, aux_mode=1)
+            dx, other = other, dx
+            lg.append(g)
+        lg.reverse()
+        # --- temporal embedding: rows of the table were concatenated as input columns [d - E, d) of every window (…:121-126) ---
+        E = self.temporal_embedding_dim
+        g_in = zf(T * dp)
+        ops.colsum(dx.view(B, T * dp), B, T * dp, g_in)
+        g_emb = torch.zeros_like(self.temporal_embedding.embedding.weight, dtype=torch.float32)
+        g_emb[:T] = g_in.view(T, dp)[:, d - E:d]
+        # --- un-pad into the reference's parameter shapes, in self.parameters() order ---
+        by_name = {"temporal_embedding.embedding.weight": g_emb, "fc.weight": g_fc_w[:, :d], "fc.bias": g_fc_b[:self.output_vector_dim],
+                   "com_attention.query_linear.weight": g_wqk[:d, :d], "com_attention.query_linear.bias": g_bqk[:d],
+                   "com_attention.key_linear.weight": g_wqk[dp:dp + d, :d], "com_attention.key_linear.bias": g_bqk[dp:dp + d]}
+        for li, g in enumerate(lg):
+            pre = f"transformer_layers.{li}."
+            by_name[pre + "multihead_attention.in_proj_weight"] = g["wqkv"].view(3, H, hp, dp)[:, :, :hd, :d].reshape(3 * d, d)
+            by_name[pre + "multihead_attention.in_proj_bias"] = g["bqkv"].view(3, H, hp)[:, :, :hd].reshape(3 * d)
+            by_name[pre + "multihead_attention.out_proj.weight"] = g["wo"].view(dp, H, hp)[:d, :, :hd].reshape(d, d)
+            by_name[pre + "multihead_attention.out_proj.bias"] = g["bo"][:d]
+            by_name[pre + "feedforward.0.weight"] = g["w1"][:self.dim_feedforward, :d]
+            by_name[pre + "feedforward.0.bias"] = g["b1"][:self.dim_feedforward]
+            by_name[pre + "feedforward.2.weight"] = g["w2"][:d, :self.dim_feedforward]
+            by_name[pre + "feedforward.2.bias"] = g["b2"][:d]
+            by_name[pre + "norm1.weight"], by_name[pre + "norm1.bias"] = g["g1"][:d], g["be1"][:d]
+            by_name[pre + "norm2.weight"], by_name[pre + "norm2.bias"] = g["g2"][:d], g["be2"][:d]
+        return [by_name[n].to(p.dtype).reshape(p.shape) if p.requires_grad else None for n, p in self.named_parameters()]

@@ -175,6 +175,14 @@ def attention_bwd(qkv, kv_off, d_o, dqkv, n_win, T, H, hd, scale, dbias=None):
          _p(dbias), stream_ptr())
 
 
+def attention_bwd_long(q, k, v, o, d_o, dq, dk, dv, n_win, T, H, hd_qk, hd_v, scale, dbq=None, dbk=None, dbv=None):
+    """Backward for whole windows of up to 256 frames (ibm_attention_bwd_long): q/k/v/o/d_o/dq/dk/dv are bf16 row-major
+    views (one row per (window, frame), head h at columns h*hd); dv None when the values are an input."""
+    call("ibm_attention_bwd_long", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(d_o),
+         d_o.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), 0 if dv is None else dv.stride(0), n_win, T, H,
+         hd_qk, hd_v, scale, _p(dbq), _p(dbk), _p(dbv), stream_ptr())
+
+
 # ---- regression loss ------------------------------------------------------------------------------
 def _ptr_array(ts: Sequence[torch.Tensor]):
     arr = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in ts])

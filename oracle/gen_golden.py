@@ -231,6 +231,41 @@ def gen_transformer(ref):
     np.savez_compressed(os.path.join(OUT, "transformer.npz"), **d)
 
 
+def gen_transformer_bwd(ref):
+    """Autograd backward of the same composition (TransformerBaseline.py:104-148, fp64): loss = sum over the three outputs of
+    <output, seeded cotangent>; every parameter gradient is frozen (fp32 copies: 208 k parameters per case)."""
+    d = {}
+    D = 23
+    for ci, (name, B, T) in enumerate([("t20", 3, 20), ("t64", 2, 64), ("t200", 2, 200)]):
+        m = ref.TransformerBaseline(D, T)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        seed = 1250 + ci
+        m.load_state_dict(seeded_state_dict(shapes, seed, dtype=torch.float64))
+        m.train()                                            # dropout p = 0.0: identical to eval
+        x = {k: seeded_tensor((B, c, T), 2250 + ci + 10 * i, dtype=torch.float64)
+             for i, (k, c) in enumerate([("pos", D), ("vel", D), ("acc", D), ("comPos", 3), ("comVel", 3), ("comAcc", 3)])}
+        vecs = torch.cat([x["pos"], x["vel"], x["acc"], x["comPos"], x["comVel"], x["comAcc"]], dim=1).transpose(1, 2)
+        emb = m.temporal_embedding(torch.arange(vecs.size(1))).expand(B, T, m.temporal_embedding_dim)
+        vecs = torch.cat([vecs, emb], dim=2)
+        for layer in m.transformer_layers:
+            vecs = layer(vecs)
+        output = m.fc(vecs)
+        blend = m.com_attention(vecs, vecs, x["comAcc"].transpose(1, 2))
+        outs = {"contact": m.contact_sigmoid(output[:, :, :2]).transpose(1, 2), "comAcc": blend.transpose(1, 2),
+                "contactForces": output[:, :, 5:].transpose(1, 2)}
+        loss = 0.0
+        for i, (k, v) in enumerate(outs.items()):
+            cot = seeded_tensor(tuple(v.shape), 2290 + ci + 10 * i, dtype=torch.float64)
+            loss = loss + (v * cot).sum()
+            d[f"{name}/out/{k}"] = v.detach().numpy().astype(np.float32)
+        loss.backward()
+        d[f"{name}/loss"] = np.array(loss.item())
+        for n, p in m.named_parameters():
+            d[f"{name}/grad/{n}"] = p.grad.numpy().astype(np.float32)
+        d[f"{name}/meta"] = np.array([D, B, T, seed, 2250 + ci, 2290 + ci])
+    np.savez_compressed(os.path.join(OUT, "transformer_bwd.npz"), **d)
+
+
 def gen_denoiser_layers(ref):
     """Reference TransformerLayer at the denoiser's configuration family (fp32, heads×64)."""
     d = {}
@@ -347,6 +382,9 @@ def main():
     if "--only-ff" in __import__("sys").argv:
         gen_ff(ref)
         return
+    if "--only-transformer-bwd" in __import__("sys").argv:
+        gen_transformer_bwd(ref)
+        return
     if "--only-windows" in __import__("sys").argv:
         gen_windows(ref)
         return
@@ -355,6 +393,7 @@ def main():
     gen_ff_bn_train(ref)
     gen_groundlink(ref)
     gen_transformer(ref)
+    gen_transformer_bwd(ref)
     gen_denoiser_layers(ref)
     gen_windows(ref)
     for f in sorted(os.listdir(OUT)):

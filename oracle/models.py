@@ -127,6 +127,29 @@ def bf16_ste(x: torch.Tensor) -> torch.Tensor:
     return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
 
 
+class _RoundBoth(torch.autograd.Function):
+    """bf16 rounding of the value in forward AND of the incoming gradient in backward."""
+
+    @staticmethod
+    def forward(ctx, x, fwd):
+        return x.to(torch.bfloat16).to(x.dtype) if fwd else x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype), None
+
+
+def bf16_both(x: torch.Tensor) -> torch.Tensor:
+    """``bf16_ste`` plus the mirror image in backward: the CUDA path also STORES the gradient of every such activation
+    as bf16 (dqkv, do, ds, dh, dx1, dx), so the gradient flowing back through the storage point is rounded too."""
+    return _RoundBoth.apply(x, True)
+
+
+def bf16_grad(x: torch.Tensor) -> torch.Tensor:
+    """Identity forward, bf16-rounded gradient (the fp32 x0_hat output whose loss gradient the path casts to bf16)."""
+    return _RoundBoth.apply(x, False)
+
+
 def bf16_weights(sd: Mapping[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """GEMM weight matrices rounded to bf16 (the kernels' shadow arena); biases, LayerNorm parameters and the
     positional table stay fp32 (read from the master arena).  Straight-through, so gradients flow to ``sd``."""
@@ -146,13 +169,18 @@ def multihead_attention(x: torch.Tensor, in_w, in_b, out_w, out_b, num_heads: in
     return o @ out_w.t() + out_b
 
 
-def transformer_layer(sd: Mapping[str, torch.Tensor], prefix: str, x: torch.Tensor, num_heads: int, rnd=_identity) -> torch.Tensor:
+def transformer_layer(sd: Mapping[str, torch.Tensor], prefix: str, x: torch.Tensor, num_heads: int, rnd=_identity,
+                      gate: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``gate`` (0/1 tensor shaped like the FFN hidden activation): replaces the ReLU's own decision — the test harness
+    passes the gates the CUDA path took, so that a gradient comparison is not dominated by the few near-zero
+    pre-activations whose sign differs between two roundings of the same forward."""
     g = lambda n: sd[prefix + n]
     a = multihead_attention(x, g("multihead_attention.in_proj_weight"), g("multihead_attention.in_proj_bias"),
                             g("multihead_attention.out_proj.weight"), g("multihead_attention.out_proj.bias"),
                             num_heads, rnd)
     x = rnd(layer_norm(rnd(x + a), g("norm1.weight"), g("norm1.bias")))
-    h = rnd(torch.clamp_min(x @ g("feedforward.0.weight").t() + g("feedforward.0.bias"), 0.0))
+    pre = x @ g("feedforward.0.weight").t() + g("feedforward.0.bias")
+    h = rnd(torch.clamp_min(pre, 0.0) if gate is None else pre * gate)
     f = h @ g("feedforward.2.weight").t() + g("feedforward.2.bias")
     return rnd(layer_norm(rnd(x + f), g("norm2.weight"), g("norm2.bias")))
 
@@ -192,9 +220,10 @@ def sinusoidal_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
 
 
 def denoiser_forward(sd: Mapping[str, torch.Tensor], cond: torch.Tensor, x_t: torch.Tensor, t: torch.Tensor,
-                     num_layers: int, num_heads: int, rnd=_identity) -> torch.Tensor:
+                     num_layers: int, num_heads: int, rnd=_identity, gates=None) -> torch.Tensor:
     """cond (B,F,C_in) packed kinematics; x_t (B,F,30); t (B,) int64 → x0_hat (B,F,30).
-    ``rnd`` = ``bf16_ste`` (with ``sd = bf16_weights(sd)``) mirrors the kernels' bf16 storage points."""
+    ``rnd`` = ``bf16_ste`` / ``bf16_both`` (with ``sd = bf16_weights(sd)``) mirrors the kernels' bf16 storage points;
+    ``gates``: one 0/1 tensor (B,F,ff) per layer, see ``transformer_layer``."""
     d = sd["in_proj.weight"].shape[0]
     h = rnd(rnd(torch.cat([x_t, cond], dim=-1)) @ sd["in_proj.weight"].t() + sd["in_proj.bias"])
     e = rnd(sinusoidal_embedding(t, d))
@@ -203,5 +232,6 @@ def denoiser_forward(sd: Mapping[str, torch.Tensor], cond: torch.Tensor, x_t: to
     e = rnd(e @ sd["time_mlp.2.weight"].t() + sd["time_mlp.2.bias"])
     h = rnd(h + e.unsqueeze(1) + sd["pos_embedding"][: h.shape[1]].unsqueeze(0))
     for l in range(num_layers):
-        h = transformer_layer(sd, f"layers.{l}.", h, num_heads, rnd)
-    return h @ sd["out_proj.weight"].t() + sd["out_proj.bias"]
+        h = transformer_layer(sd, f"layers.{l}.", h, num_heads, rnd, None if gates is None else gates[l])
+    out = h @ sd["out_proj.weight"].t() + sd["out_proj.bias"]
+    return bf16_grad(out) if rnd is bf16_both else out

@@ -9,7 +9,7 @@ kernels compute in bf16 with fp32 accumulation against an fp32 (fp64 for the tra
                  error <= 0.15 per tensor: a bf16 forward flips the sign of a few near-zero ReLU
                  pre-activations relative to the fp32 oracle, and each flipped gate changes its
                  gradient entry completely (the gradients not downstream of a ReLU gate agree to ~1 %,
-                 see tests/diag_layer.py), so a max-norm bound is not meaningful there
+                 see tools/diag_layer.py), so a max-norm bound is not meaningful there
   trajectories : |err| <= 5e-2 * max|ref| after the tested number of reverse steps
 """
 import argparse
@@ -354,8 +354,12 @@ def test_denoiser_forward_backward_vs_oracle():
 
 def _denoiser_parity(B, F, d, heads, ff, L, seed, mirror_bar):
     """One training forward + loss + backward of the denoiser through the drop-in module against
-    (1) the fp32 oracle (loose gradient bar: gate flips) and (2) the fp32 oracle evaluated on bf16-rounded weights
-    with straight-through bf16 rounding at the kernels' storage points (same ReLU gates → tight bar)."""
+    (1) the fp32 oracle (loose gradient bar: ReLU gate flips) and (2) the fp32 oracle evaluated on bf16-rounded weights
+    with bf16 rounding at the kernels' storage points in forward AND backward and with the ReLU gates the CUDA path
+    itself took (read back from its saved activations) → tight bar.  Why the gates must be shared: two roundings of
+    the same forward differ by one bf16 ulp in places, ~0.3 % of the near-zero FFN pre-activations change sign, and
+    each flipped gate replaces its gradient entry completely — 4-5 % relative L2 on every upstream tensor with a
+    free-running mirrored oracle vs 0.3-0.9 % with shared gates (tools/diag_denoiser_grads.py prints the table)."""
     from inferbiomechanics_b200.keys import InputDataKeys
     from inferbiomechanics_b200.loss.RegressionLossEvaluator import RegressionLossEvaluator
     m, sd = _small_denoiser(F=F, d=d, heads=heads, ff=ff, L=L, seed=seed)
@@ -367,10 +371,10 @@ def _denoiser_parity(B, F, d, heads, ff, L, seed, mirror_bar):
     sel = [list(x) for x in SELECTIONS["all"]]
     cond = om.concat_inputs(inputs)
 
-    def run_oracle(mirror):
+    def run_oracle(mirror, gates=None):
         params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
         if mirror:
-            x0 = om.denoiser_forward(om.bf16_weights(params), cond, x_t, t, L, heads, rnd=om.bf16_ste)
+            x0 = om.denoiser_forward(om.bf16_weights(params), cond, x_t, t, L, heads, rnd=om.bf16_both, gates=gates)
         else:
             x0 = om.denoiser_forward(params, cond, x_t, t, L, heads)
         loss = ol.regression_loss(om.split30(x0), labels, *sel)["loss"]
@@ -378,8 +382,11 @@ def _denoiser_parity(B, F, d, heads, ff, L, seed, mirror_bar):
         return x0.detach(), loss.detach(), {k: v.grad for k, v in params.items()}
 
     ref, ref_loss, ref_g = run_oracle(False)
-    mir, mir_loss, mir_g = run_oracle(True)
     out = m({**inputs, InputDataKeys.X_T: x_t, InputDataKeys.TIMESTEP: t})
+    st = m.engine().state(B, True)
+    gates = [(st[f"L{l}.h"].float() > 0).float().cpu().view(B, F, ff) for l in range(L)]
+    mir, mir_loss, _ = run_oracle(True)                     # free-running mirror: outputs and loss
+    _, _, mir_g = run_oracle(True, gates)                   # shared gates: gradients
     got = torch.cat([out[k] for k in Q], dim=-1)
     close(got.detach(), ref, 3e-2, "x0_hat vs fp32 oracle")
     close(got.detach(), mir, 1e-2, "x0_hat vs bf16-mirroring oracle")
@@ -396,18 +403,18 @@ def _denoiser_parity(B, F, d, heads, ff, L, seed, mirror_bar):
         gg, rr = p.grad.double().cpu().reshape(-1), mir_g[n].double().reshape(-1)
         e = (gg - rr).norm().item() / (rr.norm().item() + 1e-30)
         worst = max(worst, (e, n))
-        assert e <= mirror_bar, f"{n}: relative L2 error {e:.4g} vs the bf16-mirroring oracle > {mirror_bar}"
-    print(f"denoiser d={d} L={L} F={F} B={B}: worst gradient rel-L2 vs mirrored oracle {worst[0]:.4g} ({worst[1]})")
+        assert e <= mirror_bar, f"{n}: relative L2 error {e:.4g} vs the bf16-mirroring same-gates oracle > {mirror_bar}"
+    print(f"denoiser d={d} L={L} F={F} B={B}: worst gradient rel-L2 vs mirrored same-gates oracle {worst[0]:.4g} ({worst[1]})")
 
 
 def test_denoiser_small_vs_mirrored_oracle():
-    _denoiser_parity(B=6, F=10, d=128, heads=2, ff=256, L=2, seed=5, mirror_bar=2e-2)
+    _denoiser_parity(B=6, F=10, d=128, heads=2, ff=256, L=2, seed=5, mirror_bar=1.5e-2)
 
 
 def test_denoiser_bench_config_step_vs_oracle():
     """BASELINE configs[1] exactly — d=512, 8 heads x 64, FFN 2048, 8 layers, F=50 frames — at a batch the CPU oracle
     finishes in seconds (B=8: 400 rows).  Every parameter gradient of the 25 M-parameter model is compared."""
-    _denoiser_parity(B=8, F=50, d=512, heads=8, ff=2048, L=8, seed=7, mirror_bar=2e-2)
+    _denoiser_parity(B=8, F=50, d=512, heads=8, ff=2048, L=8, seed=7, mirror_bar=1.5e-2)
 
 
 def test_denoiser_trainer_step_runs_and_learns():

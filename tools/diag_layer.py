@@ -1,5 +1,5 @@
 """Diagnostic (not a pytest): run one EncoderLayerPlan forward/backward and compare every
-intermediate with a torch fp32 recomputation on the GPU.  python tests/diag_layer.py [d heads ff B T]"""
+intermediate with a torch fp32 recomputation on the GPU.  python tools/diag_layer.py [d heads ff B T]"""
 import math
 import sys
 
