@@ -150,6 +150,7 @@ def transformer_analyze_leg(dev, world: int, pk: dict, B: int = 2048, T: int = 2
     g = torch.Generator(device=dev).manual_seed(11)
     chans = [(K.POS, D), (K.VEL, D), (K.ACC, D), (K.COM_POS, 3), (K.COM_VEL, 3), (K.COM_ACC, 3)]
     x = {k: torch.randn(B, c, T, device=dev, generator=g) for k, c in chans}
+    torch.set_grad_enabled(False)                     # the analysis pass (analyze.py:112-156 runs under torch.no_grad())
     for _ in range(20):                               # ~50 ms of work: a GPU that was idle needs it to reach its clocks
         m(x)
     e0, e1 = _events()
@@ -161,6 +162,7 @@ def transformer_analyze_leg(dev, world: int, pk: dict, B: int = 2048, T: int = 2
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n_batches
     kern = _per_kernel(lambda: m(x))
+    torch.set_grad_enabled(True)
     kern_ms = sum(v["ms"] for v in kern.values())
     # end to end: pinned host inputs, outputs read back
     xh = {k: v.cpu().pin_memory() for k, v in x.items()}

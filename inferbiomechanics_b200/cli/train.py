@@ -63,6 +63,19 @@ class _ResultLog:
         self.ev.print_report(args, reset=reset, log_to_wandb=log_to_wandb)
 
 
+class _TrainerOptimizer:
+    """``optimizer``-shaped handle on a native ``Trainer`` for ``load_latest_checkpoint`` (abstract_command.py:113-114)."""
+
+    def __init__(self, trainer: Trainer):
+        self.trainer = trainer
+
+    def state_dict(self):
+        return self.trainer.optimizer_state_dict()
+
+    def load_state_dict(self, sd):
+        self.trainer.load_optimizer_state_dict(sd)
+
+
 class TrainCommand(AbstractCommand):
     def __init__(self):
         super().__init__()
@@ -152,7 +165,9 @@ class TrainCommand(AbstractCommand):
             optimizer = getattr(torch.optim, {'adagrad': 'Adagrad', 'adam': 'Adam', 'sgd': 'SGD', 'rmsprop': 'RMSprop',
                                               'adadelta': 'Adadelta', 'adamax': 'Adamax'}[args.opt_type])(model.parameters(),
                                                                                                        lr=args.learning_rate)
-        epoch_checkpoint, _ = self.load_latest_checkpoint(model, checkpoint_dir=checkpoint_dir, optimizer=optimizer)
+        # the native trainer exposes load_state_dict/state_dict in torch.optim's layout, so the same call restores it
+        epoch_checkpoint, _ = self.load_latest_checkpoint(model, checkpoint_dir=checkpoint_dir,
+                                                          optimizer=_TrainerOptimizer(trainer) if native else optimizer)
         if native and epoch_checkpoint >= 0:
             trainer.arena.sync_shadow(force=True)        # parameters were replaced under the engine
 
@@ -202,9 +217,7 @@ class TrainCommand(AbstractCommand):
                         os.makedirs(os.path.dirname(model_path), exist_ok=True)
                         torch.save({'epoch': epoch, 'model_state_dict': model.state_dict(),
                                     'optimizer_state_dict': optimizer.state_dict() if optimizer is not None else
-                                    {'opt_type': args.opt_type, 'step': trainer.step_count,
-                                     'state0': None if trainer.state0 is None else trainer.state0.cpu(),
-                                     'state1': None if trainer.state1 is None else trainer.state1.cpu()}}, model_path)
+                                    trainer.optimizer_state_dict()}, model_path)
             logging.info('-' * 80)
             logging.info(f'[{rank=}] Epoch {epoch}/{args.epochs} Training Set Evaluation: ')
             logging.info('-' * 80)

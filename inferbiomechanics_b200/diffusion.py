@@ -62,10 +62,13 @@ class GaussianDiffusion:
         xc = eng.xc(B, False)
         key = (id(model), B)
         st = self._graphs.get(key)
-        if st is None:
+        if st is None or st["model"] is not model:
+            # the entry holds the model (its id() cannot be recycled while cached) and, below, the time-MLP table the
+            # captured launches read
             st = dict(x=torch.empty(M, 30, dtype=torch.float32, device=self.device),
                       t_a=torch.zeros(1, dtype=torch.int32, device=self.device),
-                      t_b=torch.zeros(1, dtype=torch.int32, device=self.device), graph=None, seed=None)
+                      t_b=torch.zeros(1, dtype=torch.int32, device=self.device), graph=None, seed=None, model=model, table=None,
+                      table_key=None)
             self._graphs[key] = st
         x, t_a, t_b = st["x"], st["t_a"], st["t_b"]
         if x_T is None:
@@ -92,9 +95,15 @@ class GaussianDiffusion:
                 cur, nxt = nxt, cur
             return x.view(B, F, 30).clone()
 
-        # two steps per CUDA graph: the timestep ping-pongs between two device words
+        # two steps per CUDA graph: the timestep ping-pongs between two device words.  The captured launches read the
+        # per-timestep time-MLP table through a baked-in pointer: the table is re-evaluated here whenever the weights changed
+        # (optimizer step, load_state_dict) and a NEW table tensor (or a new seed) forces a re-capture; the entry keeps the
+        # captured table alive.
         done = 0
-        if st["graph"] is None or st["seed"] != seed:
+        table = eng.temb_table(self.T) if self.use_temb_table else None
+        tkey = (getattr(eng, "_temb_key", None), None if table is None else table.data_ptr())
+        if st["graph"] is None or st["seed"] != seed or st["table_key"] != tkey:
+            st["table"], st["table_key"] = table, tkey
             step(t_a, t_b, None)                  # eager warm-up (real steps): allocates buffers, sets func attributes
             step(t_b, t_a, None)
             done = 2

@@ -254,8 +254,14 @@ class EncoderLayerPlan:
                  accumulate=True)
         ops.gemm(ds, A.shadow_of(n("multihead_attention.out_proj.weight"), (d, d)), do, M, d, d, b_mn=True)
         # attention backward → dqkv, with dbqkv = colsum(dqkv) accumulated by the same kernel
-        ops.attention_bwd(a["qkv"], d, do, dqkv, n_win, T, self.H, self.hd, 1.0 / math.sqrt(self.hd),
-                          dbias=g(n("multihead_attention.in_proj_bias")))
+        if T <= 64:
+            ops.attention_bwd(a["qkv"], d, do, dqkv, n_win, T, self.H, self.hd, 1.0 / math.sqrt(self.hd),
+                              dbias=g(n("multihead_attention.in_proj_bias")))
+        else:                                     # whole windows of up to 256 frames (the TransformerBaseline's T = 200)
+            qkv, db = a["qkv"], g(n("multihead_attention.in_proj_bias"))
+            ops.attention_bwd_long(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], a["o"], do, dqkv[:, :d], dqkv[:, d:2 * d],
+                                   dqkv[:, 2 * d:], n_win, T, self.H, self.hd, self.hd, 1.0 / math.sqrt(self.hd),
+                                   dbq=db[:d], dbk=db[d:2 * d], dbv=db[2 * d:])
         # in-proj: dWqkv += dqkv^T x ; dx = dqkv · Wqkv + ds (residual)
         ops.gemm(dqkv, x, g(n("multihead_attention.in_proj_weight"), (3 * d, d)), 3 * d, d, M, a_mn=True, b_mn=True,
                  accumulate=True)

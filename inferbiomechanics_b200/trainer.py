@@ -174,6 +174,73 @@ class Trainer:
         if hasattr(self.eng, "weights_changed"):
             self.eng.weights_changed()           # engines that cache re-laid-out weights (Groundlink's conv GEMM layouts)
 
+    # ---- optimizer state in torch.optim's own state_dict layout (checkpoints, train.py:270-278) -----------------------
+    _OPT_CLASS = {"adagrad": "Adagrad", "adam": "Adam", "sgd": "SGD", "rmsprop": "RMSprop", "adadelta": "Adadelta", "adamax": "Adamax"}
+    _OPT_STATE = {"rmsprop": ("square_avg", None), "adam": ("exp_avg", "exp_avg_sq"), "sgd": (None, None), "adagrad": ("sum", None),
+                  "adadelta": ("square_avg", "acc_delta"), "adamax": ("exp_avg", "exp_inf")}
+
+    def optimizer_state_dict(self) -> dict:
+        """What ``torch.optim.<Type>(model.parameters(), lr).state_dict()`` would hold after the same steps: per-parameter
+        state tensors (CPU copies of this trainer's flat state arenas, cut at the parameter offsets) keyed by the
+        parameter's position in ``model.parameters()``, plus torch's own ``param_groups`` defaults — so the reference's
+        ``optimizer.load_state_dict(checkpoint['optimizer_state_dict'])`` (abstract_command.py:113-114) accepts it."""
+        cls = getattr(torch.optim, self._OPT_CLASS[self.opt_type])
+        sd = cls(self.arena.params, lr=self.lr).state_dict()         # param_groups with torch's defaults, empty state
+        n0, n1 = self._OPT_STATE[self.opt_type]
+        if self.step_count > 0 and n0 is not None:
+            for i, name in enumerate(self.arena.names):
+                o, k = self.arena.offsets[name]
+                shape = self.arena.params[i].shape
+                st = {"step": torch.tensor(float(self.step_count)), n0: self.state0[o:o + k].view(shape).cpu().clone()}
+                if n1 is not None:
+                    st[n1] = self.state1[o:o + k].view(shape).cpu().clone()
+                sd["state"][i] = st
+        elif self.step_count > 0:                                    # SGD without momentum keeps no tensors
+            sd["state"] = {i: {"momentum_buffer": None} for i in range(len(self.arena.names))}
+        sd["ibm_b200"] = {"opt_type": self.opt_type, "step": self.step_count}
+        return sd
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        """Inverse of ``optimizer_state_dict``; also accepts a checkpoint written by the reference's torch optimizer of the
+        same type (same parameter order) and the flat blob of earlier versions of this trainer."""
+        if not sd:
+            return
+        if "state" not in sd:                                        # legacy flat blob {'opt_type','step','state0','state1'}
+            if sd.get("opt_type") != self.opt_type:
+                raise ValueError(f"checkpoint optimizer {sd.get('opt_type')!r} != --opt-type {self.opt_type!r}")
+            for dst, src in ((self.state0, sd.get("state0")), (self.state1, sd.get("state1"))):
+                if dst is not None and src is not None:
+                    dst.copy_(src)
+            self.step_count = int(sd.get("step", 0))
+            return
+        tag = sd.get("ibm_b200")
+        if tag is not None and tag["opt_type"] != self.opt_type:
+            raise ValueError(f"checkpoint optimizer {tag['opt_type']!r} != --opt-type {self.opt_type!r}")
+        n0, n1 = self._OPT_STATE[self.opt_type]
+        state = sd["state"]
+        if len(state) not in (0, len(self.arena.names)):
+            raise ValueError(f"optimizer state holds {len(state)} parameters, the model has {len(self.arena.names)}")
+        steps = set()
+        for i, name in enumerate(self.arena.names):
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                continue
+            if n0 is not None:
+                if n0 not in st or (n1 is not None and n1 not in st):
+                    raise ValueError(f"optimizer state of parameter {i} lacks {n0!r}/{n1!r}: not a {self._OPT_CLASS[self.opt_type]} checkpoint")
+                o, k = self.arena.offsets[name]
+                if st[n0].numel() != k:
+                    raise ValueError(f"optimizer state of {name} has {st[n0].numel()} elements, the parameter {k}")
+                self.state0[o:o + k].copy_(st[n0].reshape(-1))
+                if n1 is not None:
+                    self.state1[o:o + k].copy_(st[n1].reshape(-1))
+            if "step" in st:
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): the fused optimizer keeps one")
+        self.step_count = steps.pop() if steps else int(tag["step"]) if tag else 0
+        self._graphs.clear()
+
     # ---- evaluation (no_grad forward + loss), used by analyze / dev-eval ------------------------------
     @torch.no_grad()
     def eval_step(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:

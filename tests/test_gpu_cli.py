@@ -64,3 +64,55 @@ def test_window_store_file_roundtrip(tmp_path):
         f.write(b"XX")
     with pytest.raises(ValueError):
         WindowStore.load(p, 50, 5, "all_frames", device="cuda")
+
+
+@pytest.mark.parametrize("opt", ["rmsprop", "adam", "adadelta", "sgd"])
+def test_trainer_resume_continues_the_uninterrupted_run(tmp_path, opt):
+    """Save after 3 native steps (model.state_dict() + Trainer.optimizer_state_dict(), the checkpoint train.py:270-278 writes),
+    load both into a fresh model/Trainer, run 3 more: parameters equal those of 6 uninterrupted steps.  The optimizer blob
+    is torch.optim's own layout — the matching torch optimizer loads it and holds the same tensors.
+    Tolerance 2e-5 absolute on parameters of size ~0.03: split-K weight gradients are fp32 TMA reduce-adds whose order is
+    not fixed, so two runs of the same step differ in the last bits."""
+    from inferbiomechanics_b200.data.window_store import WindowStore
+    from inferbiomechanics_b200.models.FeedForwardRegressionBaseline import FeedForwardBaseline
+    from inferbiomechanics_b200.trainer import Trainer
+
+    def fresh():
+        torch.manual_seed(0)
+        return FeedForwardBaseline(23, 2, 50, "all_frames", "sigmoid", 5, 10, hidden_dims=[64, 64]).cuda()
+
+    store = WindowStore.synthetic(1024, 50, 5, 147, "all_frames", seed=3, device="cuda")
+    idx = store.shard(0, 1)
+    batches = [idx[i * 32:(i + 1) * 32] for i in range(6)]
+    a = fresh()
+    ta = Trainer(a, opt_type=opt, lr=1e-3)
+    for b in batches:
+        ta.train_step(store, b)
+    m1 = fresh()
+    t1 = Trainer(m1, opt_type=opt, lr=1e-3)
+    for b in batches[:3]:
+        t1.train_step(store, b)
+    path = str(tmp_path / "epoch_0_batch_2.pt")
+    torch.save({"epoch": 0, "model_state_dict": m1.state_dict(), "optimizer_state_dict": t1.optimizer_state_dict()}, path)
+    ck = torch.load(path, map_location="cpu")
+    m2 = fresh()
+    m2.load_state_dict(ck["model_state_dict"])
+    t2 = Trainer(m2, opt_type=opt, lr=1e-3)
+    t2.load_optimizer_state_dict(ck["optimizer_state_dict"])
+    assert t2.step_count == 3
+    t2.arena.sync_shadow(force=True)
+    for b in batches[3:]:
+        t2.train_step(store, b)
+    for (n, p), q in zip(a.named_parameters(), m2.parameters()):
+        assert (p - q).abs().max().item() <= 2e-5, n
+    # the reference side: torch.optim's own class accepts the blob (abstract_command.py:113-114)
+    cls = getattr(torch.optim, Trainer._OPT_CLASS[opt])
+    topt = cls(m2.parameters(), lr=1e-3)
+    topt.load_state_dict({k: v for k, v in ck["optimizer_state_dict"].items() if k != "ibm_b200"})
+    n0, _ = Trainer._OPT_STATE[opt]
+    if n0 is not None:
+        st = topt.state[next(iter(m2.parameters()))]
+        o, k = t1.arena.offsets[t1.arena.names[0]]
+        assert torch.equal(st[n0].reshape(-1).cpu(), t1.state0[o:o + k].cpu()) and int(st["step"]) == 3
+    with pytest.raises(ValueError):
+        Trainer(fresh(), opt_type="adagrad", lr=1e-3).load_optimizer_state_dict(ck["optimizer_state_dict"])
