@@ -22,20 +22,26 @@ from .engine import _Buffers, _r8
 from .params import ParamArena
 
 BF16, F32 = torch.bfloat16, torch.float32
-PAD, KT = 3, 7
+FC_DROPOUT_SEED = 0x6c696e6b
 
 
 class GroundlinkEngine:
     CNN_DROPOUT_SEED = 0x636e6e64
 
-    def __init__(self, arena: ParamArena, c_in: int, features: List[int], fc_dropout: float, cnn_dropout: float = 0.0):
+    def __init__(self, arena: ParamArena, c_in: int, features: List[int], fc_dropout: float, cnn_dropout: float = 0.0,
+                 cnn_kernel: int = 7, fc_depth: int = 3):
+        """``cnn_kernel`` (odd) and ``fc_depth`` are the reference constructor's arguments (Groundlink.py:20): kernel taps of every
+        Conv1d (padding = cnn_kernel // 2, replicate) and the number of Linear layers of the per-frame MLP (fc_depth - 1 hidden
+        256 -> 256 + ELU layers, then 256 -> 30 without bias)."""
+        assert cnn_kernel % 2 == 1 and cnn_kernel >= 1 and fc_depth >= 1
+        self.kt, self.pad, self.fc_depth = cnn_kernel, cnn_kernel // 2, fc_depth
         self.arena = arena
         self.ch = [c_in] + list(features)                 # [177, 128, 128, 256, 256]
         self.ld = [_r8(c) for c in self.ch]               # row pitch of each layer's activation buffer
         self.cin_pad = [ops.round_up(self.ld[i], 64) for i in range(4)]       # per-tap K padded to whole 64-wide k blocks
         self.cout_pad = [ops.round_up(self.ch[i + 1], 64) for i in range(4)]
         self.conv_pos = (1, 4, 7, 10)                     # nn.Sequential positions (SURVEY §9.3)
-        self.fc_pos = (2, 5, 8)
+        self.fc_pos = tuple(3 * j + 2 for j in range(fc_depth))     # [Transpose, (Dropout, Linear, ELU) x (depth-1), Dropout, Linear]
         self.fc_dropout = fc_dropout
         self.cnn_dropout = float(cnn_dropout)             # nn.Dropout before every Conv1d (Groundlink.py:41, default 0.0)
         self.buf = _Buffers(arena.device)
@@ -52,6 +58,7 @@ class GroundlinkEngine:
         dev = self.arena.device
         for i, pos in enumerate(self.conv_pos):
             cout, cin = self.ch[i + 1], self.ch[i]
+            KT = self.kt
             w = self.arena.master_of(f"cnn.{pos}.weight", (cout, cin, KT))
             fw = self._w.get(f"f{i}")
             if fw is None:
@@ -69,10 +76,11 @@ class GroundlinkEngine:
     # ---- buffers ---------------------------------------------------------------------------------------------
     def _state(self, B: int, T: int):
         st = self.buf.get((B, T))
+        PAD = self.pad
         Tp = T + 2 * PAD
         Mp = B * Tp
         if "x0" not in st:
-            slack = 8                                      # rows of zeros before/after: tap shifts (+6) and the +3 store shift
+            slack = max(8, ops.round_up(self.kt + 1, 8))   # rows of zeros before/after: tap shifts (+kt-1) and the +pad store shift
             for i in range(5):
                 full = torch.zeros(Mp + 2 * slack, self.ld[i], dtype=BF16, device=self.arena.device)
                 st[f"x{i}_full"] = full
@@ -80,8 +88,9 @@ class GroundlinkEngine:
                 gfull = torch.zeros(Mp + 2 * slack, self.ld[i], dtype=BF16, device=self.arena.device)
                 st[f"g{i}_full"] = gfull
                 st[f"g{i}"] = gfull[slack:slack + Mp]
-            for k in ("h1", "h2", "h1d", "h2d", "y4d", "dh1", "dh2", "dtmp"):
-                st[k] = torch.zeros(Mp, 256, dtype=BF16, device=self.arena.device)
+            names = ["y4d"] + [f"{k}{j}" for j in range(1, self.fc_depth) for k in ("h", "hd", "dh")]
+            for k in names:
+                st[k] = torch.zeros(Mp, self.ch[-1], dtype=BF16, device=self.arena.device)
             st["out"] = torch.zeros(Mp, 32, dtype=F32, device=self.arena.device)
             st["dout"] = torch.zeros(Mp, 32, dtype=BF16, device=self.arena.device)
             st["slack"] = slack
@@ -91,15 +100,15 @@ class GroundlinkEngine:
         """(buffer, frame_stride, win_extra, col0) for the packers: frame t of window b → row b*Tp + 3 + t."""
         st, Tp, Mp = self._state(B, T)
         ld = self.ld[0]
-        return st["x0"], ld, 2 * PAD * ld, PAD * ld
+        return st["x0"], ld, 2 * self.pad * ld, self.pad * ld
 
     def out_view(self, B: int, T: int) -> torch.Tensor:
         st, Tp, Mp = self._state(B, T)
-        return st["out"].view(B, Tp, 32)[:, PAD:PAD + T, :]
+        return st["out"].view(B, Tp, 32)[:, self.pad:self.pad + T, :]
 
     def dout_view(self, B: int, T: int) -> torch.Tensor:
         st, Tp, Mp = self._state(B, T)
-        return st["dout"].view(B, Tp, 32)[:, PAD:PAD + T, :]
+        return st["dout"].view(B, Tp, 32)[:, self.pad:self.pad + T, :]
 
     # ---- forward ---------------------------------------------------------------------------------------------
     def forward(self, B: int, T: int, train: bool) -> torch.Tensor:
@@ -107,6 +116,7 @@ class GroundlinkEngine:
         A = self.arena
         W = self._weights()
         st, Tp, Mp = self._state(B, T)
+        PAD, KT, depth, C = self.pad, self.kt, self.fc_depth, self.ch[-1]
         self.step += 1
         cdrop = train and self.cnn_dropout > 0.0
         st["cnn_dropped"] = cdrop
@@ -129,22 +139,17 @@ class GroundlinkEngine:
                      act="elu", taps=KT)
             ops.replicate_pad_rows(st[f"x{i + 1}"], B, T, PAD, self.ld[i + 1])
         drop = train and self.fc_dropout > 0.0
-        y4 = st["x4"]
-        a = y4
-        if drop:
-            ops.dropout(y4, st["y4d"], self.fc_dropout, 0x6c696e6b, 3 * self.step)
-            a = st["y4d"]
-        ops.gemm(a, A.shadow_of("fc.2.weight", (256, 256)), st["h1"], Mp, 256, 256, bias=A.master_of("fc.2.bias"), act="elu")
-        a = st["h1"]
-        if drop:
-            ops.dropout(st["h1"], st["h1d"], self.fc_dropout, 0x6c696e6b, 3 * self.step + 1)
-            a = st["h1d"]
-        ops.gemm(a, A.shadow_of("fc.5.weight", (256, 256)), st["h2"], Mp, 256, 256, bias=A.master_of("fc.5.bias"), act="elu")
-        a = st["h2"]
-        if drop:
-            ops.dropout(st["h2"], st["h2d"], self.fc_dropout, 0x6c696e6b, 3 * self.step + 2)
-            a = st["h2d"]
-        ops.gemm(a, A.shadow_of("fc.8.weight", (30, 256)), st["out"], Mp, 30, 256)
+        a = st["x4"]
+        for j, pos in enumerate(self.fc_pos):                # Linear j reads the (dropped) output of layer j-1 / the CNN
+            if drop:
+                ad = st["y4d"] if j == 0 else st[f"hd{j}"]
+                ops.dropout(a, ad, self.fc_dropout, FC_DROPOUT_SEED, depth * self.step + j)
+                a = ad
+            if j < depth - 1:
+                ops.gemm(a, A.shadow_of(f"fc.{pos}.weight", (C, C)), st[f"h{j + 1}"], Mp, C, C, bias=A.master_of(f"fc.{pos}.bias"), act="elu")
+                a = st[f"h{j + 1}"]
+            else:
+                ops.gemm(a, A.shadow_of(f"fc.{pos}.weight", (30, C)), st["out"], Mp, 30, C)
         st["dropped"] = drop
         return self.out_view(B, T)
 
@@ -157,29 +162,22 @@ class GroundlinkEngine:
         st, Tp, Mp = self._state(B, T)
         drop = st.get("dropped", False)
         cdrop = st.get("cnn_dropped", False)
-        dout = st["dout"]
+        PAD, KT, depth, C = self.pad, self.kt, self.fc_depth, self.ch[-1]
         p, s = self.fc_dropout, self.step
-        # fc.8 (no bias)
-        x3 = st["h2d"] if drop else st["h2"]
-        ops.gemm(dout, x3, g("fc.8.weight", (30, 256)), 30, 256, Mp, a_mn=True, b_mn=True, accumulate=True)
-        ops.gemm(dout, A.shadow_of("fc.8.weight", (30, 256)), st["dh2"], Mp, 256, 30, b_mn=True, act="elu", aux=st["h2"], aux_mode=2)
-        if drop:
-            ops.dropout(st["dh2"], st["dh2"], p, 0x6c696e6b, 3 * s + 2)
-        # fc.5
-        x2 = st["h1d"] if drop else st["h1"]
-        ops.gemm(st["dh2"], x2, g("fc.5.weight", (256, 256)), 256, 256, Mp, a_mn=True, b_mn=True, accumulate=True)
-        ops.colsum(st["dh2"], Mp, 256, g("fc.5.bias"))
-        ops.gemm(st["dh2"], A.shadow_of("fc.5.weight", (256, 256)), st["dh1"], Mp, 256, 256, b_mn=True, act="elu", aux=st["h1"], aux_mode=2)
-        if drop:
-            ops.dropout(st["dh1"], st["dh1"], p, 0x6c696e6b, 3 * s + 1)
-        # fc.2
-        x1 = st["y4d"] if drop else st["x4"]
-        ops.gemm(st["dh1"], x1, g("fc.2.weight", (256, 256)), 256, 256, Mp, a_mn=True, b_mn=True, accumulate=True)
-        ops.colsum(st["dh1"], Mp, 256, g("fc.2.bias"))
-        # gradient w.r.t. the last conv layer's (padded) output, through its ELU
-        ops.gemm(st["dh1"], A.shadow_of("fc.2.weight", (256, 256)), st["g4"], Mp, 256, 256, b_mn=True, act="elu", aux=st["x4"], aux_mode=2)
-        if drop:
-            ops.dropout(st["g4"], st["g4"], p, 0x6c696e6b, 3 * s)
+        dy, n_out = st["dout"], 30
+        for j in range(depth - 1, -1, -1):
+            pos = self.fc_pos[j]
+            pre = st["x4"] if j == 0 else st[f"h{j}"]                    # ELU output feeding Linear j (before its dropout)
+            x_in = (st["y4d"] if j == 0 else st[f"hd{j}"]) if drop else pre
+            ops.gemm(dy, x_in, g(f"fc.{pos}.weight", (n_out, C)), n_out, C, Mp, a_mn=True, b_mn=True, accumulate=True)
+            if j < depth - 1:                                            # the last Linear has no bias (Groundlink.py:62)
+                ops.colsum(dy, Mp, C, g(f"fc.{pos}.bias"))
+            # gradient w.r.t. the ELU output below, through its derivative; for j == 0 that is the last conv layer's padded output
+            dx = st["g4"] if j == 0 else st[f"dh{j}"]
+            ops.gemm(dy, A.shadow_of(f"fc.{pos}.weight", (n_out, C)), dx, Mp, C, n_out, b_mn=True, act="elu", aux=pre, aux_mode=2)
+            if drop:
+                ops.dropout(dx, dx, p, FC_DROPOUT_SEED, depth * s + j)
+            dy, n_out = dx, C
         if self.bucket_hook is not None:
             self.bucket_hook(4)
         slack = st["slack"]

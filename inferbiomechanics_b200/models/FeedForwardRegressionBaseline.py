@@ -89,8 +89,9 @@ class FeedForwardBaseline(EngineModule):
         self.input_size = self.frame_width * self.num_frames            # FeedForward…py:52
         self.num_output_frames = self.num_frames if output_data_format == 'all_frames' else 1
         self.output_size = num_contact_bodies * (3 * 3 + 6) * self.num_output_frames   # FeedForward…py:62
-        if num_contact_bodies != 2:
-            raise NotImplementedError("the fused loss/output layout assumes 2 contact bodies (30 channels), as the dataset has")
+        # num_contact_bodies != 2 follows the reference literally: the last Linear has num_contact_bodies * 15 * F outputs and the
+        # split below still takes the first 30 * F of them (FeedForward...py:116-121), so 3+ bodies carry unused outputs and
+        # 1 body fails in the reshape exactly as the reference does
 
         net = []
         dims = [self.input_size] + list(hidden_dims) + [self.output_size]

@@ -69,8 +69,13 @@ class Groundlink(EngineModule):
         self.num_joints = num_joints
         self.root_history_len = root_history_len
         self.output_data_format = output_data_format
-        if cnn_kernel != 7 or fc_depth != 3:
-            raise NotImplementedError("the B200 engine implements the reference defaults cnn_kernel=7, fc_depth=3")
+        if cnn_kernel % 2 == 0:
+            # Conv1d(k, padding=k // 2) with an even k emits T + 1 frames per layer: the reference's own output slicing and
+            # loss then fail on the frame count, so there is no behaviour to reproduce
+            raise NotImplementedError("even cnn_kernel: Conv1d(padding=k//2) changes the number of frames (unusable in the reference too)")
+        if fc_depth < 1:
+            raise ValueError("fc_depth must be >= 1")
+        self.cnn_kernel, self.fc_depth = cnn_kernel, fc_depth
         self.cnn_dropout, self.fc_dropout = cnn_dropout, fc_dropout
         input_size = (num_dofs * 3 + 12 + num_joints * 3 + root_history_len * 6)
         self.input_size = input_size
@@ -104,7 +109,8 @@ class Groundlink(EngineModule):
         return net
 
     def _build_engine(self, arena):
-        return GroundlinkEngine(arena, self.input_size, self.cnn_features[1:], self.fc_dropout, self.cnn_dropout)
+        return GroundlinkEngine(arena, self.input_size, self.cnn_features[1:], self.fc_dropout, self.cnn_dropout,
+                                cnn_kernel=self.cnn_kernel, fc_depth=self.fc_depth)
 
     def forward(self, input: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         # 1. same shape assertions as the reference (Groundlink.py:107-118)

@@ -266,6 +266,51 @@ def gen_transformer_bwd(ref):
     np.savez_compressed(os.path.join(OUT, "transformer_bwd.npz"), **d)
 
 
+def gen_ctor_variants(ref):
+    """Non-default constructor arguments the reference accepts: FeedForwardBaseline(num_contact_bodies=3) (the last Linear
+    grows to 45 * F outputs, the output split still takes the first 30 * F — FeedForward...py:62,116-121) and
+    Groundlink(cnn_kernel, fc_depth) (Groundlink.py:20,41,51-62)."""
+    d = {}
+    D, T, s, B = 23, 50, 5, 5
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ref.FeedForwardBaseline(D, 3, T, "all_frames", "tanh", s, 10, hidden_dims=[48, 32])
+    seed = 1600
+    m.load_state_dict(seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed))
+    m.eval()
+    F = T // s
+    inputs = seeded_inputs(B, F, D, s * 3, 2600)
+    _, labels = seeded_out_labels(B, F, 3600)
+    out = m({k: v.clone() for k, v in inputs.items()})
+    ev = ref.RegressionLossEvaluator(dataset=None, split="train")
+    loss = ev(None, dict(out), {k: v.clone() for k, v in labels.items()}, [], [], ns_args(*SELECTIONS["all"]))
+    loss.backward()
+    for k, v in out.items():
+        d[f"ff_nb3/out/{k}"] = v.detach().numpy()
+    d["ff_nb3/loss"] = loss.detach().numpy()
+    grads_summary(m, d, "ff_nb3")
+    d["ff_nb3/meta"] = np.array([D, T, s, B, seed, 2600, 3600])
+    J, H = 12, 10
+    for ci, (name, k, depth, fmt, B, T) in enumerate([("gl_k5_d2", 5, 2, "all_frames", 3, 30), ("gl_k3_d4", 3, 4, "last_frame", 2, 24),
+                                                      ("gl_k9_d1", 9, 1, "all_frames", 2, 20)]):
+        m = ref.Groundlink(D, J, H, fmt, cnn_kernel=k, fc_depth=depth)
+        seed = 1610 + ci
+        m.load_state_dict(seeded_state_dict({kk: tuple(v.shape) for kk, v in m.state_dict().items()}, seed))
+        m.eval()
+        inputs = seeded_inputs(B, T, D, H * 3, 2610 + ci)
+        _, labels = seeded_out_labels(B, T if fmt == "all_frames" else 1, 3610 + ci)
+        out = m({kk: v.clone() for kk, v in inputs.items()})
+        ev = ref.RegressionLossEvaluator(dataset=None, split="train")
+        loss = ev(None, dict(out), {kk: v.clone() for kk, v in labels.items()}, [], [], ns_args(*SELECTIONS["all"]))
+        loss.backward()
+        for kk, v in out.items():
+            d[f"{name}/out/{kk}"] = v.detach().numpy()
+        d[f"{name}/loss"] = loss.detach().numpy()
+        grads_summary(m, d, name)
+        d[f"{name}/meta"] = np.array([D, J, H, B, T, seed, 2610 + ci, 3610 + ci, k, depth])
+    np.savez_compressed(os.path.join(OUT, "ctor_variants.npz"), **d)
+
+
 def gen_denoiser_layers(ref):
     """Reference TransformerLayer at the denoiser's configuration family (fp32, heads×64)."""
     d = {}
@@ -382,6 +427,9 @@ def main():
     if "--only-ff" in __import__("sys").argv:
         gen_ff(ref)
         return
+    if "--only-ctor-variants" in __import__("sys").argv:
+        gen_ctor_variants(ref)
+        return
     if "--only-transformer-bwd" in __import__("sys").argv:
         gen_transformer_bwd(ref)
         return
@@ -394,6 +442,7 @@ def main():
     gen_groundlink(ref)
     gen_transformer(ref)
     gen_transformer_bwd(ref)
+    gen_ctor_variants(ref)
     gen_denoiser_layers(ref)
     gen_windows(ref)
     for f in sorted(os.listdir(OUT)):

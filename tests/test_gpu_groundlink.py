@@ -180,3 +180,35 @@ def test_groundlink_cnn_dropout_matches_masked_emulation():
     m.train()
     t2 = m(inputs)[ol.FORCE]
     assert not torch.equal(t2, out[ol.FORCE]) and not torch.equal(e1, t2)
+
+
+@pytest.mark.parametrize("name,fmt", [("gl_k5_d2", "all_frames"), ("gl_k3_d4", "last_frame"), ("gl_k9_d1", "all_frames")])
+def test_groundlink_constructor_variants_match_reference_golden(golden, name, fmt):
+    """Groundlink(cnn_kernel, fc_depth) other than the defaults (Groundlink.py:20,41,51-62), golden from the imported reference
+    (tests/golden/ctor_variants.npz): outputs, loss and every parameter gradient at the bars of the default model."""
+    from inferbiomechanics_b200.loss.RegressionLossEvaluator import RegressionLossEvaluator
+    from inferbiomechanics_b200.models.Groundlink import Groundlink
+    g = golden("ctor_variants.npz")
+    D, J, H, B, T, seed, iseed, lseed, k, depth = (int(v) for v in g[f"{name}/meta"])
+    m = Groundlink(D, J, H, fmt, cnn_kernel=k, fc_depth=depth)
+    m.load_state_dict(seeded_state_dict({kk: tuple(v.shape) for kk, v in m.state_dict().items()}, seed))
+    m = m.cuda().eval()
+    inputs = seeded_inputs(B, T, D, H * 3, iseed)
+    _, labels = seeded_out_labels(B, T if fmt == "all_frames" else 1, lseed)
+    out = m(inputs)
+    for q in Q:
+        ref = g[f"{name}/out/{q}"]
+        assert tuple(out[q].shape) == ref.shape
+        assert np.abs(out[q].detach().cpu().numpy() - ref).max() <= 3e-2 * np.abs(ref).max(), q
+    ev = RegressionLossEvaluator(None, "train", device="cuda")
+    loss = ev(inputs, out, {kk: v.clone() for kk, v in labels.items()}, [], [], ALL)
+    np.testing.assert_allclose(loss.item(), float(g[f"{name}/loss"]), rtol=2e-2)
+    loss.backward()
+    for n, p in m.named_parameters():
+        got = strided_sample(p.grad).double().cpu()
+        ref = torch.from_numpy(g[f"{name}/grad_sample/{n}"]).double()
+        rel = (got - ref).norm().item() / (ref.norm().item() + 1e-12)
+        cos = torch.dot(got, ref).item() / (got.norm().item() * ref.norm().item() + 1e-30)
+        assert rel <= 0.12 and cos >= 0.985, f"{n}: rel L2 {rel:.4f}, cosine {cos:.4f}"
+    with pytest.raises(NotImplementedError):
+        Groundlink(D, J, H, fmt, cnn_kernel=6)

@@ -280,6 +280,34 @@ def test_feedforward_trainer_tracks_reference_loop(opt):
             l2close(delta, ref_delta, 0.08, n)
 
 
+def test_feedforward_three_contact_bodies_follows_reference(golden):
+    """num_contact_bodies = 3: 45 * F outputs of which the first 30 * F are split (FeedForward...py:62,116-121); golden from
+    the imported reference.  The unused output rows of the last Linear get exactly zero gradient."""
+    from inferbiomechanics_b200.loss.RegressionLossEvaluator import RegressionLossEvaluator
+    from inferbiomechanics_b200.models.FeedForwardRegressionBaseline import FeedForwardBaseline
+    g = golden("ctor_variants.npz")
+    D, T, s, B, seed, iseed, lseed = (int(v) for v in g["ff_nb3/meta"])
+    m = FeedForwardBaseline(D, 3, T, "all_frames", "tanh", s, 10, hidden_dims=[48, 32])
+    m.load_state_dict(seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed))
+    m = m.to("cuda").eval()
+    F = T // s
+    assert m.net[-1].out_features == 45 * F
+    inputs = seeded_inputs(B, F, D, s * 3, iseed)
+    _, labels = seeded_out_labels(B, F, lseed)
+    out = m(inputs)
+    for k in Q:
+        close(out[k].detach(), g[f"ff_nb3/out/{k}"], 3e-2, k)
+    ev = RegressionLossEvaluator(dataset=None, split="train", device="cuda")
+    loss = ev(inputs, out, {k: v.clone() for k, v in labels.items()}, [], [], ALL)
+    np.testing.assert_allclose(loss.item(), float(g["ff_nb3/loss"]), rtol=2e-2)
+    loss.backward()
+    for n, p in m.named_parameters():
+        close(strided_sample(p.grad), g[f"ff_nb3/grad_sample/{n}"], 6e-2, n)
+    assert float(m.net[-1].weight.grad[30 * F:].abs().max()) == 0.0
+    with pytest.raises(RuntimeError):                       # one body: 15 * F outputs cannot be split into 30 * F (reference: same)
+        FeedForwardBaseline(D, 1, T, "all_frames", "tanh", s, 10, hidden_dims=[32]).to("cuda")(inputs)
+
+
 # ---------------------------------------------------------------------------------------------------
 # encoder layer == reference TransformerLayer (golden from the imported reference)
 # ---------------------------------------------------------------------------------------------------
