@@ -61,6 +61,30 @@ class AbstractCommand:
             raise ValueError(f"model type {model_type!r} is not available on the B200 path (analytical needs nimblephysics)")
         return model
 
+    @staticmethod
+    def latest_checkpoint_path(checkpoint_dir: str):
+        if not os.path.exists(checkpoint_dir):
+            return None
+        checkpoints = [f for f in os.listdir(checkpoint_dir) if f.endswith(".pt")]
+        if not checkpoints:
+            return None
+        checkpoints.sort(key=lambda x: (int(x.split('_')[1]), int(x.split('_')[3].split('.')[0])))
+        return os.path.join(checkpoint_dir, checkpoints[-1])
+
+    @classmethod
+    def feedforward_layout(cls, checkpoint_dir: str):
+        """(batchnorm, dropout) of the FeedForwardBaseline that wrote the latest checkpoint, read off its ``nn.Sequential``
+        positions (FeedForward…py:68-75: per layer ``[Dropout][BatchNorm1d] Linear act``): BatchNorm leaves ``running_mean``
+        buffers, and the first Linear sits at position ``int(dropout) + int(batchnorm)``."""
+        path = cls.latest_checkpoint_path(checkpoint_dir)
+        if path is None:
+            return False, False
+        sd = torch.load(path, map_location="cpu")['model_state_dict']
+        keys = [k[len('module.'):] if k.startswith('module.') else k for k in sd]
+        bn = any(k.endswith('running_mean') for k in keys)
+        first_linear = min(int(k.split('.')[1]) for k, v in zip(keys, sd.values()) if k.endswith('.weight') and v.dim() == 2)
+        return bn, first_linear - int(bn) == 1
+
     def load_latest_checkpoint(self, model, optimizer=None, checkpoint_dir="../checkpoints"):
         if not os.path.exists(checkpoint_dir):
             print("Checkpoint directory does not exist!")

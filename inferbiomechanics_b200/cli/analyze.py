@@ -46,6 +46,8 @@ class AnalyzeCommand(AbstractCommand):
                         help='The number of timesteps of context to show when constructing the inputs.')
         sp.add_argument('--hidden-dims', type=int, nargs='+', default=[512, 512], help='Hidden dims across different layers.')
         sp.add_argument('--activation', type=str, default='sigmoid', help='Which activation func?')
+        sp.add_argument('--batchnorm', action='store_true', help='The checkpoint was trained with --batchnorm (else read off its keys).')
+        sp.add_argument('--dropout', action='store_true', help='The checkpoint was trained with --dropout (else read off its keys).')
         sp.add_argument('--device', type=str, default='cuda', help='Accepted for compatibility; this path runs on the GPU only.')
         sp.add_argument('--short', type=bool, default=False, help='Use very short datasets to test without loading a bunch of data.')
         sp.add_argument('--data-loading-workers', type=int, default=3, help='Accepted for compatibility.')
@@ -67,8 +69,12 @@ class AnalyzeCommand(AbstractCommand):
         rank, world, local = parallel.init_from_env("nccl")
         torch.cuda.set_device(local)
         device = torch.device("cuda", local)
+        # --batchnorm / --dropout shift the nn.Sequential positions of the checkpoint's keys (the reference's analyze has no
+        # such flags and cannot load those checkpoints): taken from the flags, else read off the latest checkpoint's keys
+        batchnorm, dropout = self.feedforward_layout(checkpoint_dir) if model_type == 'feedforward' else (False, False)
         model = self.get_model(_data.NUM_DOFS, 2, model_type, history_len=args.history_len, hidden_dims=args.hidden_dims,
-                               activation=args.activation, stride=args.stride, batchnorm=False, dropout=False, dropout_prob=0.0,
+                               activation=args.activation, stride=args.stride, batchnorm=args.batchnorm or batchnorm,
+                               dropout=args.dropout or dropout, dropout_prob=0.0,
                                root_history_len=root_history_len, output_data_format=args.output_data_format,
                                device=str(device)).to(device)
         self.load_latest_checkpoint(model, checkpoint_dir=checkpoint_dir)
@@ -98,6 +104,8 @@ class AnalyzeCommand(AbstractCommand):
                         # condition = the packed kinematics in the engine's concat buffer; x_T ~ Philox; CUDA-graph replays
                         store.pack_rows(idx, model.engine().xc(idx.numel(), False), col0=30)
                         x0 = diffusion.sample(model, idx.numel(), steps=args.sampling_steps, seed=1234 + rank)
+                        if store.Fo == 1:                     # --output-data-format last_frame: labels hold the last frame only
+                            x0 = x0[:, -1:]
                         cuts = [(0, 6), (6, 12), (12, 18), (18, 30)]
                         inputs = {}
                         outputs = {k: x0[:, :, a:b] for k, (a, b) in zip(LOSS_QUANTITIES, cuts)}

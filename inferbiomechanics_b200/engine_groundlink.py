@@ -48,6 +48,7 @@ class GroundlinkEngine:
         self._wver = None
         self._w: Dict[str, torch.Tensor] = {}
         self.step = 0
+        self.cnn_seed, self.fc_seed = self.CNN_DROPOUT_SEED, FC_DROPOUT_SEED     # Trainer.seed_rng folds seed and rank in
         self.bucket_hook = None
 
     # ---- weights in GEMM layouts (refreshed when the fp32 masters change) ---------------------------------
@@ -131,7 +132,7 @@ class GroundlinkEngine:
                 if xd_full is None:
                     xd_full = st[f"xd{i}_full"] = torch.zeros_like(st[f"x{i}_full"])
                     st[f"xd{i}"] = xd_full[slack:slack + Mp]
-                ops.dropout(st[f"x{i}_full"], xd_full, self.cnn_dropout, self.CNN_DROPOUT_SEED, 4 * self.step + i)
+                ops.dropout(st[f"x{i}_full"], xd_full, self.cnn_dropout, self.cnn_seed, 4 * self.step + i)
                 ops.replicate_pad_rows(st[f"xd{i}"], B, T, PAD, self.ld[i])
                 x = st[f"xd{i}"]
             y_shift = y_full[slack + PAD: slack + PAD + Mp]             # the store lands 3 rows down: frame slots of layer i+1
@@ -143,7 +144,7 @@ class GroundlinkEngine:
         for j, pos in enumerate(self.fc_pos):                # Linear j reads the (dropped) output of layer j-1 / the CNN
             if drop:
                 ad = st["y4d"] if j == 0 else st[f"hd{j}"]
-                ops.dropout(a, ad, self.fc_dropout, FC_DROPOUT_SEED, depth * self.step + j)
+                ops.dropout(a, ad, self.fc_dropout, self.fc_seed, depth * self.step + j)
                 a = ad
             if j < depth - 1:
                 ops.gemm(a, A.shadow_of(f"fc.{pos}.weight", (C, C)), st[f"h{j + 1}"], Mp, C, C, bias=A.master_of(f"fc.{pos}.bias"), act="elu")
@@ -176,7 +177,7 @@ class GroundlinkEngine:
             dx = st["g4"] if j == 0 else st[f"dh{j}"]
             ops.gemm(dy, A.shadow_of(f"fc.{pos}.weight", (n_out, C)), dx, Mp, C, n_out, b_mn=True, act="elu", aux=pre, aux_mode=2)
             if drop:
-                ops.dropout(dx, dx, p, FC_DROPOUT_SEED, depth * s + j)
+                ops.dropout(dx, dx, p, self.fc_seed, depth * s + j)
             dy, n_out = dx, C
         if self.bucket_hook is not None:
             self.bucket_hook(4)
@@ -190,7 +191,7 @@ class GroundlinkEngine:
                 # adjoint of the dropout in front of conv i+1: the same Philox mask over the identically shaped buffer (the ELU
                 # derivative fused into the producing dgrad commutes with it, and with the fold because pads replicate x)
                 Gfull = st[f"g{i + 1}_full"]
-                ops.dropout(Gfull, Gfull, self.cnn_dropout, self.CNN_DROPOUT_SEED, 4 * s + i + 1)
+                ops.dropout(Gfull, Gfull, self.cnn_dropout, self.cnn_seed, 4 * s + i + 1)
             ops.colsum(G, Mp, cout, g(f"cnn.{pos}.bias"))
             # wgrad: dW_j[co, ci] = sum_r G[r + 3, co] * Xp[r + j, ci]  (7 split-K MN-major GEMMs into GEMM-layout scratch)
             wg = self.buf.tensor(st, f"wg{i}", (cout, KT * self.cin_pad[i]), F32)

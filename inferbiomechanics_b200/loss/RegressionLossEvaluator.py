@@ -117,8 +117,13 @@ class RegressionLossEvaluator:
         self._results: List[torch.Tensor] = []
         self.losses: List[torch.Tensor] = []
         self.tau_reported_metrics: List[float] = []
+        # the reference never resets wrench_moment_reported_metrics (…py:412-426): the history is kept, but as host floats —
+        # a reset folds the device results into the float list instead of pinning one device tensor per step forever
         if not keep_wrench_moment:
-            self._wm_results: List[torch.Tensor] = []
+            self._wm_host: List[float] = []
+        elif getattr(self, "_wm_results", None):
+            self._wm_host += [float(v) for v in torch.stack(self._wm_results)[:, 34].cpu().numpy()]
+        self._wm_results: List[torch.Tensor] = []
 
     # ---- the reference's four static helpers (…py:73-158): same maths, same ValueErrors, same general
     #      contract (any C / C % 3 / C % vec_size), each one launch of csrc/loss_helpers.cu -------------------
@@ -218,8 +223,8 @@ class RegressionLossEvaluator:
     @property
     def wrench_moment_reported_metrics(self):
         if not self._wm_results:
-            return []
-        return [float(v) for v in torch.stack(self._wm_results)[:, 34].cpu().numpy()]
+            return list(self._wm_host)
+        return self._wm_host + [float(v) for v in torch.stack(self._wm_results)[:, 34].cpu().numpy()]
 
     # ---- logging (…py:324-426), text and keys as in the reference, including its two label quirks ----
     def log_to_wandb(self, args, force_loss, cop_loss, moment_loss, wrench_loss, loss, force_reported_metric,

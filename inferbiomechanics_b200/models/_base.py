@@ -35,6 +35,12 @@ class EngineModule(nn.Module):
         if self._arena is None or not self._arena.intact():
             self._arena = ParamArena(list(self.named_parameters()), dev)
             self._engine = self._build_engine(self._arena)
+            # module loop (the reference's autograd + DDP idiom): every data-parallel rank draws its own dropout masks, as
+            # per-process torch RNGs do; the native Trainer re-seeds with its own seed and step count (Trainer.seed_rng)
+            from ..parallel import world
+            for attr in ("dropout_seed", "cnn_seed", "fc_seed"):
+                if hasattr(self._engine, attr):
+                    setattr(self._engine, attr, getattr(self._engine, attr) + world()[0])
         else:
             self._arena.sync_shadow()
         return self._engine

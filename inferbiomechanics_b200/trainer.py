@@ -80,11 +80,25 @@ class Trainer:
         # DDP constructor semantics: everyone starts from rank 0's parameters (train.py:175)
         self.bucketer.broadcast_(self.arena.master)
         self.arena.sync_shadow(force=True)
+        self.seed_rng()
         self._lab: Dict[int, torch.Tensor] = {}
         self._gen = torch.Generator(device=dev).manual_seed(seed + 7919 * self.rank)
         # CUDA-graph replay of the (launch-bound) FeedForward step: key -> [eager steps seen, graph, static idx, static result]
         self._graphs: Dict[tuple, list] = {}
         self.use_graphs = os.environ.get("IBM_TRAIN_GRAPHS", "1") != "0"
+
+    def seed_rng(self) -> None:
+        """Dropout masks: Philox keyed by (engine constant ^ trainer seed) + rank, offset by the GLOBAL step count — every
+        data-parallel rank draws its own mask (the reference's per-process torch RNG does), and a resumed run continues the
+        sequence instead of replaying the masks of step 1."""
+        eng, mix = self.eng, (self.seed * 0x9E3779B1) & 0x7FFFFFFF
+        for attr in ("dropout_seed", "cnn_seed", "fc_seed"):
+            if hasattr(eng, attr):
+                base = {"dropout_seed": getattr(eng, "DROPOUT_SEED", 0), "cnn_seed": getattr(eng, "CNN_DROPOUT_SEED", 0),
+                        "fc_seed": 0x6c696e6b}[attr]
+                setattr(eng, attr, (base ^ mix) + self.rank)
+        if hasattr(eng, "step"):
+            eng.step = self.step_count
 
     def _group_boundaries(self) -> List[int]:
         offs = self.arena.offsets
@@ -212,6 +226,7 @@ class Trainer:
                 if dst is not None and src is not None:
                     dst.copy_(src)
             self.step_count = int(sd.get("step", 0))
+            self.seed_rng()
             return
         tag = sd.get("ibm_b200")
         if tag is not None and tag["opt_type"] != self.opt_type:
@@ -239,6 +254,7 @@ class Trainer:
         if len(steps) > 1:
             raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): the fused optimizer keeps one")
         self.step_count = steps.pop() if steps else int(tag["step"]) if tag else 0
+        self.seed_rng()
         self._graphs.clear()
 
     # ---- evaluation (no_grad forward + loss), used by analyze / dev-eval ------------------------------

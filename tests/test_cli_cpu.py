@@ -78,3 +78,39 @@ def test_feedforward_state_dict_positions_with_batchnorm_and_dropout():
     assert sorted(plain) == ["net.0.bias", "net.0.weight", "net.2.bias", "net.2.weight", "net.4.bias", "net.4.weight"]
     only_bn = FeedForwardBaseline(23, 2, 50, "last_frame", "relu", 5, 10, hidden_dims=[64], batchnorm=True).state_dict()
     assert tuple(only_bn["net.1.weight"].shape) == (64, 1470) and tuple(only_bn["net.4.weight"].shape) == (30, 64)
+
+
+def test_analyze_reads_batchnorm_dropout_layout_off_the_checkpoint(tmp_path):
+    """analyze has no --batchnorm/--dropout in the reference and therefore cannot load such checkpoints; here the layout is
+    read off the checkpoint's nn.Sequential positions (with and without the DDP `module.` prefix)."""
+    from inferbiomechanics_b200.cli.abstract_command import AbstractCommand
+    from inferbiomechanics_b200.models.FeedForwardRegressionBaseline import FeedForwardBaseline
+    assert AbstractCommand.feedforward_layout(str(tmp_path / "none")) == (False, False)
+    for i, (bn, do) in enumerate([(False, False), (True, False), (False, True), (True, True)]):
+        d = tmp_path / f"ck{i}"
+        os.makedirs(d)
+        m = FeedForwardBaseline(23, 2, 50, "last_frame", "relu", 5, 10, hidden_dims=[16], batchnorm=bn, dropout=do, dropout_prob=0.1)
+        sd = {("module." if i % 2 else "") + k: v for k, v in m.state_dict().items()}
+        torch.save({"epoch": 0, "model_state_dict": sd, "optimizer_state_dict": {}}, d / "epoch_0_batch_7.pt")
+        assert AbstractCommand.feedforward_layout(str(d)) == (bn, do)
+
+
+def test_evaluator_wrench_moment_history_is_kept_as_host_floats():
+    """The reference never resets wrench_moment_reported_metrics (RegressionLossEvaluator.py:412-426): the history survives
+    print_report(reset=True), but as python floats rather than one retained device tensor per step."""
+    from inferbiomechanics_b200.loss.RegressionLossEvaluator import RegressionLossEvaluator
+    ev = RegressionLossEvaluator(None, "train")
+    for v in (1.0, 2.0):
+        r = torch.zeros(40)
+        r[34] = v
+        ev._results.append(r)
+        ev._wm_results.append(r)
+    assert ev.wrench_moment_reported_metrics == [1.0, 2.0]
+    ev._reset_lists(keep_wrench_moment=True)
+    assert ev._wm_results == [] and ev._results == [] and ev.wrench_moment_reported_metrics == [1.0, 2.0]
+    r = torch.zeros(40)
+    r[34] = 3.0
+    ev._wm_results.append(r)
+    assert ev.wrench_moment_reported_metrics == [1.0, 2.0, 3.0]
+    ev._reset_lists()
+    assert ev.wrench_moment_reported_metrics == []

@@ -40,6 +40,20 @@ def test_train_then_analyze_feedforward(tmp_path, capsys):
     assert "Loaded checkpoint from epoch 1" in capsys.readouterr().out
 
 
+def test_train_batchnorm_dropout_checkpoint_is_analyzable(tmp_path):
+    """--batchnorm --dropout shift the state_dict positions; analyze reads the layout off the checkpoint."""
+    ck = str(tmp_path / "ck")
+    common = ["--no-wandb", "--synthetic-windows", "1024", "--checkpoint-dir", ck, "--history-len", "50", "--stride", "5",
+              "--hidden-dims", "64", "64", "--activation", "relu"]
+    _run(["train", *common, "--model-type", "feedforward", "--epochs", "1", "--batch-size", "64", "--batchnorm", "--dropout",
+          "--dropout-prob", "0.1", "--opt-type", "adam"])
+    sd = torch.load(os.path.join(ck, "feedforward", sorted(os.listdir(os.path.join(ck, "feedforward")))[-1]), map_location="cpu")
+    assert "net.1.running_mean" in sd["model_state_dict"] and "net.2.weight" in sd["model_state_dict"]
+    assert sd["optimizer_state_dict"]["ibm_b200"]["opt_type"] == "adam" and 0 in sd["optimizer_state_dict"]["state"]
+    an = _run(["analyze", *common, "--model-type", "feedforward"])
+    assert an.last_reports["dev"]["loss"] > 0
+
+
 def test_train_groundlink_and_diffusion_smoke(tmp_path):
     ck = str(tmp_path / "ck")
     common = ["--no-wandb", "--synthetic-windows", "512", "--checkpoint-dir", ck, "--history-len", "50", "--stride", "1",
@@ -49,6 +63,9 @@ def test_train_groundlink_and_diffusion_smoke(tmp_path):
     an = _run(["analyze", "--no-wandb", "--synthetic-windows", "512", "--checkpoint-dir", ck, "--history-len", "50", "--stride", "1",
                "--model-type", "diffusion", "--batch-size", "64", "--sampling-steps", "20", "--predict-grf-components", "0", "1", "2"])
     assert an.last_reports["dev"]["loss"] > 0
+    an = _run(["analyze", "--no-wandb", "--synthetic-windows", "256", "--checkpoint-dir", ck, "--history-len", "50", "--stride", "1",
+               "--model-type", "diffusion", "--batch-size", "64", "--sampling-steps", "4", "--output-data-format", "last_frame"])
+    assert an.last_reports["dev"]["loss"] > 0               # last_frame labels vs the last sampled frame
 
 
 def test_window_store_file_roundtrip(tmp_path):
