@@ -96,21 +96,23 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference_arm(args) -> None:
-    """The reference path on the box's host cores.  The reference is pure Python and lives only in the build
-    container (/root/reference does not exist here), so this times the CPU port of its training loop
-    (oracle/train.py; torch CPU ops + torch.optim.RMSprop, all host threads) on a bounded sample per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+CPU_SAMPLE_WINDOWS = 256        # windows per CPU step: a bounded sample of the 4096-window GPU batch
+
+
+def _cpu_denoiser_loop(sample_b: int):
+    """(step callable, kind, description).  Real reference modules when the oracle/_ref snapshot (or /root/reference) is there —
+    reference TransformerLayer x 8 + reference RegressionLossEvaluator + torch.optim.RMSprop composed per the builder's denoiser
+    spec (the reference has no denoiser: src/.gitignore:10 is its only trace) — else the functional CPU port (oracle/train.py)."""
     import torch
+    from oracle import ref_cpu
+    if ref_cpu.available():
+        loop = ref_cpu.denoiser_loop(sample_b, C_IN, F, D_MODEL, HEADS, FF, LAYERS)
+        return loop, "reference", ("reference TransformerLayer x8 (TransformerBaseline.py:8-38) + reference RegressionLossEvaluator.__call__ + "
+                                   "torch.optim.RMSprop(1e-4) from the oracle/_ref snapshot, composed per the builder's denoiser spec "
+                                   "(the reference has no diffusion model)")
     from oracle import ddpm as oddpm
     from oracle import train as otrain
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sample_b = 32
-    sd = otrain.init_denoiser(C_IN, F, D_MODEL, FF, LAYERS, seed=0)
-    tr = otrain.PortTrainer(sd, lr=1e-4, opt="rmsprop")
+    tr = otrain.PortTrainer(otrain.init_denoiser(C_IN, F, D_MODEL, FF, LAYERS, seed=0), lr=1e-4, opt="rmsprop")
     sched = oddpm.make_schedule()
     g = torch.Generator().manual_seed(1234)
     cond = torch.randn(sample_b, F, C_IN, generator=g)
@@ -121,77 +123,77 @@ def run_reference_arm(args) -> None:
         t = torch.randint(0, 1000, (sample_b,), generator=g)
         eps = torch.randn(sample_b, F, 30, generator=g)
         tr.step_denoiser(sched, cond, x0, t, eps, labels, LAYERS, HEADS)
+    return step, "port", "functional CPU port of the same step (oracle/train.py): oracle/_ref snapshot absent"
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        step()
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
+
+def run_reference_arm(args) -> None:
+    """The reference's CPU implementation of the path on the box's host cores, all threads, at the requested --steps / --warmup,
+    each step a bounded 256-window sample of the 4096-window GPU batch (CPU throughput is flat in the batch size beyond that)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import ref_cpu
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_b = CPU_SAMPLE_WINDOWS
+    step, kind, what = _cpu_denoiser_loop(sample_b)
+    warm, steps = max(1, args.warmup), max(1, args.steps)
+    dt = ref_cpu.time_steps(step, warm, steps)
     v = sample_b / dt
-    sample = f"{sample_b} windows per step (of the {PER_GPU_BATCH}-window GPU batch), {steps} timed steps, torch CPU fp32, {cores} threads"
+    sample = (f"{sample_b} windows per step (of the {PER_GPU_BATCH}-window GPU batch), {warm} warm-up + {steps} timed steps, torch CPU fp32, "
+              f"{cores} threads ({ref_cpu.host()['cpu_model']}); {what}")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": config(args.gpus, sample_b),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": config(args.gpus, PER_GPU_BATCH),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU port of the reference training-loop shape (train.py:240-284) on the builder-owned denoiser; the "
-                "reference has no diffusion model, so no stock reference code exists for this workload",
     }))
 
 
 def cpu_baseline_leg() -> dict:
-    """Bounded CPU sample of the same workload (oracle port), ~10-30 s."""
+    """Bounded CPU sample of the same workload on the host cores (~10-20 s): 2 warm-up + 8 timed steps of 256 windows."""
     import torch
-    from oracle import ddpm as oddpm
-    from oracle import train as otrain
+    from oracle import ref_cpu
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b = 32
-    tr = otrain.PortTrainer(otrain.init_denoiser(C_IN, F, D_MODEL, FF, LAYERS, seed=0), lr=1e-4)
-    sched = oddpm.make_schedule()
-    g = torch.Generator().manual_seed(1234)
-    cond = torch.randn(sample_b, F, C_IN, generator=g)
-    _, labels = otrain.synthetic_batch(sample_b, F, 23, 30, 1235)
-    x0 = torch.cat([labels[k] for k in (otrain._loss.COP, otrain._loss.FORCE, otrain._loss.TORQUE, otrain._loss.WRENCH)], dim=-1)
-    times = []
-    for i in range(4):
-        t = torch.randint(0, 1000, (sample_b,), generator=g)
-        eps = torch.randn(sample_b, F, 30, generator=g)
-        t0 = time.perf_counter()
-        tr.step_denoiser(sched, cond, x0, t, eps, labels, LAYERS, HEADS)
-        times.append(time.perf_counter() - t0)
-    dt = statistics.mean(times[1:])
-    return {"value": sample_b / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sample_b} windows/step x 3 timed steps (1 warm-up) of the same denoiser training step, torch CPU fp32"}
+    step, kind, what = _cpu_denoiser_loop(CPU_SAMPLE_WINDOWS)
+    dt = ref_cpu.time_steps(step, 2, 8)
+    return {"value": CPU_SAMPLE_WINDOWS / dt, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": dt * 1e3,
+            "cpu_model": ref_cpu.host()["cpu_model"],
+            "sample": f"{CPU_SAMPLE_WINDOWS} windows/step x 8 timed steps (2 warm-up) of the same denoiser training step, torch CPU fp32; {what}"}
 
 
-def cpu_feedforward_leg() -> dict:
-    """BASELINE configs[0] on the host cores: the CPU port of the reference FeedForward training step (1470->512->512->300,
-    sigmoid, RMSprop 1e-4; train.py:240-284) at the reference's batch 32 and at a large batch, torch CPU fp32, all threads."""
+def cpu_other_configs() -> dict:
+    """The other BASELINE configs on the host cores, REAL reference modules (5 warm-up, >= 30 timed steps for
+    configs[0]); bounded so the whole block stays under ~40 s."""
     import torch
-    from oracle import train as otrain
-    from oracle.seeded import seeded_state_dict
+    from oracle import ref_cpu
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    D, T, s = 23, 50, 5
-    F = T // s
-    k0 = (3 * D + 12 + 6 * s + 36) * F
-    shapes = {"net.0.weight": (512, k0), "net.0.bias": (512,), "net.2.weight": (512, 512), "net.2.bias": (512,),
-              "net.4.weight": (30 * F, 512), "net.4.bias": (30 * F,)}
-    tr = otrain.PortTrainer(seeded_state_dict(shapes, 7), lr=1e-4, opt="rmsprop")
-    out = {"cores": cores, "kind": "port"}
-    for B, n in ((32, 200), (4096, 8)):
-        inputs, labels = otrain.synthetic_batch(B, F, D, s * 3, 11)
-        for _ in range(3):
-            tr.step_feedforward(inputs, labels, "sigmoid", F)
-        t0 = time.perf_counter()
-        for _ in range(n):
-            tr.step_feedforward(inputs, labels, "sigmoid", F)
-        dt = (time.perf_counter() - t0) / n
-        out[f"batch_{B}"] = {"windows_per_s": B / dt, "ms_per_step": dt * 1e3, "steps_timed": n}
+    out = {"cores": cores, "cpu_model": ref_cpu.host()["cpu_model"]}
+    if not ref_cpu.available():
+        out["unavailable"] = "oracle/_ref snapshot absent (python -m oracle.build_ref in the build container)"
+        return out
+    out["kind"] = "reference"
+    ff = {}
+    for B, warm, n in ((32, 5, 60), (4096, 3, 12)):
+        dt = ref_cpu.time_steps(ref_cpu.feedforward_loop(B), warm, n)
+        ff[f"batch_{B}"] = {"windows_per_s": B / dt, "ms_per_step": dt * 1e3, "warmup": warm, "steps_timed": n}
+    out["feedforward_train"] = dict(ff, what="configs[0]: reference FeedForwardBaseline [512,512] sigmoid + RegressionLossEvaluator + RMSprop(1e-4), fp32")
+    gl = {}
+    for B, warm, n in ((32, 2, 10), (256, 1, 4)):
+        dt = ref_cpu.time_steps(ref_cpu.groundlink_loop(B), warm, n)
+        gl[f"batch_{B}"] = {"windows_per_s": B / dt, "ms_per_step": dt * 1e3, "warmup": warm, "steps_timed": n}
+    out["groundlink_train"] = dict(gl, what="reference Groundlink(23,12,10) T=50, Dropout(0.2) active + evaluator + RMSprop, fp32")
+    dt = ref_cpu.time_steps(ref_cpu.transformer_forward(32), 2, 10)
+    out["transformer_analyze"] = {"windows_per_s": 32 / dt, "ms_per_batch": dt * 1e3, "batch": 32, "steps_timed": 10,
+                                  "what": "configs[4]: reference TransformerBaseline stack + heads, T=200, fp64, no_grad"}
+    sb = 64
+    dt = ref_cpu.time_steps(ref_cpu.denoiser_sampler(sb, C_IN, F, D_MODEL, HEADS, FF, LAYERS), 1, 4)
+    out["sampling"] = {"window_steps_per_s": sb / dt, "ms_per_denoise_step": dt * 1e3, "windows": sb, "steps_timed": 4,
+                       "what": "configs[3]: one reverse step = composed denoiser forward (reference TransformerLayer x8) + posterior update, fp32"}
     return out
 
 
@@ -204,6 +206,9 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="windows per GPU per step")
     ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary sampling / elementwise roofline measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sampling", action="store_true", help="skip the configs[3] reverse-sampling block")
+    ap.add_argument("--sampling-steps", type=int, default=1000, help="denoise steps of the sampling block (configs[3]: 1000)")
+    ap.add_argument("--sampling-windows", type=int, default=512, help="windows per GPU of the sampling block (configs[3]: 4096 / 8)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -317,10 +322,14 @@ def main():
     }
     if rank == 0:
         out["clocks"] = clock_info
+    from inferbiomechanics_b200 import bench_legs
+    if not args.no_sampling:
+        # the second half of BASELINE.json's metric ("train windows/sec & denoise steps/sec"): configs[3] exactly
+        out["sampling"] = bench_legs.sampling_leg(dev, world, rank, pk, model, windows_per_gpu=args.sampling_windows,
+                                                  steps=args.sampling_steps)
     if not args.no_aux:
         out["aux"] = trainer.aux_measurements(store, batches[0], pk, world)
         # the other BASELINE configs (not the headline metric): configs[0] model on the GPU, Groundlink, configs[4] stream
-        from inferbiomechanics_b200 import bench_legs
         del trainer, store
         torch.cuda.empty_cache()
         out["aux"]["feedforward_train"] = bench_legs.feedforward_train_leg(dev, world)
@@ -329,7 +338,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg()
         if "aux" in out:
-            out["aux"]["feedforward_train"]["cpu_port"] = cpu_feedforward_leg()
+            out["aux"]["cpu_other_configs"] = cpu_other_configs()
     if rank == 0:
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(out) + "\n").encode())

@@ -18,6 +18,23 @@ def _events():
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
+def max_over_ranks(ms: float) -> float:
+    """Every multi-GPU figure is computed from the SLOWEST rank's device time (all_reduce MAX), never rank 0's alone."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def _barrier():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
 def _per_kernel(fn) -> Dict[str, dict]:
     """One extra instrumented pass: CUDA events around every C-ABI launch (live, no profiler)."""
     real_call = ops.call
@@ -62,13 +79,13 @@ def feedforward_train_leg(dev, world: int, steps: int = 20) -> dict:
         for i in range(3):
             trainer.train_step(store, batches[i % 2])
         e0, e1 = _events()
-        torch.cuda.synchronize()
+        _barrier()
         e0.record()
         for i in range(steps):
             trainer.train_step(store, batches[i % 2])
         e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        _barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / steps)
         out[f"batch_{B}"] = {"windows_per_s": world * B / (ms * 1e-3), "ms_per_step": ms,
                              "tflops": 5505024.0 * B / (ms * 1e-3) / 1e12}
         del store
@@ -94,13 +111,13 @@ def groundlink_train_leg(dev, world: int, steps: int = 10, B: int = 4096, T: int
         for _ in range(3):
             step()
         e0, e1 = _events()
-        torch.cuda.synchronize()
+        _barrier()
         e0.record()
         for _ in range(steps):
             step()
         e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        _barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / steps)
         return {"windows_per_s": world * B / (ms * 1e-3), "ms_per_step": ms, "tflops_model": 3 * 110.016e6 * B / (ms * 1e-3) / 1e12}
 
     store = WindowStore.synthetic(2 * B, T, 1, 177, "all_frames", seed=5, device=dev)
@@ -154,13 +171,13 @@ def transformer_analyze_leg(dev, world: int, pk: dict, B: int = 2048, T: int = 2
     for _ in range(20):                               # ~50 ms of work: a GPU that was idle needs it to reach its clocks
         m(x)
     e0, e1 = _events()
-    torch.cuda.synchronize()
+    _barrier()
     e0.record()
     for _ in range(n_batches):
         out = m(x)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n_batches
+    _barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / n_batches)
     kern = _per_kernel(lambda: m(x))
     torch.set_grad_enabled(True)
     kern_ms = sum(v["ms"] for v in kern.values())
@@ -174,12 +191,12 @@ def transformer_analyze_leg(dev, world: int, pk: dict, B: int = 2048, T: int = 2
         assert got == n
 
     e2e_pass(3)
-    torch.cuda.synchronize()
+    _barrier()
     e0.record()
     e2e_pass(2 * n_batches)
     e1.record()
-    torch.cuda.synchronize()
-    ms_e2e = e0.elapsed_time(e1) / (2 * n_batches)
+    _barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / (2 * n_batches))
     oh = o_last = next(iter(m.forward_stream([xh])))
     # the host link on its own: the same pinned tensors copied H2D with nothing else running (explains the e2e figure, which is
     # bound by max(compute, H2D) per batch)
@@ -193,7 +210,7 @@ def transformer_analyze_leg(dev, world: int, pk: dict, B: int = 2048, T: int = 2
             xd[k].copy_(v, non_blocking=True)
     e1.record()
     torch.cuda.synchronize()
-    h2d_only_ms = e0.elapsed_time(e1) / 4
+    h2d_only_ms = max_over_ranks(e0.elapsed_time(e1) / 4)
     del xd
     h2d = sum(v.numel() * v.element_size() for v in xh.values())
     d2h = sum(v.numel() * v.element_size() for v in oh.values())
@@ -207,3 +224,82 @@ def transformer_analyze_leg(dev, world: int, pk: dict, B: int = 2048, T: int = 2
                     "api": "TransformerBaseline.forward_stream(iterable of pinned host input dicts)"},
             "full_stream": f"2^20 windows = {(1 << 20) / (world * B / (ms * 1e-3)):.2f} s at this rate on {world} GPU(s)",
             "note": "weak scaling (contiguous window shards, no collective); d=108 rows are padded to 112 bf16 columns, heads 36->48"}
+
+
+def sampling_leg(dev, world: int, rank: int, pk: dict, model, windows_per_gpu: int = 512, steps: int = 1000) -> dict:
+    """BASELINE configs[3] as stated: DDPM reverse sampling, the FULL 1000-step schedule, 4096 windows sharded over 8 GPUs =
+    512 windows per GPU (weak scaling: every rank samples its own 512, no collective).  ``value``: kinematic conditions
+    already packed in HBM, device-timed over the 1000 graph-replayed denoise steps, MAX over ranks.  ``e2e``: the public
+    call ``GaussianDiffusion.sample_windows`` with the conditions in pinned HOST memory and the trajectories returned to
+    pinned host memory (H2D + packing + 1000 steps + D2H inside the timed region).  ``roofline``: tensor-bound — algorithmic
+    FLOPs of the GEMM launches of one denoise step / their summed CUDA-event time (one eager, instrumented step)."""
+    from .diffusion import GaussianDiffusion
+    eng = model.engine()
+    F, C = eng.F, eng.c_in
+    sb = windows_per_gpu
+    gd = GaussianDiffusion(device=dev)
+    g = torch.Generator().manual_seed(4242)
+    cond_host = torch.randn(world * sb, F, C, generator=g).pin_memory()          # the whole job's windows; a rank reads its shard
+    mine = slice(rank * sb, (rank + 1) * sb)
+    ops.pack_inputs([cond_host[mine].reshape(-1, C).to(dev)], sb * F, F, out_bf16=eng.xc(sb, False), frame_stride=eng.ld_in,
+                    win_extra=0, col0=30)
+    seed = 1
+    gd.sample(model, sb, steps=20, seed=seed + rank)                             # captures the 2-step graph, warms the clocks
+    e0, e1 = _events()
+    _barrier()
+    e0.record()
+    x0 = gd.sample(model, sb, steps=steps, seed=seed + rank)
+    e1.record()
+    _barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    assert torch.isfinite(x0).all()
+    # end to end through the public sharded call
+    gd.sample_windows(model, cond_host, batch=sb, steps=4, seed=seed)            # staging buffers, streams
+    _barrier()
+    e0.record()
+    rng, traj = gd.sample_windows(model, cond_host, batch=sb, steps=steps, seed=seed)
+    e1.record()
+    _barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    assert len(rng) == sb and tuple(traj.shape) == (sb, F, 30) and not traj.is_cuda
+    # GEMMs of one denoise step (eager, events around every launch)
+    real = ops.gemm
+    recs = []
+
+    def timed(A, Bm, out, M, N, K, **kw):
+        a, b = _events()
+        a.record()
+        r = real(A, Bm, out, M, N, K, **kw)
+        b.record()
+        recs.append((a, b, 2.0 * M * N * K))
+        return r
+
+    ops.gemm = timed
+    try:
+        gd.sample(model, sb, steps=2, seed=seed + rank, use_graph=False)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = real
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in recs) / 2
+    gemm_fl = sum(f for _, _, f in recs) / 2
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    ach = gemm_fl / (gemm_ms * 1e-3) / 1e12
+    ms_step = ms / steps
+    return {
+        "metric": "denoise_window_steps_per_sec", "value": world * sb * steps / (ms * 1e-3), "unit": "window-steps/s",
+        "n_gpus": world, "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[3]: DDPM reverse sampling of GRF/CoP/torque/wrench trajectories, full schedule",
+                   "denoise_steps": steps, "windows_per_gpu": sb, "windows_total": world * sb, "frames": F, "cond_channels": C,
+                   "d_model": eng.d, "heads": eng.H, "ffn": eng.ff, "layers": eng.L, "parallelism": f"window shards x{world}, no collective"},
+        "ms_per_denoise_step": ms_step, "seconds_per_1000_step_batch": ms * 1e-3,
+        "e2e": {"value": world * sb * steps / (ms_e2e * 1e-3), "unit": "window-steps/s", "h2d_bytes_per_step": sb * F * C * 4,
+                "d2h_bytes_per_step": sb * F * 30 * 4, "seconds": ms_e2e * 1e-3,
+                "api": "GaussianDiffusion.sample_windows(model, cond: pinned host (N, F, 177), batch=512): a step of this leg = one "
+                       "512-window batch through all denoise steps; H2D conditions + pack + sampling + D2H trajectories timed"},
+        "roofline": {"bound": "tensor", "kernel": "ibm::gemm::gemm_kernel (all GEMM launches of one denoise step, M = 25 600 rows)",
+                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                     "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": len(recs) // 2, "gemm_share_of_step": gemm_ms / ms_step,
+                     "step_model_tflops": 2.57e9 * sb / (ms_step * 1e-3) / 1e12,
+                     "note": "512 windows x 50 frames = 25 600 rows per GEMM: 13-54 GFLOP launches of 15-50 us; the step is a chain of "
+                             "~60 short dependent launches replayed from a CUDA graph"},
+    }

@@ -118,3 +118,63 @@ class GaussianDiffusion:
         for _ in range((n_steps - done) // 2):
             st["graph"].replay()
         return x.view(B, F, 30).clone()
+
+    # ---- BASELINE configs[3]: a set of windows sharded over the ranks, no collective ------------------------------
+    @torch.no_grad()
+    def sample_windows(self, model, cond: torch.Tensor, *, batch: int = 512, steps: Optional[int] = None, seed: int = 0,
+                       rank: Optional[int] = None, world: Optional[int] = None):
+        """Reverse-sample GRF / CoP / torque / wrench trajectories for ``cond``: (N, F, C_in) fp32 packed kinematics of N
+        windows (model concat order, FeedForward...py:97-108) in HOST memory (pinned for asynchronous copies).
+
+        Windows are independent: rank r takes the contiguous range ``parallel.contiguous_shard(N, r, W)`` and walks it in
+        batches of ``batch`` windows — H2D copy of the batch's conditions, one packing kernel into the denoiser's concat buffer,
+        ``steps`` (default: the full schedule) CUDA-graph-replayed denoise steps, D2H copy of the trajectories — and returns
+        ``(range, x0)`` with x0 a pinned host tensor (len(range), F, 30).  No collective; per-rank noise stream = seed + rank.
+        The copies of batch i+1 / i-1 overlap the sampling of batch i (separate streams)."""
+        from . import parallel
+        r, w = parallel.world()
+        rank = r if rank is None else rank
+        world = w if world is None else world
+        eng = model.engine()
+        F, C = eng.F, eng.c_in
+        N = cond.shape[0]
+        assert tuple(cond.shape[1:]) == (F, C) and not cond.is_cuda, "cond: host tensor (N, F, C_in)"
+        mine = parallel.contiguous_shard(N, rank, world)
+        out = torch.empty(len(mine), F, 30, dtype=torch.float32).pin_memory()
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        stage = [torch.empty(batch * F, C, dtype=torch.float32, device=dev) for _ in range(2)]
+        uploaded = [torch.cuda.Event() for _ in range(2)]
+        packed = [torch.cuda.Event() for _ in range(2)]
+        starts = list(range(mine.start, mine.stop, batch))
+
+        def upload(i):
+            a, b = starts[i], min(starts[i] + batch, mine.stop)
+            with torch.cuda.stream(up):
+                up.wait_event(packed[i & 1])
+                stage[i & 1][:(b - a) * F].copy_(cond[a:b].reshape(-1, C), non_blocking=True)
+                uploaded[i & 1].record(up)
+
+        for e in packed:
+            e.record(main)
+        if starts:
+            upload(0)
+        pending = []
+        for i, a in enumerate(starts):
+            b = min(a + batch, mine.stop)
+            nb = b - a
+            main.wait_event(uploaded[i & 1])
+            ops.pack_inputs([stage[i & 1][:nb * F]], nb * F, F, out_bf16=eng.xc(nb, False), frame_stride=eng.ld_in, win_extra=0, col0=30)
+            packed[i & 1].record(main)
+            if i + 1 < len(starts):
+                upload(i + 1)
+            x0 = self.sample(model, nb, steps=steps, seed=seed + rank + 7919 * i)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(down):
+                down.wait_event(ready)
+                out[a - mine.start:b - mine.start].copy_(x0, non_blocking=True)
+            pending.append(x0)                                # keeps the device tensor alive until the copy has run
+        down.synchronize()
+        return mine, out

@@ -536,8 +536,8 @@ def _time_kernel(fn, iters: int = 20) -> float:
 
 
 def _aux_measurements(self, store, idx, pk, world):
-    """HBM-bound kernels against the measured copy bandwidth, and reverse-sampling throughput
-    (BASELINE configs[3]: 512 windows per GPU, graph-replayed steps).  Inputs (>= 300 MB) exceed L2."""
+    """HBM-bound kernels against the measured copy bandwidth (inputs >= 300 MB exceed L2), the per-shape GEMM table and the
+    per-kernel times of one training step.  Reverse sampling (BASELINE configs[3]) is bench_legs.sampling_leg."""
     B = idx.numel()
     dev = self.arena.device
     hbm = pk["hbm_gbs"]
@@ -594,24 +594,22 @@ def _aux_measurements(self, store, idx, pk, world):
             e = shapes.setdefault("x".join(str(v) for v in shp), [0, 0.0, 0.0])
             e[0] += 1; e[1] += ms; e[2] += fl
         out["other_kernels_ms_per_step"] = getattr(self, "last_kernel_ms", {})
+        # the HBM-bound layer kernels as they run INSIDE the training step (power-capped clocks, cold L2, neighbours' tails):
+        # algorithmic bytes per launch / in-step CUDA-event time per launch, against the measured copy bandwidth
+        Mrows, d_ = B * F, eng.d
+        per_launch = {"ibm_attention_fwd": 8.0 * d_ * Mrows, "ibm_attention_bwd": 14.0 * d_ * Mrows,
+                      "ibm_layernorm_fwd": (4.0 * d_ + 8.0) * Mrows, "ibm_layernorm_bwd": (6.0 * d_ + 8.0) * Mrows,
+                      "ibm_regression_loss_fwd": 240.0 * Mrows, "ibm_regression_loss_bwd": 300.0 * Mrows}
+        tab = {}
+        for name, by in per_launch.items():
+            rec = out["other_kernels_ms_per_step"].get(name)
+            if rec and rec["ms"] > 0:
+                us = rec["ms"] * 1e3 / rec["launches"]
+                tab[name] = {"launches": rec["launches"], "us_per_launch": round(us, 1), "algorithmic_bytes": by,
+                             "achieved": by / us / 1e3, "peak": hbm, "unit": "GB/s", "frac": by / us / 1e3 / hbm}
+        out["hbm_kernels_in_step"] = tab
         out["gemm_shapes_MxNxK"] = {k: {"launches": v[0], "ms": round(v[1], 4), "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1)}
                                     for k, v in shapes.items()}
-        # reverse sampling: 512 windows per GPU, CUDA-graph replays (2 steps per replay), no collective
-        from .diffusion import GaussianDiffusion
-        sb, steps = 512, 200
-        gd = GaussianDiffusion(num_timesteps=steps, device=dev)
-        eng.xc(sb, False)[:, 30:30 + eng.c_in] = torch.randn(sb * F, eng.c_in, device=dev).to(torch.bfloat16)
-        gd.sample(self.model, sb, seed=1)                       # builds the graph
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        gd.sample(self.model, sb, seed=1)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        out["sampling"] = {"metric": "denoise_window_steps_per_sec", "value": world * sb * steps / (ms * 1e-3), "unit": "window-steps/s",
-                           "windows_per_gpu": sb, "steps_timed": steps, "ms_per_step": ms / steps,
-                           "note": "BASELINE configs[3] shape (512 windows/GPU); 1000-step run = 5x this loop; weak scaling, no collective"}
     return out
 
 

@@ -1,5 +1,6 @@
-"""Import the *real* reference modules from /root/reference (only possible in the build
-container; the GPU box has no /root/reference).  TEST INFRASTRUCTURE ONLY.
+"""Import the *real* reference modules: from /root/reference in the build container, from the verbatim snapshot
+``oracle/_ref`` (written by ``oracle/build_ref.py``, git-ignored, shipped by gpurun) on the GPU box, which has no
+/root/reference.  TEST / BASELINE INFRASTRUCTURE ONLY.
 
 The reference imports ``nimblephysics`` (C++/pybind, ~=0.10.20, not installed, not vendored)
 at ``src/data/AddBiomechanicsDataset.py:1`` and ``matplotlib`` at
@@ -13,10 +14,19 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("IBM_REFERENCE_ROOT", "/root/reference")
+SNAPSHOT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_root():
+    """/root/reference if present, else the oracle/_ref snapshot, else None."""
+    for root in (REFERENCE_ROOT, SNAPSHOT_ROOT):
+        if os.path.isfile(os.path.join(root, "src", "models", "TransformerBaseline.py")):
+            return root
+    return None
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "models"))
+    return reference_root() is not None
 
 
 def _install_stubs() -> None:
@@ -56,11 +66,12 @@ def load_reference():
     """Returns a namespace with the reference classes.  Raises RuntimeError if absent."""
     if "ns" in _cache:
         return _cache["ns"]
-    if not reference_available():
-        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError(f"reference present neither at {REFERENCE_ROOT} nor as the snapshot {SNAPSHOT_ROOT} (python -m oracle.build_ref)")
     _install_stubs()
-    src = os.path.join(REFERENCE_ROOT, "src")
-    for p in (src, REFERENCE_ROOT):
+    src = os.path.join(root, "src")
+    for p in (src, root):
         if p not in sys.path:
             sys.path.insert(0, p)
     import io
@@ -77,6 +88,6 @@ def load_reference():
         FeedForwardBaseline=FeedForwardBaseline, Groundlink=Groundlink,
         TransformerLayer=TransformerLayer, TemporalEmbedding=TemporalEmbedding,
         SimpleAttention=SimpleAttention, TransformerBaseline=TransformerBaseline,
-        RegressionLossEvaluator=RegressionLossEvaluator)
+        RegressionLossEvaluator=RegressionLossEvaluator, root=root)
     _cache["ns"] = ns
     return ns

@@ -550,6 +550,31 @@ def test_sampling_graph_equals_eager():
     torch.testing.assert_close(a, d, rtol=0, atol=0)
 
 
+def test_sample_windows_shards_without_collective():
+    """BASELINE configs[3] entry point: host conditions in, host trajectories out, contiguous window shards per rank, no
+    collective.  The shards of a 2-rank run (rank/world passed explicitly on one GPU) tile the window range, each shard
+    equals direct ``sample`` calls with the documented per-(rank, batch) seeds, and a ragged last batch is handled."""
+    from inferbiomechanics_b200 import ops
+    from inferbiomechanics_b200.diffusion import GaussianDiffusion
+    F, N, batch = 10, 21, 8
+    m, _ = _small_denoiser(F=F, L=1)
+    eng = m.engine()
+    gd = GaussianDiffusion(num_timesteps=12, device="cuda")
+    cond = torch.randn(N, F, 177, generator=torch.Generator().manual_seed(4)).pin_memory()
+    shards = [gd.sample_windows(m, cond, batch=batch, seed=9, rank=r, world=2) for r in range(2)]
+    assert [len(s[0]) for s in shards] == [11, 10] and shards[0][0].stop == shards[1][0].start == 11
+    for r, (rng, x0) in enumerate(shards):
+        assert tuple(x0.shape) == (len(rng), F, 30) and not x0.is_cuda and x0.is_pinned() and torch.isfinite(x0).all()
+        for i, a in enumerate(range(rng.start, rng.stop, batch)):
+            b = min(a + batch, rng.stop)
+            ops.pack_inputs([cond[a:b].reshape(-1, 177).cuda()], (b - a) * F, F, out_bf16=eng.xc(b - a, False), frame_stride=eng.ld_in,
+                            win_extra=0, col0=30)
+            want = gd.sample(m, b - a, seed=9 + r + 7919 * i)
+            torch.testing.assert_close(x0[a - rng.start:b - rng.start], want.cpu(), rtol=0, atol=0)
+    # different windows / ranks draw different noise
+    assert not torch.equal(shards[0][1][:8], shards[1][1][:8])
+
+
 # ---------------------------------------------------------------------------------------------------
 # host-fed loops: the pipelined generator (prefetching copies, loss read one step late) == step-by-step calls
 # ---------------------------------------------------------------------------------------------------
