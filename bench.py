@@ -335,6 +335,8 @@ def main():
         out["aux"]["feedforward_train"] = bench_legs.feedforward_train_leg(dev, world)
         out["aux"]["groundlink_train"] = bench_legs.groundlink_train_leg(dev, world)
         out["aux"]["transformer_analyze"] = bench_legs.transformer_analyze_leg(dev, world, pk)
+        if rank == 0:
+            out["aux"]["batch1_latency"] = bench_legs.batch1_latency_leg(dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg()
         if "aux" in out:

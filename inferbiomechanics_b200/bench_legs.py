@@ -303,3 +303,46 @@ def sampling_leg(dev, world: int, rank: int, pk: dict, model, windows_per_gpu: i
                      "note": "512 windows x 50 frames = 25 600 rows per GEMM: 13-54 GFLOP launches of 15-50 us; the step is a chain of "
                              "~60 short dependent launches replayed from a CUDA graph"},
     }
+
+
+def batch1_latency_leg(dev) -> dict:
+    """latency of ``model(inputs)`` on ONE window from host tensors under no_grad, as the per-window viewers call
+    it (visualize.py:157-186, save_prediction_csv.py:91-113): host wall-clock per call including the H2D copy of the window and
+    a device synchronize (the caller reads the prediction), median of 200 calls; eager launches vs the captured graph."""
+    import os
+    import statistics
+    import time
+    from .keys import MODEL_INPUT_ORDER
+    from .models.FeedForwardRegressionBaseline import FeedForwardBaseline
+    from .models.Groundlink import Groundlink
+    torch.manual_seed(0)
+    out = {}
+    widths = lambda hist: dict(zip(MODEL_INPUT_ORDER, [23, 23, 23, 3, 3, 3, 3, 36, hist, hist]))
+    cases = {"feedforward": (FeedForwardBaseline(23, 2, 50, "all_frames", "sigmoid", 5, 10).to(dev).eval(), 10, 15),
+             "groundlink": (Groundlink(23, 12, 10, "all_frames").to(dev).eval(), 50, 30)}
+    prev = os.environ.get("IBM_INFER_GRAPHS")
+    try:
+        with torch.no_grad():
+            for name, (m, F, hist) in cases.items():
+                x = {k: torch.randn(1, F, w) for k, w in widths(hist).items()}
+                res = {}
+                for mode, flag in (("eager", "0"), ("graph", "1")):
+                    os.environ["IBM_INFER_GRAPHS"] = flag
+                    for _ in range(10):
+                        m(x)
+                    torch.cuda.synchronize()
+                    ts = []
+                    for _ in range(200):
+                        t0 = time.perf_counter()
+                        o = m(x)
+                        torch.cuda.synchronize()
+                        ts.append(time.perf_counter() - t0)
+                    res[f"{mode}_us"] = round(statistics.median(ts) * 1e6, 1)
+                out[name] = res
+    finally:
+        if prev is None:
+            os.environ.pop("IBM_INFER_GRAPHS", None)
+        else:
+            os.environ["IBM_INFER_GRAPHS"] = prev
+    out["note"] = "one window per call from CPU tensors; host wall-clock incl. concat + H2D + launches + synchronize, median of 200"
+    return out

@@ -63,6 +63,23 @@ class _ResultLog:
         self.ev.print_report(args, reset=reset, log_to_wandb=log_to_wandb)
 
 
+def print_all_ranks_report(ev: RegressionLossEvaluator, args, rank: int, world: int, device) -> None:
+    """Rank-0 aggregate over all data-parallel ranks, printed next to the per-rank report the reference prints
+    (train.py:223-229,286-292 report per process).  One allreduce of the 40-float mean result; every rank must call it,
+    BEFORE the evaluator's lists are reset."""
+    if world == 1:
+        return
+    st = ev._stack()
+    local = torch.from_numpy(st.mean(axis=0)).to(device) if st.shape[0] else torch.zeros(40, device=device)
+    merged = parallel.mean_over_ranks(local)
+    if rank == 0:
+        tmp = RegressionLossEvaluator(None, ev.split)
+        tmp._results = [merged.cpu()]
+        tmp._wm_results = [merged.cpu()]
+        print(f'[all {world} ranks] {ev.split} set:')
+        tmp.print_report(args, reset=True)
+
+
 class _TrainerOptimizer:
     """``optimizer``-shaped handle on a native ``Trainer`` for ``load_latest_checkpoint`` (abstract_command.py:113-114)."""
 
@@ -192,6 +209,7 @@ class TrainCommand(AbstractCommand):
                         if (i + 1) % 100 == 0 or i == len(dev_batches) - 1:
                             print('  - Dev Batch ' + str(i + 1) + '/' + str(len(dev_batches)))
                 print(f'[{rank=}] Dev Set Evaluation: ')
+                print_all_ranks_report(dev_log.ev if native else dev_ev, args, rank, world, device)
                 (dev_log if native else dev_ev).print_report(args, log_to_wandb=log_to_wandb)
             if world > 1:
                 dist.barrier()
@@ -221,6 +239,7 @@ class TrainCommand(AbstractCommand):
             logging.info('-' * 80)
             logging.info(f'[{rank=}] Epoch {epoch}/{args.epochs} Training Set Evaluation: ')
             logging.info('-' * 80)
+            print_all_ranks_report(train_log.ev if native else train_ev, args, rank, world, device)
             (train_log if native else train_ev).print_report(args, log_to_wandb=log_to_wandb)
             logging.info('-' * 80)
 

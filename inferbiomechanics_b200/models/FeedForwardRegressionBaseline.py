@@ -132,13 +132,22 @@ class FeedForwardBaseline(EngineModule):
         eng = self.engine()
         B, F = input[InputDataKeys.POS].shape[0], input[InputDataKeys.POS].shape[1]
         assert F * self.frame_width == self.input_size, "window length does not match history_len // stride"
+        if self._latency_path(B):
+            # batch-of-1 viewers (visualize.py:181, save_prediction_csv.py:103): pack + 3 GEMMs replayed from one CUDA graph
+            def launch(rows):
+                ops.pack_inputs([rows], B * F, F, out_bf16=eng.input_buffer(B), frame_stride=self.frame_width,
+                                win_extra=eng.in_ld - self.input_size, col0=0)
+                return eng.forward(B, train=False)
+            return self._split(self._graphed_inference(input, F, launch)[:, :eng.out_cols], B)
         # 2. concat + flatten + bf16 in one kernel (row-per-window layout, K padded to a multiple of 8)
         self._pack_dict(input, eng.input_buffer(B), F, frame_stride=self.frame_width, win_extra=eng.in_ld - self.input_size, col0=0)
         return self.forward_packed(B)
 
     def forward_packed(self, B: int) -> Dict[str, torch.Tensor]:
         """Forward from an already packed engine.input_buffer(B) (the window-store fast path)."""
-        x = _FeedForwardFunction.apply(self, B, *self.parameters())
+        return self._split(_FeedForwardFunction.apply(self, B, *self.parameters()), B)
+
+    def _split(self, x: torch.Tensor, B: int) -> Dict[str, torch.Tensor]:
         Fo = self.num_output_frames
         # 4. quantity-then-frame blocks (FeedForward…py:116-121)
         return {

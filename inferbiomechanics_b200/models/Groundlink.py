@@ -129,12 +129,20 @@ class Groundlink(EngineModule):
         eng = self.engine()
         B, T = input[InputDataKeys.POS].shape[0], input[InputDataKeys.POS].shape[1]
         buf, fs, we, col0 = eng.input_rows(B, T)
+        if self._latency_path(B):
+            # batch-of-1 viewers: packer + 4 implicit-GEMM convolutions + pad refreshes + MLP replayed from one CUDA graph
+            def launch(rows):
+                ops.pack_inputs([rows], B * T, T, out_bf16=buf, frame_stride=fs, win_extra=we, col0=col0)
+                return eng.forward(B, T, False)
+            return self._split(self._graphed_inference(input, T, launch))
         # 2. concat → bf16 rows in the padded-row layout (frame t of window b at row b*(T+6) + 3 + t)
         self._pack_dict(input, buf, T, frame_stride=fs, win_extra=we, col0=col0)
         return self.forward_packed(B, T)
 
     def forward_packed(self, B: int, T: int) -> Dict[str, torch.Tensor]:
-        x = _GroundlinkFunction.apply(self, B, T, self.training and torch.is_grad_enabled(), *self.parameters())
+        return self._split(_GroundlinkFunction.apply(self, B, T, self.training and torch.is_grad_enabled(), *self.parameters()))
+
+    def _split(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         if self.output_data_format != 'all_frames':
             x = x[:, -1:, :]                       # Groundlink.py:147-148: only the last frame goes through the MLP
         return {

@@ -119,3 +119,15 @@ class GradBucketer:
     def broadcast_(self, flat_param: torch.Tensor, src: int = 0) -> None:
         if self.world > 1:
             dist.broadcast(flat_param, src=src, group=self.group)
+
+
+def mean_over_ranks(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Plain mean of a small per-rank tensor over all ranks (one allreduce of ~40 floats).  The reference keeps metrics per
+    rank (one wandb run per process, train.py:103-118); this is the optional rank-0 aggregate of SURVEY §8e/§8f-4 — with the
+    DistributedSampler's equal shard sizes the mean of per-rank means of batch means is the global mean of batch means."""
+    rank, ws = world()
+    if ws == 1:
+        return t.clone()
+    out = t.clone()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out / ws

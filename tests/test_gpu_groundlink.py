@@ -212,3 +212,37 @@ def test_groundlink_constructor_variants_match_reference_golden(golden, name, fm
         assert rel <= 0.12 and cos >= 0.985, f"{n}: rel L2 {rel:.4f}, cosine {cos:.4f}"
     with pytest.raises(NotImplementedError):
         Groundlink(D, J, H, fmt, cnn_kernel=6)
+
+
+def test_batch_of_one_latency_path_equals_eager(monkeypatch):
+    """SURVEY §8f-4: the viewers' ``model(inputs)`` on ONE window under no_grad replays a captured CUDA graph (pack + GEMMs);
+    same bits as the eager launches, picks up weight changes (the graph reads the arena through stable pointers; re-laid-out
+    conv weights are refreshed outside it), leaves the training path alone."""
+    from inferbiomechanics_b200.models.FeedForwardRegressionBaseline import FeedForwardBaseline
+    from inferbiomechanics_b200.models.Groundlink import Groundlink
+    torch.manual_seed(0)
+    cases = [(FeedForwardBaseline(23, 2, 50, "all_frames", "sigmoid", 5, 10).cuda().eval(), 10, 15),
+             (Groundlink(23, 12, 10, "last_frame").cuda().eval(), 50, 30)]
+    for m, F, hist in cases:
+        xs = [seeded_inputs(1, F, 23, hist, 40 + i) for i in range(5)]
+        with torch.no_grad():
+            monkeypatch.setenv("IBM_INFER_GRAPHS", "0")
+            eager = [{k: v.clone() for k, v in m(x).items()} for x in xs]
+            monkeypatch.setenv("IBM_INFER_GRAPHS", "1")
+            graphed = [{k: v.clone() for k, v in m(x).items()} for x in xs]      # calls 1-2 eager, 3 captures, 4-5 replay
+            assert any(st["graph"] is not None for st in m._lat.values())
+            for a, b in zip(eager, graphed):
+                for k in Q:
+                    assert torch.equal(a[k], b[k]), k
+            # weights change under the captured graph: the replay must see them
+            with torch.no_grad():
+                for p in m.parameters():
+                    p.mul_(0.5)
+            monkeypatch.setenv("IBM_INFER_GRAPHS", "0")
+            want = {k: v.clone() for k, v in m(xs[0]).items()}
+            monkeypatch.setenv("IBM_INFER_GRAPHS", "1")
+            got = m(xs[0])
+            for k in Q:
+                assert torch.equal(want[k], got[k]) and not torch.equal(want[k], eager[0][k])
+        out = m(xs[0])                                       # grad enabled: the autograd path, not the graph
+        assert out[Q[0]].requires_grad

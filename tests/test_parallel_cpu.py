@@ -84,3 +84,38 @@ def test_bucketed_allreduce_gloo_world2():
         assert ok and same
         assert fired == sorted(fired) and fired[-1] == collectives          # buckets fire progressively during "backward"
         assert collectives >= 2 and psum == 0.0                                # params equal rank 0's
+
+
+def _agg_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import argparse
+        import contextlib
+        import io
+        from inferbiomechanics_b200.cli.train import print_all_ranks_report
+        from inferbiomechanics_b200.loss.RegressionLossEvaluator import RegressionLossEvaluator
+        ev = RegressionLossEvaluator(None, "dev")
+        for b in range(3):                               # three "batches" per rank, result vector = rank*10 + batch everywhere
+            ev._results.append(torch.full((40,), float(rank * 10 + b)))
+        args = argparse.Namespace(predict_grf_components=[0], predict_cop_components=[], predict_moment_components=[],
+                                  predict_wrench_components=[])
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            print_all_ranks_report(ev, args, rank, world, torch.device("cpu"))
+        out[rank] = (buf.getvalue(), len(ev._results), float(parallel.mean_over_ranks(torch.tensor([float(rank)]))[0]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank0_metric_aggregate_gloo_world2():
+    """rank 0 prints one aggregate over all ranks (mean of per-rank means of batch results) next to the
+    per-rank reports of the reference; the per-rank lists are left untouched."""
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_agg_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    text0, n0, m0 = out[0]
+    text1, n1, m1 = out[1]
+    assert n0 == n1 == 3 and m0 == m1 == 0.5
+    assert text1 == "" and "[all 2 ranks] dev set:" in text0
+    assert "Force Avg Err: 6.0 N / kg" in text0          # mean over ranks {0,1} and batches {0,1,2} of rank*10 + batch
