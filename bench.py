@@ -231,6 +231,7 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = parallel.bind_to_gpu_numa(local)      # before any pinned allocation: host staging lands on the GPU's NUMA node
     B = args.batch
     torch.manual_seed(0)
     model = DiffusionDenoiser(frames=F, d_model=D_MODEL, num_heads=HEADS, dim_feedforward=FF, num_layers=LAYERS).to(dev)
@@ -320,6 +321,7 @@ def main():
                 "ms_per_step": e2e_ms.item() / args.steps, "api": "for loss in Trainer.train_steps_host(iterable of (inputs: Dict[str, pinned CPU Tensor], labels)): per step H2D of the 14 tensors + D2H loss read, next batch prefetched on a copy stream"},
         "gpu_launches": launches, "roofline": roofline, "final_loss": final_loss, "loss_host": loss_host,
     }
+    out["host_affinity"] = None if numa_cpus is None else f"{len(numa_cpus)} cores local to the GPU's PCIe root (rank 0)"
     if rank == 0:
         out["clocks"] = clock_info
     from inferbiomechanics_b200 import bench_legs

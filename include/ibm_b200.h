@@ -94,6 +94,13 @@ int ibm_pack_inputs(const void* const* h_src, const int32_t* h_widths, int32_t n
 int ibm_pack_channel_major(const void* const* srcs, const int32_t* channels, int32_t n_src, int64_t B, int32_t T,
                            const float* emb, int32_t E, void* out_bf16, int64_t ld, void* stream);
 
+/* Pre-packed analysis stream: rows converted once on the host to frame-major bf16 [n_rows = B*T, ld_src] (C channels per frame)
+ * -> the TransformerBaseline's input rows [n_rows, ld] = [C channels | E temporal-embedding columns of frame r % T | zeros],
+ * bit-identical to ibm_pack_channel_major on the fp32 (B, C, T) tensors (TransformerBaseline.py:108-126); v_out (may be NULL):
+ * bf16 [n_rows, 8] <- columns [v_col0, v_col0+3) | zeros (the CoM accelerations blended by SimpleAttention, …:135-137). */
+int ibm_expand_rows_bf16(const void* src_bf16, int64_t ld_src, int32_t C, int64_t n_rows, int32_t T, const float* emb,
+                         int32_t E, void* out_bf16, int64_t ld, void* v_out_bf16, int32_t v_col0, void* stream);
+
 /* Label rows (Dataset.py:216-261): raw first-pass per-frame [cop 3nb | force 3nb | torque 3nb |
  * wrench 6nb] in the SUBJECT's body order → rows30 in the DATASET's body order, force/torque/
  * wrench divided by the subject mass (IEEE fp32 division), absent bodies → 0.

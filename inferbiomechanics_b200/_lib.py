@@ -57,6 +57,7 @@ SIGNATURES = {
     "ibm_layernorm_bwd": [P, P, _i64, P, P, P, _i64, _i32, P, P, P, P, P],
     "ibm_attention_fwd": [P, _i64, P, _i64, P, _i64, P, _i64, _i64, _i32, _i32, _i32, _i32, _f, P],
     "ibm_attention_bwd": [P, _i64, _i64, P, _i64, P, _i64, _i32, _i32, _i32, _f, P, P],
+    "ibm_expand_rows_bf16": [P, _i64, _i32, _i64, _i32, P, _i32, P, _i64, P, _i32, P],
     "ibm_attention_bwd_long": [P, _i64, P, _i64, P, _i64, P, _i64, P, _i64, P, _i64, P, _i64, P, _i64, _i64, _i32, _i32, _i32, _i32, _f,
                                P, P, P, P],
     "ibm_optimizer_step": [_i32, P, P, P, P, P, _i64, _f, _f, _i64, P],

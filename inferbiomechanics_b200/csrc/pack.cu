@@ -229,6 +229,43 @@ pack_channel_major_kernel(ChanSrc src, int T, const float* __restrict__ emb, int
     *reinterpret_cast<uint32_t*>(out + (b * T + t0 + f) * ld + c) = pack_bf16x2(v[0], v[1]);
   }
 }
+// Pre-packed analysis stream (BASELINE configs[4]): rows that were converted ONCE on the host to frame-major bf16
+// ([B*T, ld_src], the C kinematic channels of a frame contiguous) are expanded into the transformer's input rows
+// [B*T, ld] = [C channels | E temporal-embedding columns of frame t | zero pad] — bit-identical to what
+// pack_channel_major_kernel writes from the fp32 channel-major tensors (same RNE bf16 values) — and, optionally, columns
+// [vcol0, vcol0 + 3) go to an 8-wide value buffer (the CoM accelerations the SimpleAttention blends, TransformerBaseline.py:135).
+// One thread per 2 output columns; reads and writes are both row-contiguous.
+__global__ void __launch_bounds__(kThreads)
+expand_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, int C, int T, const float* __restrict__ emb, int E,
+                        __nv_bfloat16* __restrict__ out, long long ld, __nv_bfloat16* __restrict__ vout, int vcol0, long long n_rows) {
+  const int pairs = (int)(ld >> 1);
+  const long long total = n_rows * pairs;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / pairs;
+    const int c = 2 * (int)(i - r * pairs);
+    const int t = (int)(r % T);
+    uint32_t w;
+    if (c + 1 < C) {
+      w = *reinterpret_cast<const uint32_t*>(src + r * ld_src + c);
+    } else {
+      float v[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int cc = c + j;
+        v[j] = cc < C ? __bfloat162float(src[r * ld_src + cc]) : (cc < C + E ? __ldg(emb + (long long)t * E + (cc - C)) : 0.f);
+      }
+      w = pack_bf16x2(v[0], v[1]);
+    }
+    *reinterpret_cast<uint32_t*>(out + r * ld + c) = w;
+    if (vout != nullptr && c < 8) {                       // threads of output columns 0..7 also write the 8-wide value row
+      float v[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) v[j] = (c + j < 3) ? __bfloat162float(src[r * ld_src + vcol0 + c + j]) : 0.f;
+      *reinterpret_cast<uint32_t*>(vout + r * 8 + c) = pack_bf16x2(v[0], v[1]);
+    }
+  }
+}
 }  // namespace ibm
 
 extern "C" int ibm_pack_channel_major(const void* const* h_src, const int32_t* h_channels, int32_t n_src, int64_t B, int32_t T,
@@ -281,6 +318,21 @@ extern "C" int ibm_pack_inputs(const void* const* h_src, const int32_t* h_widths
   }
   pack_inputs_kernel<<<grid_for(n_rows * src.offset[n_src], kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       src, n_rows, F, out_f32, static_cast<__nv_bfloat16*>(out_bf16), bf16_frame_stride, bf16_win_extra, bf16_col0);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+extern "C" int ibm_expand_rows_bf16(const void* src_bf16, int64_t ld_src, int32_t C, int64_t n_rows, int32_t T, const float* emb,
+                                    int32_t E, void* out_bf16, int64_t ld, void* v_out_bf16, int32_t v_col0, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(src_bf16 && out_bf16 && n_rows > 0 && T > 0 && C > 0 && n_rows % T == 0, "expand_rows_bf16: bad argument");
+  IBM_CHECK_ARG(E >= 0 && (E == 0 || emb), "expand_rows_bf16: embedding width without a table");
+  IBM_CHECK_ARG(ld % 2 == 0 && ld >= C + E && ld_src % 2 == 0 && ld_src >= C, "expand_rows_bf16: ld must be even and >= C + E, ld_src even and >= C");
+  IBM_CHECK_ARG(v_out_bf16 == nullptr || (v_col0 >= 0 && v_col0 + 3 <= C), "expand_rows_bf16: value columns outside the row");
+  expand_rows_bf16_kernel<<<grid_for(n_rows * (ld / 2), kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src_bf16), ld_src, C, T, emb, E, static_cast<__nv_bfloat16*>(out_bf16), ld,
+      static_cast<__nv_bfloat16*>(v_out_bf16), v_col0, n_rows);
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }

@@ -53,6 +53,13 @@ def pack_channel_major(srcs, T, emb, out_bf16):
          stream_ptr())
 
 
+def expand_rows_bf16(src_bf16, C, T, emb, out_bf16, v_out=None, v_col0=0):
+    """src bf16 [B*T, ld_src] frame-major rows (pre-packed on the host) -> out bf16 [B*T, ld] with the temporal embedding appended."""
+    n_rows = out_bf16.shape[0]
+    call("ibm_expand_rows_bf16", _p(src_bf16), src_bf16.stride(0), C, n_rows, T, _p(emb), 0 if emb is None else emb.shape[1],
+         _p(out_bf16), out_bf16.stride(0), _p(v_out), v_col0, stream_ptr())
+
+
 # ---- GEMM ---------------------------------------------------------------------------------------
 def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, M: int, N: int, K: int, *, lda=None, ldb=None, ldd=None,
          a_mn=False, b_mn=False, bias: Optional[torch.Tensor] = None, act="none", aux: Optional[torch.Tensor] = None,

@@ -211,3 +211,35 @@ def test_transformer_training_step_reduces_loss():
     with torch.no_grad():                                   # the inference path sees the updated weights
         o2 = m(x)
     assert not o2[O.CONTACT].requires_grad
+
+
+def test_prepacked_bf16_stream_is_bit_identical():
+    """configs[4] host feed: windows converted once on the host to frame-major bf16 rows (TransformerBaseline.prepack, half
+    the bytes over the link) give the bits of the fp32 dict inputs — through forward and through forward_stream."""
+    from inferbiomechanics_b200.keys import InputDataKeys as K, OutputDataKeys as O
+    from inferbiomechanics_b200.models.TransformerBaseline import TransformerBaseline
+    T, D = 200, 23
+    torch.manual_seed(2)
+    m = TransformerBaseline(D, T, dtype=torch.float32).cuda()
+    g = torch.Generator().manual_seed(3)
+    chans = [(K.POS, D), (K.VEL, D), (K.ACC, D), (K.COM_POS, 3), (K.COM_VEL, 3), (K.COM_ACC, 3)]
+    batches = [{k: torch.randn(B, c, T, generator=g) for k, c in chans} for B in (6, 6, 3)]
+    packed = [TransformerBaseline.prepack(b) for b in batches]
+    assert packed[0].shape == (6, T, 80) and packed[0].dtype == torch.bfloat16 and packed[0].is_pinned()
+    assert packed[0].numel() * 2 * 2 <= sum(v.numel() * 4 for v in batches[0].values()) * 1.03      # half the bytes (+ 2 pad columns)
+    with torch.no_grad():
+        for b, p in zip(batches, packed):
+            want = {k: v.clone() for k, v in m(b).items()}
+            got = m(p)
+            for k in (O.CONTACT, O.COM_ACC, O.CONTACT_FORCES):
+                assert torch.equal(want[k], got[k]), k
+        want = [{k: v.cpu().clone() for k, v in m(b).items()} for b in batches]
+    got = [{k: v.clone() for k, v in o.items()} for o in m.forward_stream(packed)]
+    assert len(got) == 3
+    for a, b in zip(got, want):
+        for k in (O.CONTACT, O.COM_ACC, O.CONTACT_FORCES):
+            assert torch.equal(a[k], b[k])
+    # the training path takes the packed rows too
+    out = m(packed[2])
+    out[O.CONTACT_FORCES].square().mean().backward()
+    assert m.fc.weight.grad is not None and torch.isfinite(m.fc.weight.grad).all()
