@@ -836,15 +836,28 @@ extern "C" int ibm_attention_fwd(const void* q, int64_t ldq, const void* k, int6
       if (hd_qk == 64 && hd_v == 64) return attn::launch_fwd_long<64, 64>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
       if (hd_qk == 48 && hd_v == 48) return attn::launch_fwd_long<48, 48>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
       if (hd_qk == 32 && hd_v == 32) return attn::launch_fwd_long<32, 32>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
-      // the CoM blend of the TransformerBaseline (SimpleAttention, TransformerBaseline.py:51-70): 112-wide q/k, 8-wide values
-      if (hd_qk == 112 && hd_v == 8) return attn::launch_fwd_long<112, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+      // the CoM blend of the TransformerBaseline (SimpleAttention, TransformerBaseline.py:51-70): d-wide q/k (d = 3*dofs + 9 +
+      // temporal_embedding_dim padded to a multiple of 16: 112 for the dataset's 23 DOF), 8-wide values
+      if (hd_v == 8) {
+        if (hd_qk == 112) return attn::launch_fwd_long<112, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+        if (hd_qk == 64) return attn::launch_fwd_long<64, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+        if (hd_qk == 80) return attn::launch_fwd_long<80, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+        if (hd_qk == 96) return attn::launch_fwd_long<96, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+        if (hd_qk == 128) return attn::launch_fwd_long<128, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+      }
     }
   }
   if (hd_qk == 64 && hd_v == 64) return attn::launch_fwd<64, 64>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
   if (hd_qk == 48 && hd_v == 48) return attn::launch_fwd<48, 48>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
   if (hd_qk == 32 && hd_v == 32) return attn::launch_fwd<32, 32>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
-  if (hd_qk == 112 && hd_v == 8) return attn::launch_fwd<112, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
-  set_error("attention_fwd: unsupported head dims (%d, %d); supported (64,64) (48,48) (32,32) (112,8)", hd_qk, hd_v);
+  if (hd_v == 8) {
+    if (hd_qk == 112) return attn::launch_fwd<112, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+    if (hd_qk == 64) return attn::launch_fwd<64, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+    if (hd_qk == 80) return attn::launch_fwd<80, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+    if (hd_qk == 96) return attn::launch_fwd<96, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+    if (hd_qk == 128) return attn::launch_fwd<128, 8>(q, ldq, k, ldk, v, ldv, o, ldo, n_win, T, H, scale, s);
+  }
+  set_error("attention_fwd: unsupported head dims (%d, %d); supported (64,64) (48,48) (32,32) and ({64,80,96,112,128},8)", hd_qk, hd_v);
   return IBM_E_UNSUPPORTED;
 }
 

@@ -401,10 +401,16 @@ extern "C" int ibm_attention_bwd_long(const void* q, int64_t ldq, const void* k,
   } else {
     IBM_CHECK_ARG(dbias_v == nullptr, "attention_bwd_long: dbias_v without dv");
     // the CoM blend of the TransformerBaseline (SimpleAttention, TransformerBaseline.py:51-70): the values are an input
-    if (hd_qk == 112 && hd_v == 8) IBM_BWD_LONG(112, 8, false);
+    if (hd_v == 8) {
+      if (hd_qk == 112) IBM_BWD_LONG(112, 8, false);
+      if (hd_qk == 64) IBM_BWD_LONG(64, 8, false);
+      if (hd_qk == 80) IBM_BWD_LONG(80, 8, false);
+      if (hd_qk == 96) IBM_BWD_LONG(96, 8, false);
+      if (hd_qk == 128) IBM_BWD_LONG(128, 8, false);
+    }
   }
 #undef IBM_BWD_LONG
-  set_error("attention_bwd_long: unsupported (hd_qk, hd_v, dv) = (%d, %d, %s); supported (64,64) (48,48) (32,32) with dv, (112,8) without",
+  set_error("attention_bwd_long: unsupported (hd_qk, hd_v, dv) = (%d, %d, %s); supported (64,64) (48,48) (32,32) with dv, ({64,80,96,112,128},8) without",
             hd_qk, hd_v, dv ? "yes" : "no");
   return IBM_E_UNSUPPORTED;
 }

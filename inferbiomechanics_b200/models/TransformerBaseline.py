@@ -9,7 +9,8 @@ comPos, comVel, comAcc`` (the three COM keys do not exist in the reference's ``I
 §0.3 — and are defined in ``inferbiomechanics_b200.keys``), learned temporal embedding concatenated,
 3 post-LN encoder layers, ``fc`` head, unscaled single-head "CoM blend" attention.
 
-B200 mapping: d = 108 is padded to 112 columns and each 36-wide head to 48 so every row is a
+B200 mapping: d (108 for the dataset's 23 DOF) is padded to a multiple of 16 columns (112) and each head (36-wide) to
+32 / 48 / 64 (48) so every row is a
 16-byte multiple (TMA-legal) and head slices are 16-byte aligned; the pads carry exact zeros (zero
 weight rows/columns), so results are those of the unpadded model.  GEMMs run in bf16 on tcgen05 with
 fp32 accumulation; the reference computes in fp64 — tolerance stated in tests/test_gpu_transformer.py.
@@ -119,9 +120,11 @@ class TransformerBaseline(nn.Module):
             return self._prep
         d, H, ff = self.timestep_vector_dim, self.num_heads, self.dim_feedforward
         hd = d // H
-        dp, hp, fp = ops.round_up(d, 8), _pad_head(hd), ops.round_up(ff, 8)
-        if dp != 112:
-            raise NotImplementedError(f"the CoM-blend attention kernel is built for d=108 (padded 112); got d={d}")
+        # rows are padded to a multiple of 16 columns: the CoM blend contracts over the whole row with m16n8k16 MMAs
+        dp, hp, fp = ops.round_up(d, 16), _pad_head(hd), ops.round_up(ff, 8)
+        if dp not in (64, 80, 96, 112, 128):
+            raise NotImplementedError(f"timestep vector width {d} (= 3*dofs + 9 + temporal_embedding_dim) pads to {dp}: the CoM-blend "
+                                      "attention kernels are instantiated for padded widths 64-128 (the dataset's 23 DOF give 112)")
 
         def padw(w, rows, cols):
             out = torch.zeros(rows, cols, dtype=BF16, device=dev)

@@ -243,3 +243,40 @@ def test_prepacked_bf16_stream_is_bit_identical():
     out = m(packed[2])
     out[O.CONTACT_FORCES].square().mean().backward()
     assert m.fc.weight.grad is not None and torch.isfinite(m.fc.weight.grad).all()
+
+
+@pytest.mark.parametrize("dofs,temb,heads,ff,layers,T", [(17, 14, 2, 40, 2, 33), (29, 30, 3, 60, 1, 120), (23, 6, 2, 24, 2, 64)])
+def test_transformer_other_constructor_arguments_vs_oracle(dofs, temb, heads, ff, layers, T):
+    """Constructor arguments other than the defaults (TransformerBaseline.py:79): d = 3*dofs + 9 + temporal_embedding_dim =
+    74 / 126 / 84 (padded 80 / 128 / 96), head widths 37 / 42 / 42 (padded 48): forward and every parameter gradient against
+    oracle/models.py::transformer_forward in fp64 (pinned at the default configuration by the reference golden)."""
+    from inferbiomechanics_b200.keys import InputDataKeys as K, OutputDataKeys as O
+    from inferbiomechanics_b200.models.TransformerBaseline import TransformerBaseline
+    from oracle import models as om
+    d = 3 * dofs + 9 + temb
+    if d % heads:
+        pytest.skip("embed dim not divisible by heads")
+    B = 3
+    m = TransformerBaseline(dofs, T, temporal_embedding_dim=temb, num_layers=layers, num_heads=heads, dim_feedforward=ff)
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 31 + dofs, dtype=torch.float64)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    x = {k: seeded_tensor((B, c, T), 500 + 7 * i, dtype=torch.float64)
+         for i, (k, c) in enumerate([(K.POS, dofs), (K.VEL, dofs), (K.ACC, dofs), (K.COM_POS, 3), (K.COM_VEL, 3), (K.COM_ACC, 3)])}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = om.transformer_forward(params, {k: v for k, v in x.items()}, layers, heads)
+    out = m(x)
+    loss, rloss = 0.0, 0.0
+    for i, (key, rk) in enumerate(((O.CONTACT, "contact"), (O.COM_ACC, "comAcc"), (O.CONTACT_FORCES, "contactForces"))):
+        err = (out[key].detach().cpu() - ref[rk].detach()).abs().max().item()
+        assert err <= (1e-1 if rk == "comAcc" else 4e-2) * ref[rk].detach().abs().max().item(), (key, err)
+        cot = seeded_tensor(tuple(out[key].shape), 900 + i, dtype=torch.float64)
+        loss = loss + (out[key] * cot.cuda()).sum()
+        rloss = rloss + (ref[rk] * cot).sum()
+    loss.backward()
+    rloss.backward()
+    for n, p in m.named_parameters():
+        if n == "com_attention.key_linear.bias":
+            continue                                        # identically zero in exact arithmetic (see the golden test)
+        e = _rel(p.grad, params[n].grad)
+        assert e <= 0.15, f"{n}: relative L2 {e:.4g}"
