@@ -254,6 +254,10 @@ int ibm_fold_pad_rows(void* G_bf16, int64_t ld, int64_t n_win, int32_t T, int32_
 /* Inverted dropout (nn.Dropout, Groundlink.py:53,59): y = x * keep/(1-p), keep from Philox4x32-10(seed, offset);
  * the backward pass calls it on dy with the same (seed, offset).  n % 4 == 0. */
 int ibm_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+/* Same mask generator with the Philox offset = offset + step_mul * *step_dev, the step read from device memory at execution
+ * time (graph-replayed training steps draw a fresh mask per replay; forward and backward of one step see the same value). */
+int ibm_dropout_bf16_dev(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset,
+                         const int64_t* step_dev, int64_t step_mul, void* stream);
 /* Conv1d weight (Cout,Cin,Kt) fp32 -> bf16 dgrad layout [Cin, Kt*cout_pad]: B[ci, j*cout_pad+co] = W[co,ci,Kt-1-j] */
 int ibm_conv_weight_to_dgrad(const float* w, int32_t cout, int32_t cin, int32_t kt, int32_t cout_pad,
                              void* dst_bf16, void* stream);
@@ -338,6 +342,13 @@ int ibm_attention_bwd_long(const void* q, int64_t ldq, const void* k, int64_t ld
 int ibm_optimizer_step(int32_t kind, float* param, const float* grad, float* state0, float* state1,
                        void* param_bf16, int64_t n, float lr, float grad_scale, int64_t step,
                        void* stream);
+/* Same step with the 1-based step count read from DEVICE memory (int64[1]) at execution time: a captured CUDA graph of the
+ * training step can be replayed although Adam / Adamax bias corrections change every step. */
+int ibm_optimizer_step_dev(int32_t kind, float* param, const float* grad, float* state0, float* state1,
+                           void* param_bf16, int64_t n, float lr, float grad_scale, const int64_t* step_dev,
+                           void* stream);
+/* *counter_dev += inc (one thread): the device-resident step counter of graph-replayed training steps. */
+int ibm_counter_add(int64_t* counter_dev, int64_t inc, void* stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "ibm_replicate_pad_rows": [P, _i64, _i64, _i32, _i32, _i32, P],
     "ibm_fold_pad_rows": [P, _i64, _i64, _i32, _i32, _i32, P],
     "ibm_dropout_bf16": [P, P, _i64, _f, _u64, _u64, P],
+    "ibm_dropout_bf16_dev": [P, P, _i64, _f, _u64, _u64, P, _i64, P],
     "ibm_conv_weight_to_dgrad": [P, _i32, _i32, _i32, _i32, P, P],
     "ibm_batchnorm_fwd": [P, _i64, P, _i64, _i64, _i32, P, P, P, P, P, P, _i32, _f, _f, P, P],
     "ibm_batchnorm_bwd": [P, _i64, P, _i64, P, _i64, _i64, _i32, P, P, P, _i32, _f, P, _i64, _i32, P, P, P, P, P],
@@ -60,6 +61,8 @@ SIGNATURES = {
     "ibm_expand_rows_bf16": [P, _i64, _i32, _i64, _i32, P, _i32, P, _i64, P, _i32, P],
     "ibm_attention_bwd_long": [P, _i64, P, _i64, P, _i64, P, _i64, P, _i64, P, _i64, P, _i64, P, _i64, _i64, _i32, _i32, _i32, _i32, _f,
                                P, P, P, P],
+    "ibm_optimizer_step_dev": [_i32, P, P, P, P, P, _i64, _f, _f, P, P],
+    "ibm_counter_add": [P, _i64, P],
     "ibm_optimizer_step": [_i32, P, P, P, P, P, _i64, _f, _f, _i64, P],
     "ibm_device_check": [_i32],
     "ibm_debug_gemm_max_clusters": [_i32],

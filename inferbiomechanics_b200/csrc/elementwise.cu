@@ -262,7 +262,9 @@ fold_pad_kernel(__nv_bfloat16* __restrict__ G, long long ld, long long n_win, in
 // scaled by 1/(1-p).  Forward and backward call the same kernel with the same (seed, offset), so the mask is never stored.
 __global__ void __launch_bounds__(kThreads)
 dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n, float p, float scale,
-               uint64_t seed, uint64_t offset) {
+               uint64_t seed, uint64_t offset, const long long* __restrict__ step_dev, long long step_mul) {
+  // device-resident step counter (CUDA-graph replays cannot change a by-value argument): offset += step_mul * *step_dev
+  if (step_dev != nullptr) offset += (uint64_t)(step_mul * __ldg(step_dev));
   const long long n4 = n >> 2;
   const uint32_t thresh = (uint32_t)(p * 4294967296.0);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -277,6 +279,8 @@ dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ 
     *reinterpret_cast<uint2*>(y + 4 * i) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(b.x, b.y));
   }
 }
+
+__global__ void counter_add_kernel(long long* ctr, long long inc) { *ctr += inc; }
 
 // Conv1d weight (Cout,Cin,Kt) fp32 → bf16 dgrad-GEMM layout [Cin, Kt*cout_pad]: B[ci, j'*cout_pad + co] = W[co, ci, Kt-1-j']
 __global__ void __launch_bounds__(kThreads)
@@ -319,7 +323,28 @@ extern "C" int ibm_dropout_bf16(const void* x, void* y, int64_t n, float p, uint
   IBM_CHECK_ARCH();
   IBM_CHECK_ARG(x && y && n > 0 && n % 4 == 0 && p >= 0.f && p < 1.f, "dropout: bad argument (n %% 4 == 0, 0 <= p < 1)");
   dropout_kernel<<<ew_grid(n / 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, p, 1.f / (1.f - p), seed, offset);
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, p, 1.f / (1.f - p), seed, offset, nullptr, 0);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+extern "C" int ibm_dropout_bf16_dev(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, const int64_t* step_dev,
+                                    int64_t step_mul, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(x && y && step_dev && n > 0 && n % 4 == 0 && p >= 0.f && p < 1.f, "dropout_dev: bad argument (n %% 4 == 0, 0 <= p < 1)");
+  dropout_kernel<<<ew_grid(n / 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, p, 1.f / (1.f - p), seed, offset,
+      reinterpret_cast<const long long*>(step_dev), (long long)step_mul);
+  IBM_LAUNCH_CHECK();
+  return IBM_OK;
+}
+
+extern "C" int ibm_counter_add(int64_t* counter_dev, int64_t inc, void* stream) {
+  using namespace ibm;
+  IBM_CHECK_ARCH();
+  IBM_CHECK_ARG(counter_dev != nullptr, "counter_add: null counter");
+  counter_add_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<long long*>(counter_dev), (long long)inc);
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }

@@ -14,6 +14,7 @@ constexpr int kThreads = 256;
 struct OptArgs {
   float lr, gscale;
   float bc1, bc2_sqrt;   // Adam / Adamax bias corrections for this step
+  const long long* step_dev;   // optional device-resident step count (CUDA-graph replays): the corrections are derived from it
 };
 
 template <int KIND>
@@ -47,6 +48,20 @@ template <int KIND>
 __global__ void __launch_bounds__(kThreads)
 optimizer_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ st0,
                  float* __restrict__ st1, __nv_bfloat16* __restrict__ pb, long long n, OptArgs a) {
+  if constexpr (KIND == 1 || KIND == 5) {
+    if (a.step_dev != nullptr) {
+      // one thread per block evaluates the two powers in double precision (as the host does for a by-value step)
+      __shared__ float s_bc[2];
+      if (threadIdx.x == 0) {
+        const double st = (double)__ldg(a.step_dev);
+        s_bc[0] = (float)(1.0 - pow(0.9, st));
+        s_bc[1] = (float)sqrt(1.0 - pow(0.999, st));
+      }
+      __syncthreads();
+      a.bc1 = s_bc[0];
+      a.bc2_sqrt = s_bc[1];
+    }
+  }
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   constexpr bool kS0 = KIND != 2, kS1 = (KIND == 1 || KIND == 4 || KIND == 5);
@@ -76,8 +91,25 @@ optimizer_kernel(float* __restrict__ param, const float* __restrict__ grad, floa
 
 }  // namespace ibm
 
+static int optimizer_step_impl(int32_t kind, float* param, const float* grad, float* state0, float* state1, void* param_bf16,
+                               int64_t n, float lr, float grad_scale, int64_t step, const int64_t* step_dev, void* stream);
+
 extern "C" int ibm_optimizer_step(int32_t kind, float* param, const float* grad, float* state0, float* state1,
                                   void* param_bf16, int64_t n, float lr, float grad_scale, int64_t step, void* stream) {
+  return optimizer_step_impl(kind, param, grad, state0, state1, param_bf16, n, lr, grad_scale, step, nullptr, stream);
+}
+
+extern "C" int ibm_optimizer_step_dev(int32_t kind, float* param, const float* grad, float* state0, float* state1,
+                                      void* param_bf16, int64_t n, float lr, float grad_scale, const int64_t* step_dev, void* stream) {
+  if (step_dev == nullptr) {
+    ibm::set_error("optimizer_step_dev: null step counter");
+    return IBM_E_ARG;
+  }
+  return optimizer_step_impl(kind, param, grad, state0, state1, param_bf16, n, lr, grad_scale, 1, step_dev, stream);
+}
+
+static int optimizer_step_impl(int32_t kind, float* param, const float* grad, float* state0, float* state1, void* param_bf16,
+                               int64_t n, float lr, float grad_scale, int64_t step, const int64_t* step_dev, void* stream) {
   using namespace ibm;
   IBM_CHECK_ARCH();
   IBM_CHECK_ARG(kind >= 0 && kind <= 5, "optimizer_step: unknown optimizer kind %d", kind);
@@ -92,6 +124,7 @@ extern "C" int ibm_optimizer_step(int32_t kind, float* param, const float* grad,
   a.gscale = grad_scale;
   a.bc1 = (float)(1.0 - pow(0.9, (double)step));
   a.bc2_sqrt = (float)sqrt(1.0 - pow(0.999, (double)step));
+  a.step_dev = reinterpret_cast<const long long*>(step_dev);
   long long need = ceil_div(n / 4 + 1, kThreads);
   long long cap = (long long)sm_count() * 16;
   const int grid = (int)(need < cap ? need : cap);

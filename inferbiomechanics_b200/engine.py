@@ -73,6 +73,7 @@ class FeedForwardEngine:
         self.dropout_p = float(dropout_p)
         self.step = 0                           # Philox offset base: one fresh mask per (training forward, layer)
         self.dropout_seed = self.DROPOUT_SEED   # Trainer.seed_rng folds its seed and the data-parallel rank in
+        self.step_dev = None                    # Trainer-owned device step counter: offsets are derived on the device (graph replay)
         if self.bn is not None:
             maxc = max(K for (_, _, _, K) in layers)
             self.bn_ws = ops.batchnorm_workspace(maxc, arena.device)
@@ -103,7 +104,10 @@ class FeedForwardEngine:
             last = i == n_layers - 1
             if drop:                                                    # nn.Dropout(p) on the layer input
                 xd = self.buf.tensor(s, f"xd{i}", tuple(x.shape), BF16)
-                ops.dropout(x, xd, self.dropout_p, self.dropout_seed, n_layers * self.step + i)
+                if self.step_dev is not None:
+                    ops.dropout(x, xd, self.dropout_p, self.dropout_seed, i, self.step_dev, n_layers)
+                else:
+                    ops.dropout(x, xd, self.dropout_p, self.dropout_seed, n_layers * self.step + i)
                 x = xd
             if self.bn is not None and self.bn[i] is not None:          # nn.BatchNorm1d(h0) on the (dropped) input
                 gname, bname, mod = self.bn[i]
@@ -159,7 +163,10 @@ class FeedForwardEngine:
                                       dx_colsum=arena.grad_of(self.layers[i - 1][1]) if i > 0 and not drop else None)
                     bias_done = i > 0 and not drop   # fp32 column sums of dx = bias gradient of layer i-1 (no mask in between)
                 if drop and i > 0:                                      # same Philox (seed, offset) as the forward mask
-                    ops.dropout(dx, dx, self.dropout_p, self.dropout_seed, n_layers * self.step + i)
+                    if self.step_dev is not None:
+                        ops.dropout(dx, dx, self.dropout_p, self.dropout_seed, i, self.step_dev, n_layers)
+                    else:
+                        ops.dropout(dx, dx, self.dropout_p, self.dropout_seed, n_layers * self.step + i)
                 dy = dx
             if self.bucket_hook is not None:
                 self.bucket_hook(i)               # layer i's gradients are complete

@@ -49,7 +49,15 @@ class GroundlinkEngine:
         self._w: Dict[str, torch.Tensor] = {}
         self.step = 0
         self.cnn_seed, self.fc_seed = self.CNN_DROPOUT_SEED, FC_DROPOUT_SEED     # Trainer.seed_rng folds seed and rank in
+        self.step_dev = None                    # Trainer-owned device step counter: offsets are derived on the device (graph replay)
         self.bucket_hook = None
+
+    def _drop(self, x, y, p, seed, mul, add, step):
+        """Philox offset = mul * step + add, the step taken from the device counter when the Trainer owns one."""
+        if self.step_dev is not None:
+            ops.dropout(x, y, p, seed, add, self.step_dev, mul)
+        else:
+            ops.dropout(x, y, p, seed, mul * step + add)
 
     # ---- weights in GEMM layouts (refreshed when the fp32 masters change) ---------------------------------
     def _weights(self) -> Dict[str, torch.Tensor]:
@@ -132,7 +140,7 @@ class GroundlinkEngine:
                 if xd_full is None:
                     xd_full = st[f"xd{i}_full"] = torch.zeros_like(st[f"x{i}_full"])
                     st[f"xd{i}"] = xd_full[slack:slack + Mp]
-                ops.dropout(st[f"x{i}_full"], xd_full, self.cnn_dropout, self.cnn_seed, 4 * self.step + i)
+                self._drop(st[f"x{i}_full"], xd_full, self.cnn_dropout, self.cnn_seed, 4, i, self.step)
                 ops.replicate_pad_rows(st[f"xd{i}"], B, T, PAD, self.ld[i])
                 x = st[f"xd{i}"]
             y_shift = y_full[slack + PAD: slack + PAD + Mp]             # the store lands 3 rows down: frame slots of layer i+1
@@ -144,7 +152,7 @@ class GroundlinkEngine:
         for j, pos in enumerate(self.fc_pos):                # Linear j reads the (dropped) output of layer j-1 / the CNN
             if drop:
                 ad = st["y4d"] if j == 0 else st[f"hd{j}"]
-                ops.dropout(a, ad, self.fc_dropout, self.fc_seed, depth * self.step + j)
+                self._drop(a, ad, self.fc_dropout, self.fc_seed, depth, j, self.step)
                 a = ad
             if j < depth - 1:
                 ops.gemm(a, A.shadow_of(f"fc.{pos}.weight", (C, C)), st[f"h{j + 1}"], Mp, C, C, bias=A.master_of(f"fc.{pos}.bias"), act="elu")
@@ -177,7 +185,7 @@ class GroundlinkEngine:
             dx = st["g4"] if j == 0 else st[f"dh{j}"]
             ops.gemm(dy, A.shadow_of(f"fc.{pos}.weight", (n_out, C)), dx, Mp, C, n_out, b_mn=True, act="elu", aux=pre, aux_mode=2)
             if drop:
-                ops.dropout(dx, dx, p, self.fc_seed, depth * s + j)
+                self._drop(dx, dx, p, self.fc_seed, depth, j, s)
             dy, n_out = dx, C
         if self.bucket_hook is not None:
             self.bucket_hook(4)
@@ -191,7 +199,7 @@ class GroundlinkEngine:
                 # adjoint of the dropout in front of conv i+1: the same Philox mask over the identically shaped buffer (the ELU
                 # derivative fused into the producing dgrad commutes with it, and with the fold because pads replicate x)
                 Gfull = st[f"g{i + 1}_full"]
-                ops.dropout(Gfull, Gfull, self.cnn_dropout, self.cnn_seed, 4 * s + i + 1)
+                self._drop(Gfull, Gfull, self.cnn_dropout, self.cnn_seed, 4, i + 1, s)
             ops.colsum(G, Mp, cout, g(f"cnn.{pos}.bias"))
             # wgrad: dW_j[co, ci] = sum_r G[r + 3, co] * Xp[r + j, ci]  (7 split-K MN-major GEMMs into GEMM-layout scratch)
             wg = self.buf.tensor(st, f"wg{i}", (cout, KT * self.cin_pad[i]), F32)

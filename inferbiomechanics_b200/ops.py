@@ -126,8 +126,16 @@ def fold_pad_rows(G, n_win, T, pad, cols):
     call("ibm_fold_pad_rows", _p(G), G.stride(0), n_win, T, pad, cols, stream_ptr())
 
 
-def dropout(x, y, p, seed, offset):
-    call("ibm_dropout_bf16", _p(x), _p(y), x.numel(), p, seed, offset, stream_ptr())
+def dropout(x, y, p, seed, offset, step_dev=None, step_mul=0):
+    """Philox offset = offset (+ step_mul * step_dev[0], read on the device at execution time, when a counter is given)."""
+    if step_dev is None:
+        call("ibm_dropout_bf16", _p(x), _p(y), x.numel(), p, seed, offset, stream_ptr())
+    else:
+        call("ibm_dropout_bf16_dev", _p(x), _p(y), x.numel(), p, seed, offset, _p(step_dev), step_mul, stream_ptr())
+
+
+def counter_add(counter_dev, inc=1):
+    call("ibm_counter_add", _p(counter_dev), inc, stream_ptr())
 
 
 def conv_weight_to_dgrad(w: torch.Tensor, dst: torch.Tensor, cout_pad: int):
@@ -312,6 +320,11 @@ def pack_labels(raw, nb, win_row0, contact_idx, mass, F, stride, last_only, out_
 
 
 # ---- optimizer ----------------------------------------------------------------------------------------
-def optimizer_step(kind: str, param, grad, state0, state1, param_bf16, lr, grad_scale, step):
+def optimizer_step(kind: str, param, grad, state0, state1, param_bf16, lr, grad_scale, step, step_dev=None):
+    """``step_dev`` (device int64[1]) replaces the by-value 1-based step count (graph-replayed steps)."""
+    if step_dev is not None:
+        call("ibm_optimizer_step_dev", _lib.OPT_KIND[kind], _p(param), _p(grad), _p(state0), _p(state1), _p(param_bf16), param.numel(),
+             lr, grad_scale, _p(step_dev), stream_ptr())
+        return
     call("ibm_optimizer_step", _lib.OPT_KIND[kind], _p(param), _p(grad), _p(state0), _p(state1), _p(param_bf16), param.numel(),
          lr, grad_scale, step, stream_ptr())

@@ -80,6 +80,12 @@ class Trainer:
         # DDP constructor semantics: everyone starts from rank 0's parameters (train.py:175)
         self.bucketer.broadcast_(self.arena.master)
         self.arena.sync_shadow(force=True)
+        # device-resident 1-based step counter: incremented by a one-thread kernel at the start of every step, read by the
+        # dropout kernels (Philox offset) and the optimizer kernel (Adam / Adamax bias correction), so that a captured step
+        # can be replayed although those values change from step to step
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        if hasattr(self.eng, "step_dev"):
+            self.eng.step_dev = self.step_dev
         self.seed_rng()
         self._lab: Dict[int, torch.Tensor] = {}
         self._gen = torch.Generator(device=dev).manual_seed(seed + 7919 * self.rank)
@@ -99,6 +105,7 @@ class Trainer:
                 setattr(eng, attr, (base ^ mix) + self.rank)
         if hasattr(eng, "step"):
             eng.step = self.step_count
+        self.step_dev.fill_(self.step_count)
 
     def _group_boundaries(self) -> List[int]:
         offs = self.arena.offsets
@@ -112,13 +119,15 @@ class Trainer:
 
     # ---- one optimisation step on windows idx of a store -------------------------------------------
     def _graphable(self) -> bool:
-        """The FeedForward step is ~25 short launches: at the reference's batch sizes the host, not the GPU, paces it, so
-        it is captured once per (store, batch size) and replayed.  Not captured: the denoiser (device-side RNG state and
-        host-side Philox offsets change per step, and its step is GPU-bound anyway), multi-rank runs (the NCCL side
-        stream), optimizers whose kernel takes the step count by value (adam/adamax bias correction), dropout (the mask
-        offset is a host-side argument)."""
-        return (self.use_graphs and not self.is_denoiser and not self.is_groundlink and self.world == 1 and self.opt_type not in ("adam", "adamax")
-                and getattr(self.eng, "dropout_p", 0.0) == 0.0)
+        """The FeedForward / Groundlink steps are 25-80 short launches: at the reference's batch sizes (32-64 windows,
+        train.py:52) the host, not the GPU, paces them, so a step is captured once per (store, batch size) and replayed —
+        with dropout and Adam/Adamax too, whose per-step values come from the device-resident step counter.  Not captured: the
+        denoiser (its step is GPU-bound and draws timesteps with a torch generator) and, by default, data-parallel runs:
+        capturing the side-stream NCCL allreduce (IBM_TRAIN_GRAPHS_DP=1) hung on the first 2-GPU attempt of round 2 and is
+        left as an experiment.  IBM_TRAIN_GRAPHS=0 switches replay off altogether."""
+        if not self.use_graphs or self.is_denoiser:
+            return False
+        return self.world == 1 or os.environ.get("IBM_TRAIN_GRAPHS_DP", "0") == "1"
 
     def train_step(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
         """Returns the device-resident fp32[40] result (loss at [0]); nothing is synchronised."""
@@ -144,11 +153,14 @@ class Trainer:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             try:
-                with torch.cuda.graph(graph):
+                # thread_local: the NCCL watchdog thread may query events while this thread captures
+                with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
                     self._train_step_eager(store, g[2])
             finally:
                 self._result_ring = ring
             self.step_count = count              # capture does not execute: the replay below is this step
+            if hasattr(self.eng, "step"):
+                self.eng.step = count
             g[1] = graph
         g[2].copy_(idx, non_blocking=True)
         g[1].replay()
@@ -161,8 +173,7 @@ class Trainer:
     def _train_step_eager(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
         B = idx.numel()
         lab = self._labels(store, idx)
-        self.arena.zero_grad()
-        self.bucketer.begin_step()
+        self._begin_step()
         if self.is_denoiser:
             store.pack_rows(idx, self.eng.xc(B, True), col0=30)
             return self._finish_denoiser_step(B, lab)
@@ -180,10 +191,15 @@ class Trainer:
             self._lab[B] = torch.empty(B, store.Fo, 30, dtype=torch.float32, device=self.arena.device)
         return store.labels(idx, self._lab[B])
 
+    def _begin_step(self) -> None:
+        self.arena.zero_grad()
+        self.bucketer.begin_step()
+        ops.counter_add(self.step_dev, 1)        # the step that starts now: value step_count + 1 on the device
+
     def optimizer_step(self) -> None:
         self.step_count += 1
         ops.optimizer_step(self.opt_type, self.arena.master, self.arena.grad, self.state0, self.state1, self.arena.shadow,
-                           self.lr, 1.0 / self.world, self.step_count)
+                           self.lr, 1.0 / self.world, self.step_count, step_dev=self.step_dev)
         self.arena.mark_shadow_fresh()
         if hasattr(self.eng, "weights_changed"):
             self.eng.weights_changed()           # engines that cache re-laid-out weights (Groundlink's conv GEMM layouts)
@@ -319,8 +335,7 @@ def _train_step_host(self, inputs, labels) -> float:
     lab = self._lab[("lab", B)]
     ops.pack_inputs([stage[k].view(B * Fo, -1) for k in LOSS_QUANTITIES], B * Fo, Fo, out_f32=lab.view(B * Fo, 30))
     srcs = [stage[k].view(B * F, -1) for k in MODEL_INPUT_ORDER]
-    self.arena.zero_grad()
-    self.bucketer.begin_step()
+    self._begin_step()
     self._pack_host_inputs(srcs, B, F)
     result = self._finish_step(B, F, lab)
     return float(result[0].item())
@@ -367,8 +382,7 @@ def _train_steps_host(self, batches):
         lab = self._lab[("lab", B)]
         ops.pack_inputs([stage[k].view(B * Fo, -1) for k in LOSS_QUANTITIES], B * Fo, Fo, out_f32=lab.view(B * Fo, 30))
         srcs = [stage[k].view(B * F, -1) for k in MODEL_INPUT_ORDER]
-        self.arena.zero_grad()
-        self.bucketer.begin_step()
+        self._begin_step()
         self._pack_host_inputs(srcs, B, F)
         consumed.record(main)                             # staging slot is free once both packers have run
         return self._finish_step(B, F, lab)

@@ -20,7 +20,7 @@ def _spawn(tmp_path, kind, opt, steps, B, world=2):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29731", WORKER, str(tmp_path), kind, opt, str(steps), str(B)]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr[-3000:]
     return [torch.load(os.path.join(tmp_path, f"rank{i}.pt")) for i in range(world)]
 
