@@ -192,9 +192,11 @@ int ibm_timestep_embed(const int32_t* t, int32_t t_is_scalar, int64_t B, int32_t
  * model, not once per denoise step. */
 int ibm_add_time_pos(void* h_bf16, int64_t ld, const void* temb_bf16, int64_t temb_ld,
                      const float* pos, int64_t M, int32_t F, int32_t d, const int32_t* t_row_dev, void* stream);
-/* backward of the above: dtemb[b,:] = sum_f dh[b,f,:] (bf16 out); dpos[f,:] += sum_b dh[b,f,:] (fp32 atomic) */
+/* backward of the above in ONE pass over dh: dtemb[b,:] = sum_f dh[b,f,:] (bf16 out); dpos[f,:] += sum_b dh[b,f,:] (fp32
+ * atomic); dbias (may be NULL): fp32 [d] += sum_{b,f} dh[b,f,:] — the bias gradient of the Linear that produced h (the
+ * denoiser's in-projection), which would otherwise be a second full read of dh. */
 int ibm_add_time_pos_bwd(const void* dh_bf16, int64_t ld, void* dtemb_bf16, int64_t temb_ld,
-                         float* dpos, int64_t M, int32_t F, int32_t d, void* stream);
+                         float* dpos, int64_t M, int32_t F, int32_t d, float* dbias, void* stream);
 
 /* ---- dense layers  (nn.Linear sites: FeedForward…py:73,113; Groundlink.py:51-62;
  *                     TransformerBaseline.py:12-18,91; nn.Conv1d: Groundlink.py:41) --------------- */

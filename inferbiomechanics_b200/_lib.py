@@ -36,7 +36,7 @@ SIGNATURES = {
     "ibm_ddpm_posterior_step": [P, _i64, P, P, P, P, P, P, _i64, P, P, _i64, _u64, _u64, P, P],
     "ibm_timestep_embed": [P, _i32, _i64, _i32, P, P],
     "ibm_add_time_pos": [P, _i64, P, _i64, P, _i64, _i32, _i32, P, P],
-    "ibm_add_time_pos_bwd": [P, _i64, P, _i64, P, _i64, _i32, _i32, P],
+    "ibm_add_time_pos_bwd": [P, _i64, P, _i64, P, _i64, _i32, _i32, P, P],
     "ibm_gemm_bf16": [P, _i64, _i32, P, _i64, _i32, _i64, _i64, _i64, P, _i32, P, _i64, _i32, P, _i64, _i32, _i32,
                       _i32, _i32, P, P, _i64, _i32, P],
     "ibm_colsum_bf16": [P, _i64, _i64, _i64, P, P],

@@ -189,6 +189,80 @@ add_time_pos_bwd_kernel(const __nv_bfloat16* __restrict__ dh, long long ld, __nv
   }
 }
 
+// One pass over dh for all three reductions of the stem's backward: dtemb[b] = sum_f dh[b, f] (bf16, per window), dpos[f] +=
+// sum_b dh[b, f] (fp32) and, optionally, dbias += sum_{b, f} dh[b, f] (the in-projection's bias gradient, which used to cost a
+// second full read of dh).  Block = kFusedW windows x 512 columns: thread (cc, fl) owns the 16-byte column chunk cc and the
+// frames fl, fl + 4, ...; every thread has up to K independent 16-byte loads in flight per window, dpos partial sums live in
+// registers over the block's windows and leave as vector atomics (8 KB x F per block instead of per window).
+constexpr int kFusedW = 16;
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+add_time_pos_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dh, long long ld, __nv_bfloat16* __restrict__ dtemb,
+                              long long temb_ld, float* __restrict__ dpos, float* __restrict__ dbias, long long B, int F, int d) {
+  const int cc = threadIdx.x & 63, fl = threadIdx.x >> 6;
+  const int col = (blockIdx.y * 64 + cc) * 8;
+  const bool active = col < d;
+  __shared__ float red[4][64][9];
+  float pacc[K][8], bacc[8];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pacc[k][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
+  const long long b0 = (long long)blockIdx.x * kFusedW;
+  for (int w = 0; w < kFusedW; ++w) {
+    const long long b = b0 + w;
+    if (b >= B) break;                                   // uniform across the block
+    float tacc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tacc[j] = 0.f;
+    uint4 u[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int f = fl + 4 * k;
+      u[k] = (active && f < F) ? ld_stream16(dh + (b * F + f) * ld + col) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float2 t;
+      t = unpack_bf16x2(u[k].x); pacc[k][0] += t.x; pacc[k][1] += t.y; tacc[0] += t.x; tacc[1] += t.y;
+      t = unpack_bf16x2(u[k].y); pacc[k][2] += t.x; pacc[k][3] += t.y; tacc[2] += t.x; tacc[3] += t.y;
+      t = unpack_bf16x2(u[k].z); pacc[k][4] += t.x; pacc[k][5] += t.y; tacc[4] += t.x; tacc[5] += t.y;
+      t = unpack_bf16x2(u[k].w); pacc[k][6] += t.x; pacc[k][7] += t.y; tacc[6] += t.x; tacc[7] += t.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[fl][cc][j] = tacc[j];
+    __syncthreads();
+    if (fl == 0 && active) {
+      float s8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s8[j] = red[0][cc][j] + red[1][cc][j] + red[2][cc][j] + red[3][cc][j];
+        bacc[j] += s8[j];
+      }
+      *reinterpret_cast<uint4*>(dtemb + b * temb_ld + col) =
+          make_uint4(pack_bf16x2(s8[0], s8[1]), pack_bf16x2(s8[2], s8[3]), pack_bf16x2(s8[4], s8[5]), pack_bf16x2(s8[6], s8[7]));
+    }
+    __syncthreads();
+  }
+  if (!active) return;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int f = fl + 4 * k;
+    if (f < F) {
+      float4* p = reinterpret_cast<float4*>(dpos + (long long)f * d + col);
+      atomicAdd(p, make_float4(pacc[k][0], pacc[k][1], pacc[k][2], pacc[k][3]));
+      atomicAdd(p + 1, make_float4(pacc[k][4], pacc[k][5], pacc[k][6], pacc[k][7]));
+    }
+  }
+  if (dbias != nullptr && fl == 0) {
+    float4* p = reinterpret_cast<float4*>(dbias + col);
+    atomicAdd(p, make_float4(bacc[0], bacc[1], bacc[2], bacc[3]));
+    atomicAdd(p + 1, make_float4(bacc[4], bacc[5], bacc[6], bacc[7]));
+  }
+}
+
 static int ew_grid(long long n_items) {
   long long need = ceil_div(n_items, kThreads);
   long long cap = (long long)sm_count() * 16;
@@ -263,15 +337,26 @@ extern "C" int ibm_add_time_pos(void* h_bf16, int64_t ld, const void* temb_bf16,
 }
 
 extern "C" int ibm_add_time_pos_bwd(const void* dh_bf16, int64_t ld, void* dtemb_bf16, int64_t temb_ld, float* dpos,
-                                    int64_t M, int32_t F, int32_t d, void* stream) {
+                                    int64_t M, int32_t F, int32_t d, float* dbias, void* stream) {
   using namespace ibm;
   IBM_CHECK_ARCH();
   IBM_CHECK_ARG(dh_bf16 && dtemb_bf16 && dpos && M > 0 && F > 0 && M % F == 0, "add_time_pos_bwd: bad argument");
-  IBM_CHECK_ARG(d % 64 == 0 && ld % 2 == 0 && temb_ld % 2 == 0, "add_time_pos_bwd: d must be a multiple of 64");
   const long long B = M / F;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto* dh = static_cast<const __nv_bfloat16*>(dh_bf16);
+  auto* dt = static_cast<__nv_bfloat16*>(dtemb_bf16);
+  if (d % 8 == 0 && ld % 8 == 0 && temb_ld % 8 == 0 && F <= 64 && aligned16(dh_bf16) && aligned16(dtemb_bf16) && aligned16(dpos) &&
+      (dbias == nullptr || aligned16(dbias))) {
+    dim3 grid((unsigned)ceil_div(B, kFusedW), (unsigned)ceil_div(d, 512));
+    if (F <= 52) add_time_pos_bwd_fused_kernel<13><<<grid, kThreads, 0, s>>>(dh, ld, dt, temb_ld, dpos, dbias, B, F, d);
+    else add_time_pos_bwd_fused_kernel<16><<<grid, kThreads, 0, s>>>(dh, ld, dt, temb_ld, dpos, dbias, B, F, d);
+    IBM_LAUNCH_CHECK();
+    return IBM_OK;
+  }
+  IBM_CHECK_ARG(dbias == nullptr, "add_time_pos_bwd: the bias-gradient output needs the fused path (d %% 8 == 0, F <= 64, 16-byte aligned rows)");
+  IBM_CHECK_ARG(d % 64 == 0 && ld % 2 == 0 && temb_ld % 2 == 0, "add_time_pos_bwd: d must be a multiple of 64");
   dim3 grid((unsigned)ceil_div(B, kTpWin), (unsigned)(d / 64));
-  add_time_pos_bwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dh_bf16), ld, static_cast<__nv_bfloat16*>(dtemb_bf16), temb_ld, dpos, B, F, d);
+  add_time_pos_bwd_kernel<<<grid, kThreads, 0, s>>>(dh, ld, dt, temb_ld, dpos, B, F, d);
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }

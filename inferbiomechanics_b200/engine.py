@@ -396,7 +396,8 @@ class DenoiserEngine:
                 self.bucket_hook(l)
         # dx = d loss / d h0
         dtemb, dact, dpre = (T(st, k, (B, d), BF16) for k in ("dtemb", "dact", "dpre"))
-        ops.add_time_pos_bwd(dx, dtemb, g("pos_embedding", (F, d)), M, F, d)
+        # one pass over dx: time-embedding gradient per window, positional-table gradient, in-projection bias gradient
+        ops.add_time_pos_bwd(dx, dtemb, g("pos_embedding", (F, d)), M, F, d, dbias=g("in_proj.bias"))
         ops.gemm(dtemb, st["tact"], g("time_mlp.2.weight", (d, d)), d, d, B, a_mn=True, b_mn=True, accumulate=True)
         ops.colsum(dtemb, B, d, g("time_mlp.2.bias"))
         ops.gemm(dtemb, A.shadow_of("time_mlp.2.weight", (d, d)), dact, B, d, d, b_mn=True)
@@ -404,6 +405,5 @@ class DenoiserEngine:
         ops.gemm(dpre, st["emb"], g("time_mlp.0.weight", (d, d)), d, d, B, a_mn=True, b_mn=True, accumulate=True)
         ops.colsum(dpre, B, d, g("time_mlp.0.bias"))
         _wgrad(A, "in_proj.weight", d, self.k_in, dx, self.xc(B), M, self.buf, st)
-        ops.colsum(dx, M, d, g("in_proj.bias"))
         if self.bucket_hook is not None:
             self.bucket_hook(-1)

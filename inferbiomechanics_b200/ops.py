@@ -291,8 +291,9 @@ def add_time_pos(h, temb, pos, M, F, d, t_row=None):
     call("ibm_add_time_pos", _p(h), h.stride(0), _p(temb), temb.stride(0), _p(pos), M, F, d, _p(t_row), stream_ptr())
 
 
-def add_time_pos_bwd(dh, dtemb, dpos, M, F, d):
-    call("ibm_add_time_pos_bwd", _p(dh), dh.stride(0), _p(dtemb), dtemb.stride(0), _p(dpos), M, F, d, stream_ptr())
+def add_time_pos_bwd(dh, dtemb, dpos, M, F, d, dbias=None):
+    """dbias (fp32 [d]): += the column sums of dh over all rows (bias gradient of the Linear that produced h), same pass."""
+    call("ibm_add_time_pos_bwd", _p(dh), dh.stride(0), _p(dtemb), dtemb.stride(0), _p(dpos), M, F, d, _p(dbias), stream_ptr())
 
 
 # ---- window batcher ---------------------------------------------------------------------------------

@@ -217,6 +217,18 @@ def test_timestep_embedding_and_time_pos():
     ops.add_time_pos_bwd(dh.cuda(), dtemb, dpos, B * F, F, d)
     torch.testing.assert_close(dpos.cpu(), dh.float().view(B, F, d).sum(0), rtol=1e-5, atol=1e-4)
     torch.testing.assert_close(dtemb.float().cpu(), dh.float().view(B, F, d).sum(1).to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
+    # the one-pass kernel over other shapes (ragged window groups, 50 / 60 frames, narrow and wide rows) with the bias-gradient
+    # output; accumulates into dpos / dbias
+    for B2, F2, d2 in ((37, 50, 512), (5, 60, 128), (130, 7, 1024), (16, 50, 72)):
+        dh2 = torch.randn(B2 * F2, d2, generator=g).to(torch.bfloat16)
+        dt2 = torch.empty(B2, d2, dtype=torch.bfloat16, device="cuda")
+        dp2 = torch.ones(F2, d2, device="cuda")
+        db2 = torch.full((d2,), 2.0, device="cuda")
+        ops.add_time_pos_bwd(dh2.cuda(), dt2, dp2, B2 * F2, F2, d2, dbias=db2)
+        v = dh2.float().view(B2, F2, d2)
+        torch.testing.assert_close(dp2.cpu(), 1.0 + v.sum(0), rtol=1e-5, atol=2e-4)
+        torch.testing.assert_close(db2.cpu(), 2.0 + v.sum((0, 1)), rtol=1e-5, atol=1e-3)
+        torch.testing.assert_close(dt2.float().cpu(), v.sum(1).to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
 
 
 # ---------------------------------------- LayerNorm ------------------------------------------------

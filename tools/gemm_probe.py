@@ -56,10 +56,27 @@ def run(name, iters=10):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     byts = (A.numel() + B.numel()) * 2 + out.numel() * out.element_size() + (aux.numel() * 2 if aux is not None else 0)
-    print(f"{name:18s} {m}x{n}x{k}  {ms * 1e3:8.1f} us  {2.0 * m * n * k / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:7.0f} GB/s (algorithmic)")
+    # the vendor library on the bare product (no bias / activation / residual / mask / column sums): what torch.matmul (cuBLASLt)
+    # needs for the same M x N x K with the same operand layouts — the library path would add elementwise kernels on top
+    lib = ""
+    if "--cublas" in sys.argv:
+        Af = A.t() if a_mn else A
+        Bf = B if b_mn else B.t()
+        ref = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+        for _ in range(3):
+            torch.matmul(Af, Bf, out=ref)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            torch.matmul(Af, Bf, out=ref)
+        e1.record()
+        torch.cuda.synchronize()
+        lms = e0.elapsed_time(e1) / iters
+        lib = f"   | cuBLAS bare bf16 product {lms * 1e3:8.1f} us {2.0 * m * n * k / lms / 1e9:8.1f} TFLOP/s"
+    print(f"{name:18s} {m}x{n}x{k}  {ms * 1e3:8.1f} us  {2.0 * m * n * k / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:7.0f} GB/s (algorithmic){lib}")
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES)
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(CASES)
     for nm in names:
-        run(nm, iters=3 if len(sys.argv) > 1 else 10)
+        run(nm, iters=10)
