@@ -55,6 +55,12 @@ int ibm_version(void);
 size_t ibm_last_error(char* buf, size_t cap);
 /* 0 iff `device` is compute capability 10.x */
 int ibm_device_check(int device);
+/* Walk order of the big row-streaming kernels (GEMM tiles, LayerNorm rows, attention windows).  0 = ascending (default,
+ * or IBM_WALK_ORDER unset); 1 = consecutive big launches alternate ascending / descending, so that a consumer starts on the
+ * rows its producer wrote last (still in L2); 2 = every launch alternates, whatever its size (tests).  Results do not depend
+ * on it (split-K sums are taken in a different order).  Process-wide host state: set it once, from the
+ * thread that launches (the reference drives one device from one Python thread per rank, src/cli/train.py:100-102). */
+int ibm_set_walk_order(int32_t mode);
 /* bytes of zero-initialised device scratch the reduction kernels need (loss, layernorm bwd) */
 size_t ibm_workspace_bytes(void);
 

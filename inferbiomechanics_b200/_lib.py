@@ -66,6 +66,7 @@ SIGNATURES = {
     "ibm_optimizer_step": [_i32, P, P, P, P, P, _i64, _f, _f, _i64, P],
     "ibm_device_check": [_i32],
     "ibm_debug_gemm_max_clusters": [_i32],
+    "ibm_set_walk_order": [_i32],
 }
 _SPECIAL = {
     "ibm_version": ([], c_int32),

@@ -264,7 +264,7 @@ template <int HD>
 __global__ void __launch_bounds__(kThreads, 4)
 attn_fwd_pipe_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
                      const __nv_bfloat16* __restrict__ v, int64_t ldv, __nv_bfloat16* __restrict__ o, int64_t ldo, int T,
-                     int H, int64_t n_win, float scale_log2) {
+                     int H, int64_t n_win, float scale_log2, int rev) {
   constexpr int LD = HD + kPad;
   constexpr int TILE = 64 * LD;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -274,7 +274,7 @@ attn_fwd_pipe_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __n
   for (int i = threadIdx.x; i < 2 * 3 * TILE / 8; i += kThreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   auto load_item = [&](int64_t win, int stage) {
-    const int64_t row0 = win * T;
+    const int64_t row0 = (rev ? n_win - 1 - win : win) * T;       // rev: windows from the last one down (ibm_set_walk_order)
     __nv_bfloat16* Qs = base + stage * 3 * TILE;
     load_tile_async<HD, LD>(Qs, q + row0 * ldq + h * HD, ldq, T);
     load_tile_async<HD, LD>(Qs + TILE, k + row0 * ldk + h * HD, ldk, T);
@@ -323,7 +323,7 @@ attn_fwd_pipe_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __n
       if (r0 + 8 < T) *reinterpret_cast<uint32_t*>(Qs + (r0 + 8) * LD + j * 8 + 2 * t) = pack_bf16x2(oacc[j][2] * inv1, oacc[j][3] * inv1);
     }
     __syncwarp();
-    store_rows16<HD, LD>(Qs, o + win * T * ldo + h * HD, ldo, warp * 16, T, lane);
+    store_rows16<HD, LD>(Qs, o + (rev ? n_win - 1 - win : win) * T * ldo + h * HD, ldo, warp * 16, T, lane);
     __syncthreads();                                 // stage st is free for the load issued next iteration
   }
 }
@@ -730,7 +730,7 @@ static int launch_fwd_pipe(const void* q, int64_t ldq, const void* k, int64_t ld
   if (rc) return rc;
   kern<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
                                     static_cast<const __nv_bfloat16*>(v), ldv, static_cast<__nv_bfloat16*>(o), ldo, T, H, n_win,
-                                    scale * 1.4426950408889634f);
+                                    scale * 1.4426950408889634f, next_walk_reverse(n_win * T * (int64_t)H * HD * 2 * 4));
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }

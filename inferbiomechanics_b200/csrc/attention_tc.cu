@@ -94,7 +94,7 @@ __device__ __forceinline__ void add_bf16x8(float (&a)[8], uint4 u) {
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmDQKV, int T, int H, int64_t n_win, int64_t kv_off, float scale,
-                   float* __restrict__ dbias) {
+                   float* __restrict__ dbias, int rev) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // stage st: Q | K | dO at smem + st * 3 * kTile
@@ -122,6 +122,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   const int64_t cta = blockIdx.x / H, ctas = gridDim.x / H;
   const int64_t n_pairs = (n_win + 1) >> 1;
   const int n_it = cta < n_pairs ? (int)((n_pairs - cta + ctas - 1) / ctas) : 0;      // pairs of this CTA
+  // i-th pair of this CTA; rev: pairs are taken from the last one down (ibm_set_walk_order)
+  const int64_t pair0 = rev ? n_pairs - 1 - cta : cta, pair_step = rev ? -ctas : ctas;
+  auto pair_of = [&](int i) -> int64_t { return pair0 + (int64_t)i * pair_step; };
 
   // zero everything once: pad rows (>= T of each 64-row half) of the operand tiles stay zero for the whole kernel, and
   // so do the cross-window blocks of P and dS (only the diagonal blocks are ever written)
@@ -156,7 +159,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     if (lane == 0 && n_it > 0) {
       const uint32_t tx_qkd = 6u * (uint32_t)T * 128u, tx_v = 2u * (uint32_t)T * 128u;
       auto window_row = [&](int i, int it) {
-        int64_t w = 2 * (cta + (int64_t)i * ctas) + it;
+        int64_t w = 2 * pair_of(i) + it;
         if (w >= n_win) w = n_win - 1;                // odd tail: a valid window again, its results are not stored
         return (int32_t)(w * T);
       };
@@ -302,7 +305,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           mbar_wait(stg_bar, (uint32_t)(i & 1));
 #pragma unroll
           for (int it = 0; it < 2; ++it) {
-            const int64_t w = 2 * (cta + (int64_t)i * ctas) + it;
+            const int64_t w = 2 * pair_of(i) + it;
             if (w >= n_win) break;
             const int32_t row0 = (int32_t)(w * T);
             tma_store_2d(&tmDQKV, Gq + it * 64 * 128, h * HD, row0);
@@ -345,7 +348,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       if (i > 0) mbar_wait(sf_bar, (uint32_t)((i - 1) & 1));           // the previous pair's stores have read the staging tiles
       // odd tail: the second window of the last pair is a duplicate — its rows are staged as zeros (they are not stored,
       // and must not enter the bias gradient)
-      const bool dup = own == 1 && 2 * (cta + (int64_t)i * ctas) + 1 >= n_win;
+      const bool dup = own == 1 && 2 * pair_of(i) + 1 >= n_win;
       if (ri < T) {
         const uint32_t ro = r * 128;
 #pragma unroll
@@ -773,7 +776,8 @@ int attention_bwd_tc(const void* qkv, int64_t ld, int64_t kv_off, const void* d_
   int64_t grid = (int64_t)sm_count() / H * H;
   if (grid < H) grid = H;
   if (grid > n_pairs * H) grid = n_pairs * H;
-  attn_bwd_tc_kernel<<<(unsigned)grid, kThreads, kSmem, s>>>(mq, md, mg, T, H, n_win, kv_off, scale, dbias);
+  attn_bwd_tc_kernel<<<(unsigned)grid, kThreads, kSmem, s>>>(mq, md, mg, T, H, n_win, kv_off, scale, dbias,
+                                                             next_walk_reverse(n_win * T * (int64_t)H * HD * 2 * 7));
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }

@@ -13,6 +13,9 @@ namespace ibm {
 void set_error(const char* fmt, ...);
 int check_arch();                       // IBM_OK iff current device is sm_100
 int sm_count();
+// 1 if the launch being prepared should walk its rows / tiles in DESCENDING order (see ibm_set_walk_order); launches
+// streaming less than 48 MB neither alternate nor count
+int next_walk_reverse(int64_t bytes_streamed);
 
 #define IBM_CHECK_ARG(cond, ...)                       \
   do {                                                 \

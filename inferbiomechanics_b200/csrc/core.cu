@@ -1,5 +1,6 @@
 // Library plumbing: error buffer, architecture gate, workspace size.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -48,11 +49,38 @@ int sm_count() {
   return g_sms[dev] > 0 ? g_sms[dev] : 148;
 }
 
+// ---- walk order of the big row-streaming kernels (ibm_set_walk_order) --------------------------------------------
+// mode 0: every kernel walks its rows / tiles in ascending order.  mode 1 ("zigzag"): big launches alternate between
+// ascending and descending, so a kernel starts on the rows its producer wrote LAST — the part of the producer's output that
+// is still in the 126 MB L2 — instead of on rows that were evicted hundreds of megabytes ago.  mode 2: every launch
+// alternates, whatever its size (parity tests of the descending paths on small shapes).
+static int g_walk_mode = -1;
+static unsigned g_walk_count = 0;
+
+int next_walk_reverse(int64_t bytes_streamed) {
+  if (g_walk_mode < 0) {
+    const char* e = getenv("IBM_WALK_ORDER");
+    g_walk_mode = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  }
+  if (g_walk_mode == 0 || (g_walk_mode == 1 && bytes_streamed < (int64_t)(48ll << 20))) return 0;
+  return (int)(g_walk_count++ & 1u);
+}
+
 }  // namespace ibm
 
 extern "C" {
 
 int ibm_version(void) { return 100; }
+
+int ibm_set_walk_order(int32_t mode) {
+  if (mode < 0 || mode > 2) {
+    ibm::set_error("ibm_set_walk_order: mode must be 0 (ascending), 1 (big launches alternate) or 2 (all launches alternate), got %d", mode);
+    return IBM_E_ARG;
+  }
+  ibm::g_walk_mode = mode;
+  ibm::g_walk_count = 0;
+  return IBM_OK;
+}
 
 size_t ibm_last_error(char* buf, size_t cap) {
   size_t n = strlen(ibm::g_err);

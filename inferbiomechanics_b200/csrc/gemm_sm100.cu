@@ -96,6 +96,7 @@ struct Args {
   uint8_t* mask;           // optional sign bitmask [M][ldmask bytes], bit (c & 7) of byte c >> 3 <-> column c
   int64_t ldmask;
   int32_t mask_mode;       // 1: write (output > 0) after the activation; 2: zero the outputs whose bit is clear
+  int32_t reverse;         // work items are taken from the last one down (ibm_set_walk_order); never with A-stationary
 };
 
 __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int nstages) {
@@ -174,7 +175,10 @@ __device__ __forceinline__ void epi_dispatch_aux(float (&v)[PT], uint32_t xrow, 
   }
 }
 
-template <int BN, bool kOutF32, bool kAccum, bool kAux, int CG, int NT, bool kAS>
+// MM: the sign-bitmask mode as a compile-time constant (0 none, 1 write, 2 gate) for the hot bf16 shapes, so that the
+// plain epilogue does not carry the registers of the two mask paths (ptxas: every runtime-mask variant sits at the
+// 168-register cap with spills); -1 = read args.mask_mode at run time.
+template <int BN, bool kOutF32, bool kAccum, bool kAux, int CG, int NT, bool kAS, int MM = -1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const Args args) {
@@ -200,6 +204,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + kASlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mask_mode = MM >= 0 ? MM : args.mask_mode;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -235,6 +240,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int n_tiles = args.tiles_m * args.tiles_n;                       // tiles_m counts CG*128-row blocks
   const int total_work = n_tiles * args.splits;
   constexpr int BN_LOAD = BN / CG;
+  // position in the worker's round-robin sequence -> work item: descending when args.reverse (the consumer of a tensor
+  // then starts on the rows its producer wrote last, which are still in L2)
+  auto item_of = [&](int w) { return args.reverse ? total_work - 1 - w : w; };
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
@@ -281,8 +289,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else
       for (int w = worker; w < total_work; w += n_workers) {
-        const int split = w / n_tiles;
-        const int tile = w - split * n_tiles;
+        const int split = item_of(w) / n_tiles;
+        const int tile = item_of(w) - split * n_tiles;
         const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
         const int m0 = (tm * CG + rank) * BLOCK_M, n0 = tn * NT * BN;
         const int nb0 = n0 + rank * BN_LOAD;                      // first B row this CTA loads (per column tile: + t*BN)
@@ -364,7 +372,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else
       for (int w = worker; w < total_work; w += n_workers) {
-        const int split = w / n_tiles;
+        const int split = item_of(w) / n_tiles;
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
         // NT == 1: accumulator `as` (the other one is being drained).  NT == 2: both accumulators, one per column tile.
@@ -422,7 +430,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int xg = 0;                                     // chunks consumed so far by this warp (aux ring position)
     int pw = worker, pts = 0, pch = half;           // prefetch cursor: (work item, column tile, chunk) of this warp's next aux load
     auto chunks_of = [&](int w, int ts) {
-      const int n0w = (((w % n_tiles) % args.tiles_n) * NT + ts) * BN;
+      const int n0w = (((item_of(w) % n_tiles) % args.tiles_n) * NT + ts) * BN;
       return ((int)max((int64_t)0, min((int64_t)BN, args.N - n0w)) + CW - 1) / CW;
     };
     auto issue_aux = [&](int buf) {                 // lane 0 only
@@ -431,7 +439,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++pts == NT) { pts = 0; pw += n_workers; }
       }
       if (pw >= total_work) return;
-      const int t2 = pw % n_tiles;
+      const int t2 = item_of(pw) % n_tiles;
       mbar_arrive_expect_tx(&my_aux_bar[buf], kWarpStage);
       tma_load_2d(my_aux + buf * kWarpStage, &tmX, &my_aux_bar[buf], ((t2 % args.tiles_n) * NT + pts) * BN + pch * CW,
                   ((t2 / args.tiles_n) * CG + rank) * BLOCK_M + q * 32);
@@ -456,7 +464,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int w0 = kAS ? worker * args.tiles_n : worker; w0 < total_work; w0 += w_step0)
     for (int wi = w0; wi < w0 + w_inner; ++wi)
     for (int tsub = 0; tsub < NT; ++tsub) {           // column tile inside the supertile: accumulator `as` == tsub when NT == 2
-      const int w = kAS ? w0 + (wi - w0 + worker) % args.tiles_n : wi;      // A-stationary: rotated column order (see producer)
+      const int w = kAS ? w0 + (wi - w0 + worker) % args.tiles_n : item_of(wi);      // A-stationary: rotated column order (see producer)
       const int tile = w % n_tiles;
       const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
       const int m0 = (tm * CG + rank) * BLOCK_M + q * 32, n0 = (tn * NT + tsub) * BN;       // this warp's first row
@@ -467,7 +475,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // so that the (uncoalesced, tiny) loads fly under the main loop
       uint2 mbits[(BN / CW + 1) / 2];
       if constexpr (!kOutF32 && !kAux) {
-        if (args.mask_mode == 2) {
+        if (mask_mode == 2) {
           const int64_t row = (int64_t)m0 + lane;
 #pragma unroll
           for (int i = 0; i < (BN / CW + 1) / 2; ++i) {
@@ -544,7 +552,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             epi_dispatch_plain<PT>(v, args.act);
             if constexpr (!kOutF32) {
-              if (args.mask_mode == 1) {
+              if (mask_mode == 1) {
                 // the sign pattern of the (post-activation) outputs: what the dgrad of this layer needs instead of the
                 // whole activation matrix (1 bit instead of 16 per element)
                 // outputs are >= 0 here (ReLU): x > 0  <=>  the sign bit of -bits(x) is set; a funnel shift pushes that
@@ -557,7 +565,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 const int64_t row = (int64_t)m0 + lane;
                 if (row < args.M && c0 + PT <= args.N) *reinterpret_cast<uint2*>(args.mask + row * args.ldmask + (c0 >> 3)) = make_uint2(lo, hi);
-              } else if (args.mask_mode == 2) {
+              } else if (mask_mode == 2) {
                 const uint2 mb = mbits[(ch - half) >> 1];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -642,11 +650,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // ------------------------------------------- host side -------------------------------------------
 
-template <int BN, bool F32, bool ACC, bool AUX, int CG, int NT = 1, bool AS = false>
+template <int BN, bool F32, bool ACC, bool AUX, int CG, int NT = 1, bool AS = false, int MM = -1>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& x, const Args& args, int grid,
                   cudaStream_t s) {
   static bool attr_set = false;     // per instantiation
-  auto kern = gemm_kernel<BN, F32, ACC, AUX, CG, NT, AS>;
+  auto kern = gemm_kernel<BN, F32, ACC, AUX, CG, NT, AS, MM>;
   if (!attr_set) {
     IBM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, AUX, CG, NT, AS>::kSmem));
     attr_set = true;
@@ -815,6 +823,7 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   args.mask = static_cast<uint8_t*>(mask);
   args.ldmask = ldmask;
   args.mask_mode = mask_mode;
+  args.reverse = 0;
   // With taps the B operand is [N, taps * kb_per_tap * 64] (each tap's K padded to whole k blocks).
   const int64_t Kb = taps == 1 ? K : (int64_t)args.kb_total * BLOCK_K;
 
@@ -848,6 +857,11 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
     const char* e = getenv("IBM_GEMM_AS");
     as_on = (e && e[0] == '1') ? 1 : 0;
   }
+  const bool use_as = as_on && cg == 2 && bn == 256 && nt == 1 && aux_mode == 0 && !accumulate && taps == 1 && args.kb_total <= kASlots &&
+      args.tiles_n >= 2 && args.tiles_m >= 2 * workers;
+  // bytes this launch streams: both operands once plus the output (the walk order only matters, and only alternates, for
+  // launches that cannot live in L2)
+  if (!use_as) args.reverse = next_walk_reverse((M * K + N * K) * 2 + M * N * (f32 ? 4 : 2));
   if (as_on && cg == 2 && bn == 256 && nt == 1 && aux_mode == 0 && !accumulate && taps == 1 && args.kb_total <= kASlots &&
       args.tiles_n >= 2 && args.tiles_m >= 2 * workers) {
     grid = workers * cg;
@@ -868,6 +882,11 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
     return launch<256, false, false, false, 2, 2>(ta, tb, td, tx, args, grid, s);
   }
   if (cg == 2) {
+    if (bn == 256 && !accumulate && !f32 && aux_mode == 0) {      // the hot bf16 shapes: mask mode compiled in
+      if (mask_mode == 0) return launch<256, false, false, false, 2, 1, false, 0>(ta, tb, td, tx, args, grid, s);
+      if (mask_mode == 1) return launch<256, false, false, false, 2, 1, false, 1>(ta, tb, td, tx, args, grid, s);
+      return launch<256, false, false, false, 2, 1, false, 2>(ta, tb, td, tx, args, grid, s);
+    }
     if (bn == 256) IBM_GEMM_DISPATCH(256, 2);
     IBM_GEMM_DISPATCH(128, 2);
   }

@@ -44,7 +44,7 @@ template <int CH, int R, bool FULL>
 __global__ void __launch_bounds__(kThreads)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ y, long long ld,
                      const float* __restrict__ gamma, const float* __restrict__ beta, long long M, int d, float eps,
-                     float* __restrict__ mean, float* __restrict__ rstd) {
+                     float* __restrict__ mean, float* __restrict__ rstd, int rev) {
   extern __shared__ __align__(128) uint8_t smem_ln[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t row_bytes = (uint32_t)ld * 2u;
@@ -66,8 +66,9 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
 
   const long long n_groups = (M + R - 1) / R;
   const long long gw = (long long)blockIdx.x * kWarps + wid, gstride = (long long)gridDim.x * kWarps;
+  // rev: the grid walks the row groups from the last one down (ibm_set_walk_order)
   auto issue = [&](long long grp, int st) {        // lane 0
-    const long long m0 = grp * R;
+    const long long m0 = (rev ? n_groups - 1 - grp : grp) * R;
     const uint32_t bytes = (uint32_t)((M - m0 < R ? M - m0 : R)) * row_bytes;
     mbar_arrive_expect_tx(&bars[st], bytes);
     bulk_load(ring + (size_t)st * group_bytes, s + m0 * ld, bytes, &bars[st]);
@@ -84,7 +85,7 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
     const uint8_t* tile = ring + (size_t)st * group_bytes;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const long long m = grp * R + r;
+      const long long m = (rev ? n_groups - 1 - grp : grp) * R + r;
       if (m >= M) break;
       float v[CH][8];
       float sum = 0.f;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, CH <= 2 ? 2 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ s, long long ld,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      long long M, int d, __nv_bfloat16* __restrict__ ds, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, float* __restrict__ dcolsum) {
+                     float* __restrict__ dbeta, float* __restrict__ dcolsum, int rev) {
   extern __shared__ __align__(128) uint8_t smem_ln[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t row_bytes = (uint32_t)ld * 2u;
@@ -257,7 +258,9 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   __syncthreads();
 
   const long long gw = (long long)blockIdx.x * kWarps + wid, gstride = (long long)gridDim.x * kWarps;
-  auto issue = [&](long long m, int st) {           // lane 0
+  auto phys = [&](long long m) { return rev ? M - 1 - m : m; };      // rev: rows are visited from the last one down
+  auto issue = [&](long long mv, int st) {          // lane 0
+    const long long m = phys(mv);
     mbar_arrive_expect_tx(&bars[st], 2 * row_bytes);
     uint8_t* dst = ring + (size_t)st * 2 * row_bytes;
     bulk_load(dst, dy + m * ld, row_bytes, &bars[st]);
@@ -274,11 +277,11 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 #pragma unroll
     for (int j = 0; j < 8; ++j) ag[k][j] = ab[k][j] = ac[k][j] = 0.f;
   int it = 0;
-  float mu_n = gw < M ? __ldg(mean + gw) : 0.f, rs_n = gw < M ? __ldg(rstd + gw) : 0.f;
+  float mu_n = gw < M ? __ldg(mean + phys(gw)) : 0.f, rs_n = gw < M ? __ldg(rstd + phys(gw)) : 0.f;
   for (long long m = gw; m < M; m += gstride, ++it) {
     const int st = it % kStages;
     const float mu = mu_n, rs = rs_n;
-    if (m + gstride < M) { mu_n = __ldg(mean + m + gstride); rs_n = __ldg(rstd + m + gstride); }   // next row's statistics
+    if (m + gstride < M) { mu_n = __ldg(mean + phys(m + gstride)); rs_n = __ldg(rstd + phys(m + gstride)); }   // next row's statistics
     mbar_wait(&bars[st], (uint32_t)((it / kStages) & 1));
     const uint8_t* tile = ring + (size_t)st * 2 * row_bytes;
     float xh[CH][8], g[CH][8];
@@ -321,8 +324,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
           o[j] = (FULL || c + j < d) ? rs * (g[k][j] - s1 - xh[k][j] * s2) : 0.f;
           ac[k][j] += o[j];
         }
-        st_stream16(ds + m * ld + c, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+        st_stream16(ds + phys(m) * ld + c, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                      pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
       }
     }
   }
@@ -376,7 +379,7 @@ static int launch_ln_fwd(const __nv_bfloat16* sp, __nv_bfloat16* yp, int64_t ld,
   int grid = 0;
   int rc = ln_grid(kern, smem, ceil_div(M, R), &grid);
   if (rc) return rc;
-  kern<<<grid, kThreads, smem, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd);
+  kern<<<grid, kThreads, smem, st>>>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd, next_walk_reverse(2 * M * ld * 2));
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }
@@ -414,7 +417,8 @@ static int launch_ln_bwd(const __nv_bfloat16* dyp, const __nv_bfloat16* sp, int6
   int grid = 0;
   int rc = ln_grid(kern, smem, M, &grid);
   if (rc) return rc;
-  kern<<<grid, kThreads, smem, st>>>(dyp, sp, ld, gamma, mean, rstd, M, d, dsp, dgamma, dbeta, dcolsum);
+  kern<<<grid, kThreads, smem, st>>>(dyp, sp, ld, gamma, mean, rstd, M, d, dsp, dgamma, dbeta, dcolsum,
+                                     next_walk_reverse(3 * M * ld * 2));
   IBM_LAUNCH_CHECK();
   return IBM_OK;
 }

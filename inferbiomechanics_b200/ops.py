@@ -83,6 +83,12 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
     return out
 
 
+def set_walk_order(mode: int) -> None:
+    """0: kernels walk rows / tiles in ascending order; 1: big launches (>= 48 MB streamed) alternate ascending /
+    descending so a consumer starts on what its producer wrote last (still in L2); 2: every launch alternates (tests)."""
+    call("ibm_set_walk_order", int(mode))
+
+
 def colsum(X: torch.Tensor, M: int, N: int, out: torch.Tensor, ld=None) -> None:
     call("ibm_colsum_bf16", _p(X), X.stride(0) if ld is None else ld, M, N, _p(out), stream_ptr())
 

@@ -75,9 +75,21 @@ def make_buckets(boundaries: Sequence[int], total: int, bucket_elems: int) -> Li
 
 
 class GradBucketer:
-    """Fires one allreduce(SUM) per bucket of the flat gradient tensor, optionally on a side stream."""
+    """Fires one allreduce(SUM) per bucket of the flat gradient tensor, optionally on a side stream.
 
-    def __init__(self, flat_grad: torch.Tensor, buckets: Sequence[Tuple[int, int, int]], group=None):
+    Two schedules (``mode``, default from IBM_ALLREDUCE):
+      * ``"overlap"`` — a bucket's allreduce goes to a side stream as soon as backward has finished its last layer group
+        (what DistributedDataParallel's hooks do, train.py:175,281);
+      * ``"tail"`` — nothing is enqueued during backward; ``finish()`` issues ONE allreduce of the whole arena on the compute
+        stream.  The collective is exposed (the arena crosses NVSwitch once, a few hundred microseconds for 100 MB) but no
+        NCCL CTA ever shares the machine with the persistent GEMMs, whose statically assigned CTA pairs lose whole rounds
+        when a co-resident kernel holds one of their SMs; and a step holds exactly one collective on one stream, which is
+        the shape a CUDA graph of the small-batch steps captures."""
+
+    def __init__(self, flat_grad: torch.Tensor, buckets: Sequence[Tuple[int, int, int]], group=None, mode: Optional[str] = None):
+        self.mode = mode or os.environ.get("IBM_ALLREDUCE", "overlap")
+        if self.mode not in ("overlap", "tail"):
+            raise ValueError(f"IBM_ALLREDUCE / mode must be 'overlap' or 'tail', got {self.mode!r}")
         self.flat = flat_grad
         self.buckets = list(buckets)
         self.group = group
@@ -86,12 +98,17 @@ class GradBucketer:
         self.comm_stream = torch.cuda.Stream(device=flat_grad.device) if self.cuda else None
         self._fired = 0
         self.collectives = 0
+        # tail mode only: called INSTEAD of the collective (the trainer's graph capture ends one CUDA graph and begins the
+        # next here, and issues the allreduce itself between the two replays)
+        self.finish_hook: Optional[Callable[[], None]] = None
 
     def begin_step(self) -> None:
         self._fired = 0
 
     def group_done(self, group_index: int) -> None:
         """Call when backward has produced all gradients of layer group ``group_index`` (and all later ones)."""
+        if self.mode == "tail":
+            return
         while self._fired < len(self.buckets) and self.buckets[self._fired][2] >= group_index:
             self._launch(self.buckets[self._fired])
             self._fired += 1
@@ -112,9 +129,21 @@ class GradBucketer:
 
     def finish(self) -> None:
         """Flush remaining buckets and make the compute stream wait for the collectives."""
+        if self.mode == "tail":
+            if self.finish_hook is not None:
+                self.finish_hook()
+            else:
+                self.allreduce_all()
+            return
         self.group_done(-1)
         if self.cuda and self.world > 1:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def allreduce_all(self) -> None:
+        """One allreduce(SUM) of the whole arena on the current stream."""
+        if self.world > 1:
+            self.collectives += 1
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
 
     def broadcast_(self, flat_param: torch.Tensor, src: int = 0) -> None:
         if self.world > 1:

@@ -70,7 +70,13 @@ class Trainer:
         # layer groups for the bucketed allreduce
         bounds = self._group_boundaries()
         bucket_mb = float(os.environ.get("IBM_BUCKET_MB", bucket_mb))      # experiments: bucket size of the gradient allreduce
-        self.bucketer = parallel.GradBucketer(self.arena.grad, parallel.make_buckets(bounds, n, int(bucket_mb * (1 << 20) / 4)))
+        # FeedForward / Groundlink gradients are a few MB: one allreduce of the whole arena after backward ("tail") costs less
+        # than a bucket per layer group (0.46 vs 0.51 ms per B = 32 step on 2 GPUs) and leaves one point in the step where a
+        # captured step is cut in two (see _train_step_graphed).  The denoiser keeps the overlapped buckets unless IBM_ALLREDUCE says otherwise.
+        self.use_graphs = os.environ.get("IBM_TRAIN_GRAPHS", "1") != "0"
+        self.dp_graphs = self.use_graphs and not self.is_denoiser and os.environ.get("IBM_TRAIN_GRAPHS_DP", "1") != "0"
+        self.bucketer = parallel.GradBucketer(self.arena.grad, parallel.make_buckets(bounds, n, int(bucket_mb * (1 << 20) / 4)),
+                                              mode=None if self.is_denoiser else os.environ.get("IBM_ALLREDUCE", "tail"))
         if self.is_denoiser:
             self.eng.bucket_hook = lambda l: self.bucketer.group_done(l + 1)      # group 0 = stem, l+1 = layer l, L+1 = head
         elif self.is_groundlink:
@@ -91,7 +97,6 @@ class Trainer:
         self._gen = torch.Generator(device=dev).manual_seed(seed + 7919 * self.rank)
         # CUDA-graph replay of the (launch-bound) FeedForward step: key -> [eager steps seen, graph, static idx, static result]
         self._graphs: Dict[tuple, list] = {}
-        self.use_graphs = os.environ.get("IBM_TRAIN_GRAPHS", "1") != "0"
 
     def seed_rng(self) -> None:
         """Dropout masks: Philox keyed by (engine constant ^ trainer seed) + rank, offset by the GLOBAL step count — every
@@ -121,19 +126,49 @@ class Trainer:
     def _graphable(self) -> bool:
         """The FeedForward / Groundlink steps are 25-80 short launches: at the reference's batch sizes (32-64 windows,
         train.py:52) the host, not the GPU, paces them, so a step is captured once per (store, batch size) and replayed —
-        with dropout and Adam/Adamax too, whose per-step values come from the device-resident step counter.  Not captured: the
-        denoiser (its step is GPU-bound and draws timesteps with a torch generator) and, by default, data-parallel runs:
-        capturing the side-stream NCCL allreduce (IBM_TRAIN_GRAPHS_DP=1) hung on the first 2-GPU attempt of round 2 and is
-        left as an experiment.  IBM_TRAIN_GRAPHS=0 switches replay off altogether."""
+        with dropout and Adam/Adamax too, whose per-step values come from the device-resident step counter.  Data-parallel
+        steps are captured as TWO graphs cut at the gradient allreduce, which stays an ordinary NCCL call between the two
+        replays (a captured NCCL allreduce hung on replay in both attempts of round 2 — side-stream buckets and a single
+        collective on the capture stream — so NCCL is kept out of the graphs).  Not captured: the denoiser (its step is
+        GPU-bound and draws timesteps with a torch generator).  IBM_TRAIN_GRAPHS=0 switches replay off altogether,
+        IBM_TRAIN_GRAPHS_DP=0 for data-parallel runs only."""
         if not self.use_graphs or self.is_denoiser:
             return False
-        return self.world == 1 or os.environ.get("IBM_TRAIN_GRAPHS_DP", "0") == "1"
+        return self.world == 1 or (self.dp_graphs and self.bucketer.mode == "tail")
 
     def train_step(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
         """Returns the device-resident fp32[40] result (loss at [0]); nothing is synchronised."""
         if self._graphable():
             return self._train_step_graphed(store, idx)
         return self._train_step_eager(store, idx)
+
+    def _capture_step(self, store: WindowStore, idx: torch.Tensor) -> list:
+        """Captures one eager step into CUDA graphs: one graph on a single rank; under data parallelism [everything up to the
+        end of backward] and [optimizer], the bucketer's finish_hook closing the first graph and opening the second at the
+        point where the eager step issues its allreduce.  Capture does not execute."""
+        graphs = [torch.cuda.CUDAGraph()]
+        mode = "thread_local" if self.world > 1 else "global"     # the NCCL watchdog thread may query events meanwhile
+        side = torch.cuda.Stream(device=self.arena.device)
+        side.wait_stream(torch.cuda.current_stream())
+
+        def cut():
+            graphs[-1].capture_end()
+            nxt = torch.cuda.CUDAGraph()
+            nxt.capture_begin(pool=graphs[0].pool(), capture_error_mode=mode)
+            graphs.append(nxt)
+
+        self.bucketer.finish_hook = cut if self.world > 1 else None
+        try:
+            with torch.cuda.stream(side):
+                graphs[0].capture_begin(capture_error_mode=mode)
+                try:
+                    self._train_step_eager(store, idx)
+                finally:
+                    graphs[-1].capture_end()
+        finally:
+            self.bucketer.finish_hook = None
+        torch.cuda.current_stream().wait_stream(side)
+        return graphs
 
     def _train_step_graphed(self, store: WindowStore, idx: torch.Tensor) -> torch.Tensor:
         key = (id(store), idx.numel(), self.lr, self.model.training)     # launch arguments baked into the captured step
@@ -151,19 +186,19 @@ class Trainer:
             ring, self._result_ring = self._result_ring, [g[3]]
             count = self.step_count
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
             try:
-                # thread_local: the NCCL watchdog thread may query events while this thread captures
-                with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
-                    self._train_step_eager(store, g[2])
+                graphs = self._capture_step(store, g[2])
             finally:
                 self._result_ring = ring
             self.step_count = count              # capture does not execute: the replay below is this step
             if hasattr(self.eng, "step"):
                 self.eng.step = count
-            g[1] = graph
+            g[1] = graphs
         g[2].copy_(idx, non_blocking=True)
-        g[1].replay()
+        g[1][0].replay()
+        for graph in g[1][1:]:                   # data parallel: [... backward] -> allreduce of the arena -> [optimizer]
+            self.bucketer.allreduce_all()
+            graph.replay()
         self.step_count += 1
         self.arena._versions = self.arena._version_sum()
         result = self._result_ring[self.step_count % len(self._result_ring)]

@@ -582,3 +582,83 @@ def test_pack_channel_major_bit_exact(B, T, E):
     want = want.reshape(B * T, C + E).to(torch.bfloat16)
     assert torch.equal(out[:, :C + E].cpu(), want)
     assert (out[:, C + E:] == 0).all()
+
+
+# ---------------------------------------- walk order -----------------------------------------------
+def test_walk_order_does_not_change_results():
+    """ibm_set_walk_order: GEMM work items, LayerNorm rows and attention windows taken in DESCENDING order (mode 2 alternates
+    every launch, so two launches cover both directions) give the ascending order's results — bit for bit where the
+    arithmetic has no cross-item sums (everything except split-K reduce-adds and fp32 atomics of column sums)."""
+    from inferbiomechanics_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    dev = "cuda"
+
+    def run_all():
+        out = {}
+        M, N, K = 1111, 768, 512                       # ragged M: the last row block is partial in either direction
+        A = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+        W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        res = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev)
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        out["gemm_plain"] = ops.gemm(A, W, y, M, N, K, bias=bias, act="relu").clone()
+        out["gemm_aux"] = ops.gemm(A, W, torch.empty_like(y), M, N, K, bias=bias, aux=res, aux_mode=1).clone()
+        mask = torch.zeros(M, N // 8, dtype=torch.uint8, device=dev)
+        out["gemm_mask_w"] = ops.gemm(A, W, torch.empty_like(y), M, N, K, bias=bias, act="relu", mask=mask, mask_mode=1).clone()
+        out["mask"] = mask.clone()
+        cs = torch.zeros(N, device=dev)
+        out["gemm_mask_r"] = ops.gemm(A, W, torch.empty_like(y), M, N, K, mask=mask, mask_mode=2, colsum=cs).clone()
+        out["~colsum"] = cs
+        M2 = 2048 * 4                                  # supertiles (K >= 1024, enough row blocks) with the aux ring
+        A2 = torch.randn(M2, 1024, generator=g).to(torch.bfloat16).to(dev)
+        W2 = (torch.randn(512, 1024, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+        r2 = torch.randn(M2, 512, generator=g).to(torch.bfloat16).to(dev)
+        out["gemm_super_aux"] = ops.gemm(A2, W2, torch.empty(M2, 512, dtype=torch.bfloat16, device=dev), M2, 512, 1024, aux=r2, aux_mode=1).clone()
+        wg = torch.zeros(512, 1024, device=dev)
+        d2 = torch.randn(M2, 512, generator=g).to(torch.bfloat16).to(dev)
+        ops.gemm(d2, A2, wg, 512, 1024, M2, a_mn=True, b_mn=True, accumulate=True)
+        out["~wgrad"] = wg
+        Ml, d = 3001, 512
+        s = (torch.randn(Ml, d, generator=g) * 2).to(torch.bfloat16).to(dev)
+        gamma, beta = (1 + 0.1 * torch.randn(d, generator=g)).to(dev), (0.1 * torch.randn(d, generator=g)).to(dev)
+        yl = torch.empty_like(s)
+        mean, rstd = torch.empty(Ml, device=dev), torch.empty(Ml, device=dev)
+        ops.layernorm_fwd(s, yl, gamma, beta, Ml, d, mean=mean, rstd=rstd)
+        out["ln_y"], out["ln_mean"], out["ln_rstd"] = yl, mean, rstd
+        dy = torch.randn(Ml, d, generator=g).to(torch.bfloat16).to(dev)
+        ds = torch.empty_like(s)
+        dg, db, dc = (torch.zeros(d, device=dev) for _ in range(3))
+        ops.layernorm_bwd(dy, s, gamma, mean, rstd, Ml, d, ds, dg, db, dc)
+        out["ln_ds"], out["~ln_dg"], out["~ln_db"], out["~ln_dc"] = ds, dg, db, dc
+        n_win, T, H, hd = 301, 50, 8, 64               # odd window count: the last pair of the backward is half empty
+        qkv = (torch.randn(n_win * T, 3 * H * hd, generator=g) * 0.8).to(torch.bfloat16).to(dev)
+        o = torch.empty(n_win * T, H * hd, dtype=torch.bfloat16, device=dev)
+        ops.attention_fwd_fused(qkv, H * hd, o, n_win, T, H, hd, 0.125)
+        out["attn_o"] = o
+        do = torch.randn(n_win * T, H * hd, generator=g).to(torch.bfloat16).to(dev)
+        dqkv = torch.empty_like(qkv)
+        dbias = torch.zeros(3 * H * hd, device=dev)
+        ops.attention_bwd(qkv, H * hd, do, dqkv, n_win, T, H, hd, 0.125, dbias=dbias)
+        out["attn_dqkv"], out["~attn_dbias"] = dqkv, dbias
+        torch.cuda.synchronize()
+        return out
+
+    try:
+        ops.set_walk_order(0)
+        g.manual_seed(77)
+        ref = run_all()
+        for rep in range(2):                           # every launch alternates: the two passes swap directions per op
+            ops.set_walk_order(2)
+            if rep == 1:
+                ops.layernorm_fwd(ref["ln_y"], torch.empty_like(ref["ln_y"]), torch.ones(512, device=dev), torch.zeros(512, device=dev), 8, 512)
+            g.manual_seed(77)
+            got = run_all()
+            for k, v in ref.items():
+                if k.startswith("~"):                  # sums across work items: order of fp32 additions differs
+                    torch.testing.assert_close(got[k], v, rtol=1e-4, atol=1e-3 * (v.abs().max().item() + 1e-6), msg=k)
+                else:
+                    assert torch.equal(got[k], v), f"{k} differs with walk order 2, pass {rep}"
+    finally:
+        ops.set_walk_order(0)
+    with pytest.raises(Exception):
+        ops.set_walk_order(3)

@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "workers", "dp_equivalence_worker.py")
 
 
-def _spawn(tmp_path, kind, opt, steps, B, world=2):
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+def _spawn(tmp_path, kind, opt, steps, B, world=2, extra_env=None):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", **(extra_env or {}))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29731", WORKER, str(tmp_path), kind, opt, str(steps), str(B)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
@@ -69,3 +69,23 @@ def test_denoiser_ranks_stay_in_lockstep(tmp_path):
         assert torch.equal(p, ranks[1]["params"][n]), f"{n} differs between ranks"
         assert torch.isfinite(p).all()
     assert ranks[0]["losses"] != ranks[1]["losses"]
+
+
+@pytest.mark.parametrize("kind", ["feedforward", "groundlink"])
+def test_data_parallel_graph_replay_equals_eager(tmp_path, kind):
+    """The small models' data-parallel step is replayed from two CUDA graphs cut at the gradient allreduce (trainer.py
+    _capture_step; the reference's default is batch 64 under DDP, train.py:52,175): same parameters and losses as the eager
+    launches, ranks in lockstep.  fp32 atomics (bias-gradient column sums) make the two runs differ in the last bits only."""
+    _need_two()
+    steps, B = 7, 32                                   # steps 1-2 eager, step 3 captures, 4-7 replay
+    d_e, d_g = tmp_path / "eager", tmp_path / "graph"
+    d_e.mkdir(), d_g.mkdir()
+    eager = _spawn(str(d_e), kind, "rmsprop", steps, B, extra_env={"IBM_TRAIN_GRAPHS": "0"})
+    graph = _spawn(str(d_g), kind, "rmsprop", steps, B)
+    assert eager[0]["graphs"] == 0 and graph[0]["graphs"] == 1
+    for n, p in graph[0]["params"].items():
+        assert torch.equal(p, graph[1]["params"][n]), f"{n} differs between ranks"
+        ref = eager[0]["params"][n]
+        assert (p - ref).abs().max().item() <= 2e-3 * steps * 1e-3 + 1e-6 * ref.abs().max().item(), n     # << one lr-sized update
+    for a, b in zip(eager[0]["losses"], graph[0]["losses"]):
+        assert abs(a - b) <= 1e-4 * abs(a)

@@ -86,6 +86,38 @@ def test_bucketed_allreduce_gloo_world2():
         assert collectives >= 2 and psum == 0.0                                # params equal rank 0's
 
 
+def _tail_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 5000
+        grad = torch.randn(n, generator=torch.Generator().manual_seed(100 + rank))
+        bucketer = parallel.GradBucketer(grad, parallel.make_buckets([0, 700, 2100, 4000], n, 1500), mode="tail")
+        for step in range(2):
+            bucketer.begin_step()
+            for group in (3, 2, 1, 0):
+                bucketer.group_done(group)
+            before = bucketer.collectives
+            bucketer.finish()
+            assert bucketer.collectives == before + 1
+        want = torch.stack([torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]).sum(0)
+        out[rank] = (torch.allclose(grad, want * world, atol=1e-5), bucketer.collectives)     # summed twice: (a+b) then 2(a+b)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tail_allreduce_gloo_world2():
+    """mode='tail': nothing fires during backward, finish() issues exactly one allreduce of the whole arena per step."""
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_tail_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        ok, collectives = out[r]
+        assert ok and collectives == 2
+    with pytest.raises(ValueError):
+        parallel.GradBucketer(torch.zeros(4), [(0, 4, 0)], mode="sometimes")
+
+
 def _agg_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
