@@ -96,6 +96,7 @@ struct Args {
   uint8_t* mask;           // optional sign bitmask [M][ldmask bytes], bit (c & 7) of byte c >> 3 <-> column c
   int64_t ldmask;
   int32_t mask_mode;       // 1: write (output > 0) after the activation; 2: zero the outputs whose bit is clear
+  int32_t stagger;         // supertiles: start on accumulator 0 while accumulator 1 is still being drained
   int32_t reverse;         // work items are taken from the last one down (ibm_set_walk_order); never with A-stationary
 };
 
@@ -377,10 +378,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
         // NT == 1: accumulator `as` (the other one is being drained).  NT == 2: both accumulators, one per column tile.
         mbar_wait(&tempty_bar[as], aphase ^ 1u);
-        if constexpr (NT == 2) mbar_wait(&tempty_bar[1], aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        auto issue_kblock = [&](int st, int t, bool first) {        // the four k steps of one 64-wide k block into accumulator t
+          const uint32_t sa = smem_u32(smem_a + st * kStageA);
+          const uint32_t sb = smem_u32(smem_b + st * C::kStageB) + t * (C::kStageB / NT);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            if constexpr (CG == 2) umma_bf16_pair(tmem_d + t * BN, adesc, bdesc, idesc, (!first || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d + t * BN, adesc, bdesc, idesc, (!first || k > 0) ? 1u : 0u);
+          }
+        };
+        int kb = kb0;
+        if constexpr (NT == 2) {
+          // Staggered start: the epilogue drains accumulator 0 first, then accumulator 1.  As soon as accumulator 0 is free
+          // the first k blocks of THIS item are multiplied into it (their operand stages are kept), and when accumulator 1
+          // follows, the same stages feed it and are released — up to kStages k blocks of tensor work hide the second half
+          // of the previous item's epilogue, which a supertile otherwise exposes completely.
+          const int pre = args.stagger ? min(C::kStages, kb1 - kb0) : 0;
+          int st = stage;
+          uint32_t ph = phase;
+          for (int j = 0; j < pre; ++j) {
+            mbar_wait(&full_bar[st], ph);
+            tc_fence_after();
+            issue_kblock(st, 0, j == 0);
+            advance(st, ph, C::kStages);
+          }
+          mbar_wait(&tempty_bar[1], aphase ^ 1u);
+          tc_fence_after();
+          for (int j = 0; j < pre; ++j) {
+            issue_kblock(stage, 1, j == 0);
+            umma_commit_pair(&empty_bar[stage]);
+            advance(stage, phase, C::kStages);
+          }
+          kb += pre;
+        }
+        for (; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem_a + stage * kStageA);
@@ -824,6 +859,12 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
   args.ldmask = ldmask;
   args.mask_mode = mask_mode;
   args.reverse = 0;
+  static int stagger_on = -1;
+  if (stagger_on < 0) {
+    const char* e = getenv("IBM_GEMM_STAGGER");
+    stagger_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  args.stagger = stagger_on;
   // With taps the B operand is [N, taps * kb_per_tap * 64] (each tap's K padded to whole k blocks).
   const int64_t Kb = taps == 1 ? K : (int64_t)args.kb_total * BLOCK_K;
 
