@@ -41,10 +41,6 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kStageA = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int kWarpStage = 32 * 128;                    // one epilogue warp's staging tile: 32 rows x 128 B = 4 KB
 constexpr int kSmemCap = 227 * 1024;                    // opt-in dynamic shared memory per CTA on sm_100
-// aux tiles (residual / saved activation): true = each epilogue thread loads its own 128-byte row piece straight from
-// global memory (L2-resident: the producer prefetches the tile a tile ahead) into registers; false = per-warp TMA ring in
-// shared memory.  Direct loads give the 64 KB of ring space back to the operand pipeline (4 -> 6 stages at 256 x 256).
-constexpr bool kAuxDirect = false;
 constexpr int kOutBufsPerWarp = 1;                      // output staging tiles per epilogue warp
 
 // CG = CTAs per MMA (cta_group): 1 = one 128 x BN tile per CTA; 2 = a CTA pair computes a 256 x BN tile, each CTA
@@ -68,8 +64,10 @@ struct Cfg {
   static constexpr int kOutBufs = kOutBufsPerWarp;
   // supertiles keep ONE aux tile per warp: it is copied to registers as soon as it lands and the next load is issued
   // into the same tile at once, so the load flies during the chunk's arithmetic and store (an operand stage is worth
-  // more than the second aux tile there)
-  static constexpr int kAuxBufs = (AUX && !kAuxDirect) ? (NT == 2 ? 1 : 2) : 0;
+  // more than the second aux tile there).  Measured alternatives (profiles/r02b_gemm_experiments.md): two aux tiles paid
+  // for by storing the rows straight from registers (390 vs 364 us, FFN-2 forward), per-thread cp.async or plain global
+  // loads of the aux rows (393 / 470 us) — all slower.
+  static constexpr int kAuxBufs = AUX ? (NT == 2 ? 1 : 2) : 0;
   static constexpr int kEpiBytes = kEpiWarps * (kOutBufs + kAuxBufs) * kWarpStage;
   static constexpr int kFixed = 1024 /*align slack*/ + kEpiBytes + 512 /*mbarriers, tmem slot*/ + (AS ? kASlots * kStageA : 0);
   static constexpr int kFit = (kSmemCap - kFixed) / ((AS ? 0 : kStageA) + kStageB);
@@ -96,6 +94,7 @@ struct Args {
   uint8_t* mask;           // optional sign bitmask [M][ldmask bytes], bit (c & 7) of byte c >> 3 <-> column c
   int64_t ldmask;
   int32_t mask_mode;       // 1: write (output > 0) after the activation; 2: zero the outputs whose bit is clear
+  int32_t pf_aux;          // aux tiles are pulled into L2 ahead of the epilogue: 0 no, 1 by TMA prefetches of the producer, 2 by warp 3
   int32_t stagger;         // supertiles: start on accumulator 0 while accumulator 1 is still being drained
   int32_t reverse;         // work items are taken from the last one down (ibm_set_walk_order); never with A-stationary
 };
@@ -186,7 +185,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   using C = Cfg<BN, kAux, CG, NT, kAS>;
   static_assert(NT == 1 || (NT == 2 && CG == 2 && BN == 256), "supertiles: CTA pairs, 256-wide tiles");
   static_assert(!kAS || (CG == 2 && NT == 1 && !kAux && !kAccum), "A-stationary: CTA pairs, plain epilogue, no split-K");
-  constexpr bool kAuxRegs = kAuxDirect || NT == 2;   // aux values reach the arithmetic through registers
+  constexpr bool kAuxRegs = NT == 2;                 // aux values reach the arithmetic through registers
   static_assert(CG == 1 || BN >= 128, "a CTA pair splits B into two halves of at least one 64-wide swizzle atom");
   static_assert(!kAux || (!kOutF32 && !kAccum), "TMA-staged aux tiles exist for bf16 outputs only");
   extern __shared__ uint8_t smem_raw[];
@@ -251,7 +250,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = CG * (kStageA + C::kStageB);     // the pair's loads all complete on the leader's barrier
-      const bool prefetch_aux = kAux;
+      const bool prefetch_aux = kAux && args.pf_aux == 1;
       if constexpr (kAS) {
         // row block by row block: refill the A slots (each as soon as the previous block's last column tile has consumed
         // it), then stream B for every column tile
@@ -446,6 +445,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
+  } else if (warp == 3) {
+    // ================================== aux prefetcher (optional) =============================
+    // pulls the aux tile of work item i into L2 with plain prefetches (LSU path: nothing is queued in the TMA unit ahead of
+    // the operand loads) when the accumulators of item i-1 complete, i.e. one main loop before the epilogue reads it
+    if constexpr (kAux && !kAS) {
+      if (args.pf_aux == 2) {
+        int as = 0;
+        uint32_t aphase = 0;
+        constexpr int kLinesPerRow = NT * BN * 2 / 128;
+        for (int w = worker; w < total_work; w += n_workers) {
+          const int tile = item_of(w) % n_tiles;
+          const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
+          const int64_t m0 = (int64_t)(tm * CG + rank) * BLOCK_M;
+          const int n0 = tn * NT * BN;
+          for (int i = lane; i < BLOCK_M * kLinesPerRow; i += 32) {
+            const int64_t row = m0 + i / kLinesPerRow;
+            const int col = n0 + (i % kLinesPerRow) * 64;
+            if (row < args.M && col < args.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(args.aux + row * args.ldaux + col));
+          }
+          mbar_wait(&tfull_bar[as], aphase);          // item w's main loop is over: the next item's starts now
+          if (NT == 2) { aphase ^= 1u; } else if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+      }
+    }
   } else if (warp >= kEpiWarp0) {
     // ======================================= epilogue ========================================
     // warp (q, half): TMEM lanes [32q, +32) = tile rows [32q, +32); column chunks half, half+2, … of the tile.
@@ -480,7 +503,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   ((t2 / args.tiles_n) * CG + rank) * BLOCK_M + q * 32);
       pch += 2;
     };
-    if (kAux && !kAuxDirect && lane == 0) {
+    if (kAux && lane == 0) {
       issue_aux(0);
       if (C::kAuxBufs == 2) issue_aux(1);
     }
@@ -533,28 +556,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int xb = C::kAuxBufs == 2 ? (xg & 1) : 0;
         const uint32_t xph = C::kAuxBufs == 2 ? (uint32_t)((xg >> 1) & 1) : (uint32_t)(xg & 1);
         uint4 ax[PT / 8];                          // this thread's aux row piece when it travels through registers
-        if (kAux && kAuxDirect) {
-          const int64_t row = (int64_t)m0 + lane;
-          const __nv_bfloat16* ap = args.aux + row * args.ldaux + c0;
-          if (row < args.M && c0 + PT <= args.N) {
-#pragma unroll
-            for (int j = 0; j < PT / 8; ++j) ax[j] = ld_stream16(ap + 8 * j);
-          } else {                                 // ragged edge: element-wise, zero beyond the matrix
-#pragma unroll
-            for (int j = 0; j < PT / 8; ++j) {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int col = c0 + 8 * j + 2 * e;
-                const float lo = (row < args.M && col < args.N) ? __bfloat162float(ap[8 * j + 2 * e]) : 0.f;
-                const float hi = (row < args.M && col + 1 < args.N) ? __bfloat162float(ap[8 * j + 2 * e + 1]) : 0.f;
-                w[e] = pack_bf16x2(lo, hi);
-              }
-              ax[j] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
-        }
-        if (kAux && !kAuxDirect) {
+        if (kAux) {
           mbar_wait(&my_aux_bar[xb], xph);         // this chunk's aux tile has landed
           if constexpr (NT == 2) {
             // single aux tile: move it to registers and put the next load in flight right away
@@ -643,7 +645,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (kAccum) tma_reduce_add_2d(&tmD, my_out + ob * kWarpStage, c0, m0);
           else tma_store_2d(&tmD, my_out + ob * kWarpStage, c0, m0);
           tma_commit_group();
-          if (kAux && !kAuxDirect && NT == 1) issue_aux(xb);   // every lane is past its reads of aux tile xb
+          if (kAux && NT == 1) issue_aux(xb);   // every lane is past its reads of aux tile xb
         }
         if constexpr (!kOutF32) {
           if (args.colsum != nullptr) {
@@ -865,6 +867,15 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
     stagger_on = (e && e[0] == '0') ? 0 : 1;
   }
   args.stagger = stagger_on;
+  // L2 prefetch of the aux tiles a main loop ahead of the epilogue: OFF.  Measured on one box (profiles/r02b_gemm_experiments.md):
+  // both ways of doing it — 32 TMA prefetch ops per item in the producer, or plain prefetch.global.L2 from the spare warp —
+  // cost 4 % on every aux shape (FFN-2 forward 364 -> 378 us, QKV dgrad 284 -> 298); IBM_GEMM_PFAUX=1/2 re-enables them.
+  static int pf_aux = -1;
+  if (pf_aux < 0) {
+    const char* e = getenv("IBM_GEMM_PFAUX");
+    pf_aux = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+  }
+  args.pf_aux = pf_aux;
   // With taps the B operand is [N, taps * kb_per_tap * 64] (each tap's K padded to whole k blocks).
   const int64_t Kb = taps == 1 ? K : (int64_t)args.kb_total * BLOCK_K;
 

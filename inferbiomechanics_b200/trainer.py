@@ -16,6 +16,7 @@ the reference's own autograd loop; this is the path bench.py times.
 from __future__ import annotations
 
 import argparse
+import gc
 import os
 from typing import Dict, List, Optional
 
@@ -148,6 +149,12 @@ class Trainer:
         point where the eager step issues its allreduce.  Capture does not execute."""
         graphs = [torch.cuda.CUDAGraph()]
         mode = "thread_local" if self.world > 1 else "global"     # the NCCL watchdog thread may query events meanwhile
+        # as torch.cuda.graph() does: collect garbage first — a CUDAGraph (or a tensor with cross-stream events) finalised by
+        # the cyclic collector in the middle of the capture issues calls that invalidate it — and keep the collector off meanwhile
+        gc.collect()
+        torch.cuda.synchronize()
+        gc_was_on = gc.isenabled()
+        gc.disable()
         side = torch.cuda.Stream(device=self.arena.device)
         side.wait_stream(torch.cuda.current_stream())
 
@@ -167,6 +174,8 @@ class Trainer:
                     graphs[-1].capture_end()
         finally:
             self.bucketer.finish_hook = None
+            if gc_was_on:
+                gc.enable()
         torch.cuda.current_stream().wait_stream(side)
         return graphs
 

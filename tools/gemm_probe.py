@@ -17,6 +17,7 @@ CASES = {
     "qkv_fwd": (M, 1536, 512, 0, 0, 1, "none", 0, 0, 0),
     "ffn1_fwd": (M, 2048, 512, 0, 0, 1, "relu", 0, 0, 0),
     "ffn2_fwd_res": (M, 512, 2048, 0, 0, 1, "none", 1, 0, 0),
+    "ffn2_fwd_plain": (M, 512, 2048, 0, 0, 1, "none", 0, 0, 0),       # the same product without the residual tile (4 operand stages)
     "outproj_fwd_res": (M, 512, 512, 0, 0, 1, "none", 1, 0, 0),
     "outproj_dgrad": (M, 512, 512, 0, 1, 0, "none", 0, 0, 0),
     "ffn2_dgrad": (M, 2048, 512, 0, 1, 0, "relu", 2, 0, 0),
