@@ -2,6 +2,8 @@
 // reductions.  Replaces nn.LayerNorm at /root/reference/src/models/TransformerBaseline.py:21-22,31,36
 // (the residual add is fused into the producing GEMM's epilogue, see gemm_sm100.cu aux_mode 1).
 // HBM-bound: forward reads s and writes y (2 units); backward reads dy, s and writes ds (3 units).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -36,11 +38,23 @@ __device__ __forceinline__ void unpack8(uint4 u, float (&v)[8]) {
   a = unpack_bf16x2(u.w); v[6] = a.x; v[7] = a.y;
 }
 
+// Packed fp32 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per instruction and issue slot).  The
+// LayerNorm kernels are issue-bound at the clock the power-capped training step runs at (ncu, profiles/r01d: 59 % / 71 %
+// issue-active at 1.9 GHz for forward / backward, half of the instructions elementwise fp32 math on 16 values per lane):
+// pairing the elementwise work takes the forward from ~222 to ~125 and the backward from ~402 to ~200 warp instructions
+// per row.  Each lane of a pair is rounded exactly like the scalar instruction it replaces.
+__device__ __forceinline__ void unpack8p(uint4 u, float2 (&v)[4]) {
+  v[0] = unpack_bf16x2(u.x); v[1] = unpack_bf16x2(u.y); v[2] = unpack_bf16x2(u.z); v[3] = unpack_bf16x2(u.w);
+}
+__device__ __forceinline__ uint4 pack8p(const float2 (&o)[4]) {
+  return make_uint4(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y), pack_bf16x2(o[2].x, o[2].y), pack_bf16x2(o[3].x, o[3].y));
+}
+
 // each lane owns chunks of 8 consecutive columns: columns (k*32 + lane)*8 … +7 for k < CH.  A row group is R
 // consecutive rows (R * ld * 2 contiguous bytes: one bulk copy).
 // FULL: d == ld == CH*256 (no pad columns, every chunk complete) — the column predicates fold away, which halves
 // the instruction count of these issue-bound kernels (profiles/r01c: 355 → ~190 warp instructions per row forward).
-template <int CH, int R, bool FULL>
+template <int CH, int R, bool FULL, bool PK>
 __global__ void __launch_bounds__(kThreads)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ y, long long ld,
                      const float* __restrict__ gamma, const float* __restrict__ beta, long long M, int d, float eps,
@@ -78,6 +92,20 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
       if (gw + i * gstride < n_groups) issue(gw + i * gstride, i);
   }
   const float inv_d = 1.f / (float)d;
+  // full rows of up to 512 columns: gamma / beta of this lane's 16 columns live in registers (read from shared memory, the
+  // 32-byte lane stride of the float4 reads costs two wavefronts each: 64 of the 72 LSU wavefronts per row were these)
+  constexpr bool kRegGB = FULL && PK && CH <= 2;
+  float2 G2[kRegGB ? CH : 1][4], B2[kRegGB ? CH : 1][4];
+  if constexpr (kRegGB) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = (k * 32 + lane) * 8 + 2 * i;
+        G2[k][i] = make_float2(__ldg(gamma + c), __ldg(gamma + c + 1));
+        B2[k][i] = make_float2(__ldg(beta + c), __ldg(beta + c + 1));
+      }
+  }
   int it = 0;
   for (long long grp = gw; grp < n_groups; grp += gstride, ++it) {
     const int st = it % kStages;
@@ -87,6 +115,47 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restr
     for (int r = 0; r < R; ++r) {
       const long long m = (rev ? n_groups - 1 - grp : grp) * R + r;
       if (m >= M) break;
+      if constexpr (FULL && PK) {
+        float2 v[CH][4];
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          unpack8p(lds16(tile + r * row_bytes + (k * 32 + lane) * 16), v[k]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc = __fadd2_rn(acc, v[k][i]);
+        }
+        const float mu = warp_sum(acc.x + acc.y) * inv_d;
+        const float2 nmu = make_float2(-mu, -mu);
+        acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[k][i] = __fadd2_rn(v[k][i], nmu);
+            acc = __ffma2_rn(v[k][i], v[k][i], acc);
+          }
+        const float rs = rsqrtf(warp_sum(acc.x + acc.y) * inv_d + eps);
+        const float2 rs2 = make_float2(rs, rs);
+        if (lane == 0) { if (mean) mean[m] = mu; if (rstd) rstd[m] = rs; }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          const int c = (k * 32 + lane) * 8;
+          float2 o[4];
+          if constexpr (kRegGB) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = __ffma2_rn(__fmul2_rn(v[k][i], rs2), G2[k][i], B2[k][i]);
+          } else {
+            const float4 g0 = *reinterpret_cast<const float4*>(sg + c), g1 = *reinterpret_cast<const float4*>(sg + c + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + c), b1 = *reinterpret_cast<const float4*>(sb + c + 4);
+            o[0] = __ffma2_rn(__fmul2_rn(v[k][0], rs2), make_float2(g0.x, g0.y), make_float2(b0.x, b0.y));
+            o[1] = __ffma2_rn(__fmul2_rn(v[k][1], rs2), make_float2(g0.z, g0.w), make_float2(b0.z, b0.w));
+            o[2] = __ffma2_rn(__fmul2_rn(v[k][2], rs2), make_float2(g1.x, g1.y), make_float2(b1.x, b1.y));
+            o[3] = __ffma2_rn(__fmul2_rn(v[k][3], rs2), make_float2(g1.z, g1.w), make_float2(b1.z, b1.w));
+          }
+          st_stream16(y + m * ld + c, pack8p(o));
+        }
+        continue;
+      }
       float v[CH][8];
       float sum = 0.f;
 #pragma unroll
@@ -232,7 +301,7 @@ layernorm_fwd_narrow_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* 
 // Column reductions (dgamma, dbeta, colsum(ds)) are accumulated in registers over the rows a warp
 // visits, combined across the block's 8 warps in shared memory, then one fp32 atomic per column
 // per block.  A ring stage holds one row of dy and one row of s.
-template <int CH, bool FULL>
+template <int CH, bool FULL, bool PK>
 __global__ void __launch_bounds__(kThreads, CH <= 2 ? 2 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ s, long long ld,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -271,11 +340,24 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       if (gw + i * gstride < M) issue(gw + i * gstride, i);
   }
   const float inv_d = 1.f / (float)d;
-  float ag[CH][8], ab[CH][8], ac[CH][8];
+  // column accumulators as fp32 pairs (see the note on packed arithmetic above); element j of chunk k is half (j & 1) of pair j / 2
+  float2 ag2[CH][4], ab2[CH][4], ac2[CH][4];
+#define LN_ACC(a, k, j) (((j) & 1) ? a[k][(j) >> 1].y : a[k][(j) >> 1].x)
 #pragma unroll
   for (int k = 0; k < CH; ++k)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ag[k][j] = ab[k][j] = ac[k][j] = 0.f;
+    for (int i = 0; i < 4; ++i) ag2[k][i] = ab2[k][i] = ac2[k][i] = make_float2(0.f, 0.f);
+  constexpr bool kRegG = FULL && PK && CH <= 2;      // gamma of this lane's 16 columns in registers
+  float2 GM[kRegG ? CH : 1][4];
+  if constexpr (kRegG) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = (k * 32 + lane) * 8 + 2 * i;
+        GM[k][i] = make_float2(__ldg(gamma + c), __ldg(gamma + c + 1));
+      }
+  }
   int it = 0;
   float mu_n = gw < M ? __ldg(mean + phys(gw)) : 0.f, rs_n = gw < M ? __ldg(rstd + phys(gw)) : 0.f;
   for (long long m = gw; m < M; m += gstride, ++it) {
@@ -284,6 +366,49 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     if (m + gstride < M) { mu_n = __ldg(mean + phys(m + gstride)); rs_n = __ldg(rstd + phys(m + gstride)); }   // next row's statistics
     mbar_wait(&bars[st], (uint32_t)((it / kStages) & 1));
     const uint8_t* tile = ring + (size_t)st * 2 * row_bytes;
+    if constexpr (FULL && PK) {
+      float2 xh[CH][4], g[CH][4];
+      float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+      const float2 nmu = make_float2(-mu, -mu), rs2 = make_float2(rs, rs);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const int c = (k * 32 + lane) * 8;
+        unpack8p(lds16(tile + c * 2), g[k]);
+        unpack8p(lds16(tile + row_bytes + c * 2), xh[k]);
+        float2 gm[4];
+        if constexpr (kRegG) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gm[i] = GM[k][i];
+        } else {
+          const float4 g0 = *reinterpret_cast<const float4*>(sg + c), g1 = *reinterpret_cast<const float4*>(sg + c + 4);
+          gm[0] = make_float2(g0.x, g0.y); gm[1] = make_float2(g0.z, g0.w); gm[2] = make_float2(g1.x, g1.y); gm[3] = make_float2(g1.z, g1.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xh[k][i] = __fmul2_rn(__fadd2_rn(xh[k][i], nmu), rs2);
+          ag2[k][i] = __ffma2_rn(g[k][i], xh[k][i], ag2[k][i]);       // dgamma
+          ab2[k][i] = __fadd2_rn(ab2[k][i], g[k][i]);                  // dbeta
+          g[k][i] = __fmul2_rn(g[k][i], gm[i]);
+          a1 = __fadd2_rn(a1, g[k][i]);
+          a2 = __ffma2_rn(g[k][i], xh[k][i], a2);
+        }
+      }
+      __syncwarp();                                   // every lane has read this stage
+      if (lane == 0 && m + kStages * gstride < M) issue(m + kStages * gstride, st);
+      const float s1 = warp_sum(a1.x + a1.y) * inv_d, s2 = warp_sum(a2.x + a2.y) * inv_d;
+      const float2 ns1 = make_float2(-s1, -s1), ns2 = make_float2(-s2, -s2);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        float2 o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          o[i] = __fmul2_rn(__ffma2_rn(xh[k][i], ns2, __fadd2_rn(g[k][i], ns1)), rs2);
+          ac2[k][i] = __fadd2_rn(ac2[k][i], o[i]);
+        }
+        st_stream16(ds + phys(m) * ld + (k * 32 + lane) * 8, pack8p(o));
+      }
+      continue;
+    }
     float xh[CH][8], g[CH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -298,8 +423,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         for (int j = 0; j < 8; ++j) {
           if (FULL || c + j < d) {
             xh[k][j] = (xh[k][j] - mu) * rs;
-            ag[k][j] = fmaf(g[k][j], xh[k][j], ag[k][j]);     // dgamma
-            ab[k][j] += g[k][j];                               // dbeta
+            LN_ACC(ag2, k, j) = fmaf(g[k][j], xh[k][j], LN_ACC(ag2, k, j));     // dgamma
+            LN_ACC(ab2, k, j) += g[k][j];                                         // dbeta
             g[k][j] *= gm[j];
             s1 += g[k][j];
             s2 = fmaf(g[k][j], xh[k][j], s2);
@@ -322,7 +447,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           o[j] = (FULL || c + j < d) ? rs * (g[k][j] - s1 - xh[k][j] * s2) : 0.f;
-          ac[k][j] += o[j];
+          LN_ACC(ac2, k, j) += o[j];
         }
         st_stream16(ds + phys(m) * ld + c, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
                                                       pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
@@ -338,9 +463,9 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     const int c = (k * 32 + lane) * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      sm[(0 * 8 + wid) * W + c + j] = ag[k][j];
-      sm[(1 * 8 + wid) * W + c + j] = ab[k][j];
-      sm[(2 * 8 + wid) * W + c + j] = ac[k][j];
+      sm[(0 * 8 + wid) * W + c + j] = LN_ACC(ag2, k, j);
+      sm[(1 * 8 + wid) * W + c + j] = LN_ACC(ab2, k, j);
+      sm[(2 * 8 + wid) * W + c + j] = LN_ACC(ac2, k, j);
     }
   }
   __syncthreads();
@@ -352,6 +477,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     if (dbeta) atomicAdd(dbeta + c, b);
     if (dcolsum) atomicAdd(dcolsum + c, e);
   }
+#undef LN_ACC
 }
 
 // persistent grid: blocks per SM from the occupancy calculator, capped by the work
@@ -366,10 +492,23 @@ static int ln_grid(K kern, size_t smem, long long units, int* grid) {
   return IBM_OK;
 }
 
-template <int CH, int R, bool FULL>
+// IBM_LN_PACKED=0: the scalar arithmetic of round 1 (A/B measurements)
+static bool ln_packed() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IBM_LN_PACKED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int CH, int R, bool FULL, bool PK = true>
 static int launch_ln_fwd(const __nv_bfloat16* sp, __nv_bfloat16* yp, int64_t ld, const float* gamma, const float* beta, int64_t M,
                          int32_t d, float eps, float* mean, float* rstd, cudaStream_t st) {
-  auto kern = layernorm_fwd_kernel<CH, R, FULL>;
+  if constexpr (FULL && PK) {
+    if (!ln_packed()) return launch_ln_fwd<CH, R, FULL, false>(sp, yp, ld, gamma, beta, M, d, eps, mean, rstd, st);
+  }
+  auto kern = layernorm_fwd_kernel<CH, R, FULL, FULL && PK>;
   const size_t smem = (size_t)2 * CH * 256 * sizeof(float) + (size_t)kWarps * kStages * R * ld * 2 + kWarps * kStages * 8;
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -402,11 +541,14 @@ static int launch_ln_fwd_narrow(const __nv_bfloat16* sp, __nv_bfloat16* yp, int6
   return IBM_OK;
 }
 
-template <int CH, bool FULL>
+template <int CH, bool FULL, bool PK = true>
 static int launch_ln_bwd(const __nv_bfloat16* dyp, const __nv_bfloat16* sp, int64_t ld, const float* gamma, const float* mean,
                          const float* rstd, int64_t M, int32_t d, __nv_bfloat16* dsp, float* dgamma, float* dbeta, float* dcolsum,
                          cudaStream_t st) {
-  auto kern = layernorm_bwd_kernel<CH, FULL>;
+  if constexpr (FULL && PK) {
+    if (!ln_packed()) return launch_ln_bwd<CH, FULL, false>(dyp, sp, ld, gamma, mean, rstd, M, d, dsp, dgamma, dbeta, dcolsum, st);
+  }
+  auto kern = layernorm_bwd_kernel<CH, FULL, FULL && PK>;
   const size_t ring = (size_t)kWarps * kStages * 2 * ld * 2, comb = (size_t)3 * kWarps * CH * 256 * sizeof(float);
   const size_t smem = (size_t)CH * 256 * sizeof(float) + (ring > comb ? ring : comb) + kWarps * kStages * 8;
   static size_t smem_set = 0;
