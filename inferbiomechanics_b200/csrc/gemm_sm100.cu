@@ -94,6 +94,7 @@ struct Args {
   uint8_t* mask;           // optional sign bitmask [M][ldmask bytes], bit (c & 7) of byte c >> 3 <-> column c
   int64_t ldmask;
   int32_t mask_mode;       // 1: write (output > 0) after the activation; 2: zero the outputs whose bit is clear
+  int32_t fp2;             // EXPERIMENT switch: packed fp32 adds in the epilogue (IBM_GEMM_FP2=0: scalar)
   int32_t pf_aux;          // aux tiles are pulled into L2 ahead of the epilogue: 0 no, 1 by TMA prefetches of the producer, 2 by warp 3
   int32_t stagger;         // supertiles: start on accumulator 0 while accumulator 1 is still being drained
   int32_t reverse;         // work items are taken from the last one down (ibm_set_walk_order); never with A-stationary
@@ -147,10 +148,18 @@ __device__ __forceinline__ void epi_aux(float (&v)[PT], uint32_t xrow, int rsw, 
     t = unpack_bf16x2(u.y); y[2] = t.x; y[3] = t.y;
     t = unpack_bf16x2(u.z); y[4] = t.x; y[5] = t.y;
     t = unpack_bf16x2(u.w); y[6] = t.x; y[7] = t.y;
+    if constexpr (MODE == 1 && ACT == IBM_ACT_NONE) {      // residual add: packed fp32 adds
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float x = v[8 * jj + e];
-      v[8 * jj + e] = MODE == 1 ? act_t<ACT>(x) + y[e] : x * dact_t<ACT>(y[e]);
+      for (int e = 0; e < 8; e += 2) {
+        const float2 r = __fadd2_rn(make_float2(v[8 * jj + e], v[8 * jj + e + 1]), make_float2(y[e], y[e + 1]));
+        v[8 * jj + e] = r.x; v[8 * jj + e + 1] = r.y;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = v[8 * jj + e];
+        v[8 * jj + e] = MODE == 1 ? act_t<ACT>(x) + y[e] : x * dact_t<ACT>(y[e]);
+      }
     }
   }
 }
@@ -575,9 +584,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (c0 + PT <= args.N) {
               const float4* b4 = reinterpret_cast<const float4*>(args.bias + c0);
 #pragma unroll
-              for (int j = 0; j < PT / 4; ++j) {
+              for (int j = 0; j < PT / 4; ++j) {       // packed fp32 adds (FADD2): half the issue slots of the bias add
                 const float4 b = __ldg(b4 + j);
-                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                if (args.fp2) {
+                  const float2 lo = __fadd2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(b.x, b.y));
+                  const float2 hi = __fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(b.z, b.w));
+                  v[4 * j] = lo.x; v[4 * j + 1] = lo.y; v[4 * j + 2] = hi.x; v[4 * j + 3] = hi.y;
+                } else {
+                  v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                }
               }
             } else {
 #pragma unroll
@@ -867,6 +882,12 @@ extern "C" int ibm_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, con
     stagger_on = (e && e[0] == '0') ? 0 : 1;
   }
   args.stagger = stagger_on;
+  static int fp2_on = -1;
+  if (fp2_on < 0) {
+    const char* e = getenv("IBM_GEMM_FP2");
+    fp2_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  args.fp2 = fp2_on;
   // L2 prefetch of the aux tiles a main loop ahead of the epilogue: OFF.  Measured on one box (profiles/r02b_gemm_experiments.md):
   // both ways of doing it — 32 TMA prefetch ops per item in the producer, or plain prefetch.global.L2 from the spare warp —
   // cost 4 % on every aux shape (FFN-2 forward 364 -> 378 us, QKV dgrad 284 -> 298); IBM_GEMM_PFAUX=1/2 re-enables them.
