@@ -12,7 +12,8 @@ import sys
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "inferbiomechanics_b200", "libibm_b200.so")
 PAT = {"UTC*MMA (tcgen05.mma)": r"\bUTC[A-Z]*MMA", "LDTM/STTM (tcgen05.ld/st)": r"\b(LDTM|STTM)", "UTMALDG (TMA load)": r"\bUTMALDG",
        "UTMASTG/UTMAREDG (TMA store / reduce)": r"\b(UTMASTG|UTMAREDG)", "UBLKCP (bulk copy)": r"\bUBLKCP", "HMMA (mma.sync)": r"\bHMMA",
-       "LDGSTS (cp.async)": r"\bLDGSTS", "LDSM (ldmatrix)": r"\bLDSM", "SYNCS (mbarrier)": r"\bSYNCS"}
+       "LDGSTS (cp.async)": r"\bLDGSTS", "LDSM (ldmatrix)": r"\bLDSM", "SYNCS (mbarrier)": r"\bSYNCS",
+       "FADD2/FMUL2/FFMA2 (packed fp32)": r"\bF(ADD|MUL|FMA)2\b"}
 
 
 def main():
