@@ -94,7 +94,7 @@ struct Args {
   uint8_t* mask;           // optional sign bitmask [M][ldmask bytes], bit (c & 7) of byte c >> 3 <-> column c
   int64_t ldmask;
   int32_t mask_mode;       // 1: write (output > 0) after the activation; 2: zero the outputs whose bit is clear
-  int32_t fp2;             // EXPERIMENT switch: packed fp32 adds in the epilogue (IBM_GEMM_FP2=0: scalar)
+  int32_t fp2;             // bias adds as packed fp32 (FADD2); IBM_GEMM_FP2=0 keeps the scalar adds for A/B runs
   int32_t pf_aux;          // aux tiles are pulled into L2 ahead of the epilogue: 0 no, 1 by TMA prefetches of the producer, 2 by warp 3
   int32_t stagger;         // supertiles: start on accumulator 0 while accumulator 1 is still being drained
   int32_t reverse;         // work items are taken from the last one down (ibm_set_walk_order); never with A-stationary
@@ -306,8 +306,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(args.kb_total, kb0 + args.kb_per_split);
         if (prefetch_aux) {
-          // the epilogue of this tile runs ~1.5 tile-times from now: pull its aux tile into L2 so the
-          // epilogue's one-chunk-ahead TMA loads see L2 latency, not DRAM latency
+          // round-1 behaviour (IBM_GEMM_PFAUX=1, off by default: measured 4 % slower): the epilogue of this tile runs ~1.5
+          // tile-times from now, pull its aux tile into L2 so the epilogue's one-chunk-ahead TMA loads see L2 latency
           for (int c = 0; c < NT * BN && n0 + c < args.N; c += 64)
             for (int r = 0; r < BLOCK_M; r += 32) tma_prefetch_l2_2d(&tmX, n0 + c, m0 + r);
         }
