@@ -101,7 +101,19 @@ def _tail_worker(rank, world, port, out):
             bucketer.finish()
             assert bucketer.collectives == before + 1
         want = torch.stack([torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]).sum(0)
-        out[rank] = (torch.allclose(grad, want * world, atol=1e-5), bucketer.collectives)     # summed twice: (a+b) then 2(a+b)
+        ok = torch.allclose(grad, want * world, atol=1e-5)                                      # summed twice: (a+b) then 2(a+b)
+        # finish_hook (the trainer's graph capture cuts the step there): called INSTEAD of the collective, which the caller
+        # then issues itself with allreduce_all()
+        calls = []
+        bucketer.finish_hook = lambda: calls.append(bucketer.collectives)
+        bucketer.begin_step()
+        bucketer.finish()
+        ok = ok and calls == [2] and bucketer.collectives == 2 and torch.allclose(grad, want * world, atol=1e-5)
+        bucketer.finish_hook = None
+        bucketer.allreduce_all()
+        ok = ok and bucketer.collectives == 3 and torch.allclose(grad, want * world * world, atol=1e-4)
+        bucketer.collectives = 2
+        out[rank] = (ok, bucketer.collectives)
     finally:
         dist.destroy_process_group()
 
