@@ -355,36 +355,44 @@ def window_digest(items) -> str:
     return h.hexdigest()
 
 
-def gen_windows(ref_unused=None):
-    """Run the reference's AddBiomechanicsDataset itself over synthetic subjects (fake nimblephysics reader)."""
+def reference_dataset(subjects, T, s, fmt, tmp):
+    """The reference's own AddBiomechanicsDataset (Dataset.py:64-139) over ``subjects`` through the fake nimblephysics reader:
+    one empty ``.b3d`` per subject under ``tmp`` (plus a file the class must skip: "vander", Dataset.py:89, and a non-.b3d)."""
     import contextlib
     import io
+    from . import fake_nimble
+    load_reference()                                   # puts /root/reference/src on sys.path
+    n_subj = len(subjects)
+    os.makedirs(os.path.join(tmp, "grp_a"))
+    os.makedirs(os.path.join(tmp, "grp_b"))
+    for i in range(n_subj):
+        open(os.path.join(tmp, "grp_a" if i % 2 else "grp_b", f"subj{i:02d}.b3d"), "w").close()
+    open(os.path.join(tmp, "grp_a", "VanDerZee2022_x.b3d"), "w").close()     # skipped: "vander" (Dataset.py:89)
+    open(os.path.join(tmp, "grp_b", "notes.txt"), "w").close()               # skipped: not .b3d
+    found = [os.path.join(r, f) for r, _, fs in os.walk(tmp) for f in fs
+             if f.endswith(".b3d") and "vander" not in f.lower()]
+    assert len(found) == n_subj
+    # subject k of the synthetic list is the k-th file the reference's own os.walk discovers
+    fake_nimble.install({p: subjects[k] for k, p in enumerate(found)})
+    from data.AddBiomechanicsDataset import AddBiomechanicsDataset
+    with contextlib.redirect_stdout(io.StringIO()):
+        ds = AddBiomechanicsDataset(tmp, T, geometry_folder="", stride=s, output_data_format=fmt,
+                                    skip_loading_skeletons=True)
+    assert ds.subject_paths == found
+    return ds
+
+
+def gen_windows(ref_unused=None):
+    """Run the reference's AddBiomechanicsDataset itself over synthetic subjects (fake nimblephysics reader)."""
     import tempfile
     from torch.utils.data import DataLoader
     from torch.utils.data.distributed import DistributedSampler
-    from . import fake_nimble
     from .windows import make_synthetic_subjects
-    load_reference()                                   # puts /root/reference/src on sys.path
     d = {}
     for name, (seed, n_subj, T, s, fmt, hist, max_len, n_samp) in WINDOW_CASES.items():
         subjects = make_synthetic_subjects(seed, n_subj, T, hist_cols=hist, max_len=max_len)
         with tempfile.TemporaryDirectory() as tmp:
-            os.makedirs(os.path.join(tmp, "grp_a"))
-            os.makedirs(os.path.join(tmp, "grp_b"))
-            for i in range(n_subj):
-                open(os.path.join(tmp, "grp_a" if i % 2 else "grp_b", f"subj{i:02d}.b3d"), "w").close()
-            open(os.path.join(tmp, "grp_a", "VanDerZee2022_x.b3d"), "w").close()     # skipped: "vander" (Dataset.py:89)
-            open(os.path.join(tmp, "grp_b", "notes.txt"), "w").close()               # skipped: not .b3d
-            found = [os.path.join(r, f) for r, _, fs in os.walk(tmp) for f in fs
-                     if f.endswith(".b3d") and "vander" not in f.lower()]
-            assert len(found) == n_subj
-            # subject k of the synthetic list is the k-th file the reference's own os.walk discovers
-            fake_nimble.install({p: subjects[k] for k, p in enumerate(found)})
-            from data.AddBiomechanicsDataset import AddBiomechanicsDataset
-            with contextlib.redirect_stdout(io.StringIO()):
-                ds = AddBiomechanicsDataset(tmp, T, geometry_folder="", stride=s, output_data_format=fmt,
-                                            skip_loading_skeletons=True)
-            assert ds.subject_paths == found
+            ds = reference_dataset(subjects, T, s, fmt, tmp)
             N = len(ds)
             d[f"{name}/windows"] = np.asarray(ds.windows, dtype=np.int32).reshape(N, 3)
             d[f"{name}/meta"] = np.array([seed, n_subj, T, s, hist, max_len, ds.num_dofs, ds.num_contact_bodies])
