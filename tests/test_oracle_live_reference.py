@@ -151,3 +151,36 @@ def test_transformer_layer_live(d, heads, ff, T, B):
 def _layer_takes_dtype(ref) -> bool:
     import inspect
     return "dtype" in inspect.signature(ref.TransformerLayer.__init__).parameters
+
+
+@pytest.mark.parametrize("dofs,T,emb,layers,heads,ffw,B", [(23, 20, 30, 3, 3, 60, 2), (10, 9, 9, 1, 2, 16, 3), (23, 64, 30, 2, 6, 24, 1),
+                                                          (5, 3, 6, 4, 1, 8, 2)])
+def test_transformer_baseline_live(dofs, T, emb, layers, heads, ffw, B):
+    """TransformerBaseline.forward (TransformerBaseline.py:104-148) composed from the reference's own sub-modules (its forward
+    needs key constants that do not exist) with non-default constructor arguments; outputs and the gradient of
+    every parameter (fp64)."""
+    ref = load_reference()
+    torch.manual_seed(dofs * 100 + T)
+    m = ref.TransformerBaseline(dofs, T, temporal_embedding_dim=emb, num_layers=layers, num_heads=heads, dim_feedforward=ffw).eval()
+    x = {k: torch.randn(B, c, T, dtype=torch.float64) for k, c in (("pos", dofs), ("vel", dofs), ("acc", dofs), ("comPos", 3),
+                                                                     ("comVel", 3), ("comAcc", 3))}
+    vecs = torch.cat([x["pos"], x["vel"], x["acc"], x["comPos"], x["comVel"], x["comAcc"]], dim=1).transpose(1, 2)
+    e = m.temporal_embedding(torch.arange(vecs.size(1))).expand(B, T, m.temporal_embedding_dim)
+    vecs = torch.cat([vecs, e], dim=2)
+    for layer in m.transformer_layers:
+        vecs = layer(vecs)
+    output = m.fc(vecs)
+    want = {"contact": m.contact_sigmoid(output[:, :, :2]).transpose(1, 2),
+            "comAcc": m.com_attention(vecs, vecs, x["comAcc"].transpose(1, 2)).transpose(1, 2),
+            "contactForces": output[:, :, 5:].transpose(1, 2)}
+    w = {k: torch.randn(v.shape, dtype=torch.float64) for k, v in want.items()}
+    sum((want[k] * w[k]).sum() for k in want).backward()
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    got = om.transformer_forward(sd, x, layers, heads)
+    for k in want:
+        torch.testing.assert_close(got[k], want[k].detach(), rtol=1e-9, atol=1e-10, msg=k)
+    sum((got[k] * w[k]).sum() for k in got).backward()
+    for n, p in m.named_parameters():
+        ref_g = p.grad if p.grad is not None else torch.zeros_like(p)
+        got_g = sd[n].grad if sd[n].grad is not None else torch.zeros_like(p)
+        torch.testing.assert_close(got_g, ref_g, rtol=1e-7, atol=1e-10, msg=n)
